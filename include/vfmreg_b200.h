@@ -1,0 +1,183 @@
+/*
+ * vfmreg_b200.h -- C ABI of libvfmreg_b200.so: the B200 (sm_100a) implementation of the
+ * descriptor-match-and-solve hot path of vniclas/VFM-Registration.
+ *
+ * Plain pointers and sizes only (no torch / pybind types).  Every entry point names the
+ * reference interface it replaces (paths relative to the reference checkout); the
+ * reference-side bindings a maintainer would add are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - All functions return VFMREG_OK (0) or an error code; vfmreg_last_error() gives the text
+ *     (thread-local).  Nothing here falls back to a CPU path: without a CUDA device
+ *     vfmreg_create() fails with VFMREG_ERR_NOGPU.
+ *   - "device pointer" arguments are caller-owned, contiguous, row-major CUDA allocations on
+ *     the context's device; the library never frees or retains them past the call's stream
+ *     ordering.  Work is enqueued on the context's stream (vfmreg_set_stream) and is
+ *     asynchronous unless stated otherwise.
+ *   - Indices are int32 in CALLER ARRAY ORDER (the reference's indices are relative to
+ *     tsl::robin_map iteration order and never leave C++, VoxelHashMap.cpp:662-676).
+ */
+#ifndef VFMREG_B200_H
+#define VFMREG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFMREG_VERSION 100
+
+#if defined(__GNUC__)
+#define VFMREG_API __attribute__((visibility("default")))
+#else
+#define VFMREG_API
+#endif
+
+enum {
+  VFMREG_OK = 0,
+  VFMREG_ERR_ARG = 1,    /* bad shape / null pointer / unsupported size (reference: ValueError("Invalid shape"), mapping.py:72-73) */
+  VFMREG_ERR_CUDA = 2,   /* a CUDA call or kernel launch failed */
+  VFMREG_ERR_NOGPU = 3,  /* no usable sm_100 device: there is no CPU fallback */
+  VFMREG_ERR_ALLOC = 4
+};
+
+/* flags for vfmreg_match_nn / vfmreg_register */
+#define VFMREG_NORMALIZE   0x1u   /* fvec_renorm_L2 both sides first (VoxelHashMap.cpp:474,480) */
+#define VFMREG_MUTUAL      0x2u   /* also search b->a; register() keeps mutual pairs only (registration_node.py:530) */
+#define VFMREG_ALGO_MASK   0xF00u
+#define VFMREG_ALGO_AUTO   0x000u
+#define VFMREG_ALGO_SIMT   0x100u /* exact fp32 CUDA-core kernel */
+#define VFMREG_ALGO_TC     0x200u /* tcgen05 fp16 candidate search + exact fp32 re-rank (bit-identical results) */
+
+typedef struct vfmreg_ctx vfmreg_ctx;
+
+VFMREG_API int vfmreg_version(void);
+VFMREG_API const char* vfmreg_last_error(void);
+VFMREG_API int vfmreg_device_count(void);
+
+/* One context per (process, device): owns a stream-ordered scratch arena. */
+VFMREG_API int vfmreg_create(int device, vfmreg_ctx** ctx);
+VFMREG_API void vfmreg_destroy(vfmreg_ctx* ctx);
+VFMREG_API int vfmreg_set_stream(vfmreg_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = legacy default stream */
+VFMREG_API int vfmreg_sync(vfmreg_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+VFMREG_API int64_t vfmreg_kernel_launches(const vfmreg_ctx* ctx);
+/* device time in ms of the most recent launch of the named kernel group, measured with CUDA events on the
+ * context's stream when profiling is enabled: group 0 = match GEMM, 1 = ransac score, 2 = project/gather, 3 = vit gemm */
+VFMREG_API int vfmreg_enable_timing(vfmreg_ctx* ctx, int on);
+VFMREG_API int vfmreg_group_time_ms(vfmreg_ctx* ctx, int group, float* ms_total, int* launches);
+
+/* ---------------------------------------------------------------------------------------------
+ * a6/a7/a8  descriptor top-1 search.
+ * Replaces VoxelHashMap::GetVFMCorrespondences' faiss block (VoxelHashMap.cpp:469-496: float32
+ * renormalise, IndexFlatIP::add, search(k=1)) and, with VFMREG_MUTUAL, the two cKDTree queries of
+ * find_correspondences (registration_node.py:487-527).
+ *   a (n x d), b (m x d) float32 device; outputs device arrays:
+ *   idx01[n], sim01[n] = argmax_j <a_i,b_j> (lowest j on ties) and its value,
+ *   sec01[n] = runner-up value (may be NULL); idx10/sim10/sec10 [m] likewise for b->a (MUTUAL only, may be NULL).
+ * Values are the canonical fp32 inner products (DESIGN.md "Canonical arithmetic").
+ * ------------------------------------------------------------------------------------------- */
+VFMREG_API int vfmreg_match_nn(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64_t m, int32_t d, uint32_t flags,
+                    int32_t* idx01, float* sim01, float* sec01, int32_t* idx10, float* sim10, float* sec10);
+
+/* Cosine gate (keep sim >= min_cos, VoxelHashMap.cpp:501-511), mutual check (registration_node.py:530) and
+ * Lowe ratio test ((1-s1) < ratio^2 (1-s2)); pass NAN to disable min_cos / ratio.  Emits the kept
+ * (query, match) pairs in query order into corr[n][2] and their number into *count (both device). */
+VFMREG_API int vfmreg_filter_correspondences(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const float* sec01,
+                                  const int32_t* idx10, int64_t n, float min_cos, float ratio, int mutual,
+                                  int32_t* corr, int32_t* count);
+
+/* ---------------------------------------------------------------------------------------------
+ * a10  RANSAC on a correspondence list.
+ * Replaces o3d.pipelines.registration.registration_ransac_based_on_correspondence(src, tgt, corres, max_dist,
+ * TransformationEstimationPointToPoint(False), ransac_n=3, RANSACConvergenceCriteria(n_hyp, 1))
+ * (call site registration_node.py:319-327).
+ *   src_xyz (n x 3), tgt_xyz (m x 3): device, float32 (xyz_f64 = 0) or float64 (1)
+ *   corr (max_corr x 2) int32 device; count: device int32 holding the number of valid rows (<= max_corr)
+ *   sample_idx: device (n_hyp x 3) int32 indices into corr, or NULL -> drawn on the device from `seed`
+ *   thresh: inlier distance tau (the reference passes 10000); refit != 0: least-squares refit on the inliers
+ * Outputs (device; any of counts/sumq/mask may be NULL):
+ *   T[16] row-major 4x4 float64; counts[n_hyp] inlier count per hypothesis (-1 = degenerate sample);
+ *   sumq[n_hyp] = sum of rint(d^2 * 2^40 / tau^2) over inliers; mask[max_corr] inlier mask of the winner;
+ *   stats[4] int64 = {best hypothesis or -1, its inlier count, its sumq, number of correspondences}.
+ * ------------------------------------------------------------------------------------------- */
+VFMREG_API int vfmreg_ransac(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int xyz_f64, const int32_t* corr,
+                  const int32_t* count, int32_t max_corr, const int32_t* sample_idx, int32_t n_hyp, uint64_t seed,
+                  double thresh, int refit, double* T, int32_t* counts, int64_t* sumq, uint8_t* mask, int64_t* stats);
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole consumer path = RegistrationNode.ransac_registration(method='vfm') without ICP
+ * (registration_node.py:273-328): match -> gate -> RANSAC.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t flags;        /* VFMREG_NORMALIZE | VFMREG_MUTUAL | VFMREG_ALGO_* */
+  float min_cos;         /* NAN = no gate; the reference uses 0.8 (registration_node.py:418) */
+  float ratio;           /* NAN = no ratio test */
+  int32_t n_hyp;         /* the reference uses 50000 (registration_node.py:326) */
+  int32_t refit;
+  double inlier_thresh;  /* the reference uses 10000 (registration_node.py:323) */
+  uint64_t seed;
+} vfmreg_register_params;
+
+typedef struct {
+  double T[16];          /* row-major 4x4, maps source into target */
+  int64_t best_hyp;
+  int64_t n_inliers;
+  int64_t sumq;
+  int64_t n_corr;
+  double fitness;        /* n_inliers / n_corr */
+  double rmse;           /* over the inliers of the returned hypothesis */
+} vfmreg_register_result;
+
+/* Device-resident inputs (src_xyz n x 3, tgt_xyz m x 3, src_feats n x d, tgt_feats m x d, all float32).
+ * sample_idx: device (n_hyp x 3) or NULL.  corr_out (n x 2 int32) / mask_out (n uint8): device, optional.
+ * Blocks until the result struct (host memory) is filled. */
+VFMREG_API int vfmreg_register(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
+                    const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* params,
+                    const int32_t* sample_idx, int32_t* corr_out, uint8_t* mask_out, vfmreg_register_result* result);
+
+/* Same with HOST buffers: inputs are copied host->device and corr/mask device->host inside the call
+ * (the end-to-end path a NumPy caller such as the reference's registration_node.py exercises). */
+VFMREG_API int vfmreg_register_host(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
+                         const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* params,
+                         const int32_t* sample_idx, int32_t* corr_out, uint8_t* mask_out,
+                         vfmreg_register_result* result);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3/a4/a5  point -> pixel projection + feature gather + first-camera-wins scatter.
+ * Replaces project_pcl_to_image (dataloader/nclt.py:311-366, dataloader/oxford_robotcar.py:330-363) and
+ * create_descriptors' gather/dedup/scatter (prepare_scenes.py:57-104) in one pass, sampling the ViT token grid
+ * directly instead of materialising the full-resolution map of image_features.py:104-108.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  double P[12];          /* 3x4 row-major: pixel_h = P * [x y z 1]^T in FULL-resolution pixels (K * T_cam_from_lidar) */
+  int32_t img_h, img_w;  /* image size (after subsampling) the black-pixel test and the feature map refer to */
+  int32_t crop_y0, crop_x0, crop_h, crop_w; /* window in subsampled pixels; image/feature origin = window origin */
+  int32_t grid_h, grid_w;/* token grid of this camera */
+  double subsample;      /* pixel = P-projection / subsample, then truncated toward zero (nclt.py:334-343) */
+  int32_t z_inclusive;   /* 0: keep z > 0 (nclt.py:337); 1: keep z >= 0 (oxford_robotcar.py:344) */
+  int32_t float_bounds;  /* 1: Oxford order -- test 0 <= u <= W, 0 <= v <= H on the un-truncated coordinate, then truncate
+                            (oxford_robotcar.py:356-362; u == W / v == H would index out of range in the reference and is
+                            dropped here); 0: NCLT order -- truncate, then test the crop window (nclt.py:342-347) */
+  int32_t black_mode;    /* 0: ignore the image; 1: a black pixel hides the point from this camera (nclt.py:354-359);
+                            2: a black pixel claims the point with a zero descriptor (prepare_scenes.py:58-62 on Oxford) */
+  int32_t rot90;         /* 1: (u, v) live in the np.rot90(k=1) frame of the stored image / token grid
+                            (prepare_scenes.py:73-74,80-81); img_h/img_w/crop then describe the rotated frame */
+} vfmreg_camera;
+
+/* points (n x 3) f32 device; cams: HOST array of n_cam descriptors; tokens: device f32, camera c's grid at
+ * tokens + token_offsets[c] (HOST int64 array, in floats), layout (grid_h, grid_w, d);
+ * images: device uint8 HWC RGB per camera at images + image_offsets[c] (HOST int64, bytes), or NULL to skip
+ * the black-pixel test.  mode 0: bilinear sample of the token grid == nearest pixel of the align_corners=False
+ * upsampled map (image_features.py:104-108 then prepare_scenes.py:85-91).
+ * Outputs (device): desc (n x d) f32, zeros for unseen points; cam_of_point[n] int32 (-1 unseen), uv[n][2] int32 (optional). */
+VFMREG_API int vfmreg_project_gather(vfmreg_ctx* ctx, const float* points, int64_t n, const vfmreg_camera* cams, int32_t n_cam,
+                          const float* tokens, const int64_t* token_offsets, const uint8_t* images,
+                          const int64_t* image_offsets, int32_t d, float* desc, int32_t* cam_of_point, int32_t* uv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFMREG_B200_H */

@@ -48,15 +48,17 @@ ORC_API int orc_simd(void) {
 }
 
 /* ------------------------------------------------------------------------------------
- * Row L2 renormalisation, canonical order: 32 strided partial sums (partial l takes
- * elements l, l+32, ... by fused multiply-add), then an xor-butterfly 16,8,4,2,1.
+ * Row L2 renormalisation, canonical order: 32 partial sums (partial l takes the float4
+ * groups 4l..4l+3, 128+4l.., ... element by element with fused multiply-add = one warp lane
+ * issuing 128-bit loads), then an xor-butterfly 16,8,4,2,1.
  * inv = 1/sqrt(s) in float32, rows with s == 0 are left untouched (faiss: `if (nr > 0)`).
  * ---------------------------------------------------------------------------------- */
 static float orc_row_sumsq(const float* x, int d) {
     float part[32], tmp[32];
     for (int l = 0; l < 32; ++l) {
         float acc = 0.0f;
-        for (int k = l; k < d; k += 32) acc = fmaf(x[k], x[k], acc);
+        for (int base = 4 * l; base < d; base += 128)
+            for (int c = 0; c < 4 && base + c < d; ++c) acc = fmaf(x[base + c], x[base + c], acc);
         part[l] = acc;
     }
     for (int off = 16; off >= 1; off >>= 1) {

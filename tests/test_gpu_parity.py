@@ -1,0 +1,164 @@
+"""GPU parity (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs.  Bit-exact against the canonical-order C restatement (indices, similarities, inlier counts,
+masks, transforms); against the float64 NumPy oracle on unambiguous queries and within 1e-4 Frobenius on T."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import cref, match, ransac  # noqa: E402
+from vfm_registration_b200 import synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def vfm():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import vfm_registration_b200 as v
+    v.get_context(0)  # raises if libvfmreg_b200.so is missing: no fallback
+    return v
+
+
+def _cmp_match(g, c, o, key, n_expected_clear=0.9):
+    idx = g["idx" + key].cpu().numpy()
+    sim = g["sim" + key].cpu().numpy()
+    sec = g["sec" + key].cpu().numpy()
+    assert np.array_equal(idx, c["idx" + key]), f"idx{key} differs from the C oracle at {np.nonzero(idx != c['idx' + key])[0][:5]}"
+    assert np.array_equal(sim, c["sim" + key]) and np.array_equal(sec, c["sec" + key])
+    clear = (o["sim" + key] - o["sec" + key]) > 1e-5
+    assert clear.mean() >= n_expected_clear
+    assert np.array_equal(idx[clear], o["idx" + key][clear])
+    assert np.abs(sim - o["sim" + key]).max() < 1e-5  # fp32 accumulation tolerance vs float64
+
+
+@pytest.mark.parametrize("n,m,d,algo", [(1000, 3000, 384, "simt"), (257, 1031, 100, "simt"), (64, 129, 7, "simt"),
+                                        (1, 5, 384, "simt"), (5, 1, 16, "simt")])
+def test_match_nn_vs_oracles(vfm, n, m, d, algo):
+    rng = np.random.default_rng(n * 7 + m)
+    a = rng.standard_normal((n, d)).astype(np.float32)
+    b = rng.standard_normal((m, d)).astype(np.float32)
+    if n > 10:
+        a[3] = 0
+        b[min(m - 1, 9)] = b[2]  # duplicate map row -> exact tie
+    g = vfm.match_nn(a, b, mutual=True, algo=algo)
+    gd = {k: getattr(g, k) for k in ("idx01", "sim01", "sec01", "idx10", "sim10", "sec10")}
+    c = cref.match_nn(a, b, mutual=True)
+    o = match.match_nn(a, b, mutual=True)
+    _cmp_match(gd, c, o, "01", 0.9 if m > 1 else 0.0)
+    _cmp_match(gd, c, o, "10", 0.9 if n > 1 else 0.0)
+
+
+def test_match_no_normalize(vfm):
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((200, 64)).astype(np.float32) * 3
+    b = rng.standard_normal((300, 64)).astype(np.float32) * 0.5
+    g = vfm.match_nn(a, b, normalize=False)
+    c = cref.match_nn(a, b, normalize=False)
+    assert np.array_equal(g.idx01.cpu().numpy(), c["idx01"]) and np.array_equal(g.sim01.cpu().numpy(), c["sim01"])
+
+
+def test_filter_correspondences(vfm):
+    s = synth.make_pair(21, 4000, 1500, 128)
+    g = vfm.match_nn(s["scan_feat"], s["map_feat"], mutual=True)
+    c = cref.match_nn(s["scan_feat"], s["map_feat"], mutual=True)
+    for kw in (dict(min_cos=0.8), dict(mutual=True), dict(min_cos=0.5, mutual=True), dict(ratio=0.9), dict(),
+               dict(min_cos=0.8, ratio=0.8, mutual=True), dict(min_cos=1.1)):
+        corr = vfm.filter_correspondences(g, **kw).cpu().numpy()
+        want = match.filter_correspondences(c["idx01"], c["sim01"], c["sec01"], c["idx10"], **kw)
+        assert np.array_equal(corr, want), kw
+    inl = np.nonzero(s["perm"] >= 0)[0]
+    corr = vfm.filter_correspondences(g, min_cos=0.8).cpu().numpy()
+    assert np.array_equal(corr[:, 0], inl) and np.array_equal(corr[:, 1], s["perm"][inl])
+
+
+def _corr_for(s, k, n_good, rng):
+    good = np.nonzero(s["perm"] >= 0)[0]
+    bad = np.nonzero(s["perm"] < 0)[0]
+    q = np.sort(np.concatenate([good[:n_good], bad[: k - n_good]]))
+    j = np.where(s["perm"][q] >= 0, s["perm"][q], rng.integers(0, len(s["map_xyz"]), len(q)))
+    return np.stack([q, j], 1).astype(np.int32)
+
+
+@pytest.mark.parametrize("thresh,refit,f64", [(1.0, False, False), (1e4, False, False), (1.0, True, True), (0.5, False, True)])
+def test_ransac_bit_exact_vs_c_oracle(vfm, thresh, refit, f64):
+    s = synth.make_pair(31, 6000, 2500, 16)
+    rng = np.random.default_rng(9)
+    corr = _corr_for(s, 1500, 400, rng)
+    si = ransac.sample_indices(3, 8192, len(corr))
+    si[5] = [7, 7, 9]      # repeated sample -> degenerate hypothesis
+    si[6] = [1, 1, 1]
+    src = s["scan_xyz"].astype(np.float64) if f64 else s["scan_xyz"]
+    tgt = s["map_xyz"].astype(np.float64) if f64 else s["map_xyz"]
+    g = vfm.ransac_kabsch(src, tgt, corr, sample_idx=si, thresh=thresh, refit=refit)
+    c = cref.ransac(s["scan_xyz"], s["map_xyz"], corr, si, thresh, refit=refit)
+    assert np.array_equal(g.counts.cpu().numpy(), c["counts"])
+    assert np.array_equal(g.sumq.cpu().numpy(), c["sumq"])
+    assert g.counts[5].item() == -1 and g.counts[6].item() == -1
+    assert g.best == c["best"] and g.n_inliers == c["n_inliers"]
+    assert np.array_equal(g.mask.cpu().numpy(), c["mask"])
+    if refit:
+        assert np.linalg.norm(g.T - c["T"]) < 1e-9   # refit sums are reduced in a different order on the device
+    else:
+        assert np.array_equal(g.T, c["T"])           # bit-exact 4x4
+    o = ransac.ransac(s["scan_xyz"], s["map_xyz"], corr, si, thresh, refit=refit)
+    assert np.linalg.norm(g.T - o["T"]) < 1e-4 and g.best == o["best"] and np.array_equal(g.mask.cpu().numpy(), o["mask"])
+    if thresh <= 1.0:
+        rte, rre = synth.pose_errors(g.T, s["T_gt"])
+        assert rte < 0.5 and rre < 1.0
+
+
+def test_ransac_device_rng_and_small_k(vfm):
+    s = synth.make_pair(33, 2000, 900, 16)
+    rng = np.random.default_rng(1)
+    corr = _corr_for(s, 500, 200, rng)
+    g = vfm.ransac_kabsch(s["scan_xyz"], s["map_xyz"], corr, n_hyp=3000, seed=123, thresh=1.0)
+    c = cref.ransac(s["scan_xyz"], s["map_xyz"], corr, None, 1.0, seed=123, n_hyp=3000)
+    assert g.best == c["best"] and np.array_equal(g.T, c["T"]) and np.array_equal(g.counts.cpu().numpy(), c["counts"])
+    for k in (0, 1, 2):
+        g = vfm.ransac_kabsch(s["scan_xyz"], s["map_xyz"], corr[:k], n_hyp=64, thresh=1.0)
+        assert g.best == -1 and np.array_equal(g.T, np.eye(4)) and g.fitness == 0.0
+
+
+@pytest.mark.parametrize("host", [True, False])
+@pytest.mark.parametrize("kw", [dict(min_cos=0.8, inlier_thresh=1.0), dict(min_cos=0.8), dict(min_cos=None, mutual=True, inlier_thresh=1.0),
+                                dict(min_cos=0.3, ratio=0.9, mutual=True, inlier_thresh=1.0, refit=True)])
+def test_register_end_to_end(vfm, host, kw):
+    """Config-1 style pair (smaller): whole path through vfmreg_register[_host] vs the oracle chain."""
+    s = synth.make_pair(1, 4096, 2048, 384)
+    h = 1024
+    args = (s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"])
+    if not host:
+        args = tuple(torch.from_numpy(x).cuda() for x in args)
+    r = vfm.register(*args, ransac_iters=h, seed=42, **kw)
+    m = cref.match_nn(s["scan_feat"], s["map_feat"], mutual=True)
+    corr = match.filter_correspondences(m["idx01"], m["sim01"], m["sec01"], m["idx10"], min_cos=kw.get("min_cos"),
+                                        mutual=kw.get("mutual", False), ratio=kw.get("ratio"))
+    assert np.array_equal(r.corr, corr)
+    c = cref.ransac(s["scan_xyz"], s["map_xyz"], corr, None, kw.get("inlier_thresh", 1e4), refit=kw.get("refit", False),
+                    seed=42, n_hyp=h)
+    assert r.best_hyp == c["best"] and np.array_equal(r.inlier_mask, c["mask"]) and r.n_inliers == c["n_inliers"]
+    assert np.linalg.norm(r.T - c["T"]) < (1e-9 if kw.get("refit") else 1e-300)
+    assert abs(r.fitness - c["fitness"]) < 1e-12 and abs(r.rmse - c["rmse"]) < 1e-9
+    if kw.get("inlier_thresh", 1e4) <= 1.0:
+        rte, rre = synth.pose_errors(r.T, s["T_gt"])
+        assert rte < 1.0 and rre < 5.0   # recall@(1 m, 5 deg)
+
+
+def test_register_sample_idx_and_errors(vfm):
+    s = synth.make_pair(2, 1500, 600, 64)
+    m = cref.match_nn(s["scan_feat"], s["map_feat"])
+    corr = match.filter_correspondences(m["idx01"], m["sim01"], min_cos=0.8)
+    si = np.random.default_rng(4).integers(0, len(corr), (2048, 3)).astype(np.int32)
+    r = vfm.register(s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"], sample_idx=si, inlier_thresh=1.0)
+    c = cref.ransac(s["scan_xyz"], s["map_xyz"], corr, si, 1.0)
+    assert r.best_hyp == c["best"] and np.array_equal(r.T, c["T"])
+    # all rejected -> K = 0 -> identity, fitness 0 (never UB on empty correspondences)
+    r0 = vfm.register(s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"], min_cos=1.1, ransac_iters=128)
+    assert np.array_equal(r0.T, np.eye(4)) and r0.fitness == 0.0 and len(r0.corr) == 0 and r0.best_hyp == -1
+    with pytest.raises(ValueError, match="Invalid shape"):
+        vfm.register(s["scan_xyz"][:, :2], s["map_xyz"], s["scan_feat"], s["map_feat"])
+    with pytest.raises(ValueError, match="Invalid shape"):
+        vfm.register(s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"][:, :32])
+    with pytest.raises(vfm.VfmRegError):
+        vfm.register(s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"], ransac_iters=0)

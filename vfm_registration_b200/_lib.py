@@ -1,0 +1,96 @@
+"""ctypes binding of libvfmreg_b200.so (include/vfmreg_b200.h).
+
+The shared library is the product; this module only loads it and declares the argument types.  It fails loudly
+when the library is missing or cannot be loaded -- there is no Python / CPU fallback for any of its entry points."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvfmreg_b200.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_NOGPU, ERR_ALLOC = 0, 1, 2, 3, 4
+NORMALIZE, MUTUAL = 0x1, 0x2
+ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0x000, 0x100, 0x200
+
+
+class VfmRegError(RuntimeError):
+    pass
+
+
+class RegisterParams(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("min_cos", C.c_float), ("ratio", C.c_float), ("n_hyp", C.c_int32),
+                ("refit", C.c_int32), ("inlier_thresh", C.c_double), ("seed", C.c_uint64)]
+
+
+class RegisterResult(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("best_hyp", C.c_int64), ("n_inliers", C.c_int64), ("sumq", C.c_int64),
+                ("n_corr", C.c_int64), ("fitness", C.c_double), ("rmse", C.c_double)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("P", C.c_double * 12), ("img_h", C.c_int32), ("img_w", C.c_int32), ("crop_y0", C.c_int32),
+                ("crop_x0", C.c_int32), ("crop_h", C.c_int32), ("crop_w", C.c_int32), ("grid_h", C.c_int32),
+                ("grid_w", C.c_int32), ("subsample", C.c_double), ("z_inclusive", C.c_int32),
+                ("float_bounds", C.c_int32), ("black_mode", C.c_int32), ("rot90", C.c_int32)]
+
+
+_P = C.c_void_p
+_SIGS = {
+    "vfmreg_version": (C.c_int, []),
+    "vfmreg_last_error": (C.c_char_p, []),
+    "vfmreg_device_count": (C.c_int, []),
+    "vfmreg_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "vfmreg_destroy": (None, [_P]),
+    "vfmreg_set_stream": (C.c_int, [_P, _P]),
+    "vfmreg_sync": (C.c_int, [_P]),
+    "vfmreg_kernel_launches": (C.c_int64, [_P]),
+    "vfmreg_enable_timing": (C.c_int, [_P, C.c_int]),
+    "vfmreg_group_time_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "vfmreg_match_nn": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
+    "vfmreg_filter_correspondences": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_int, _P, _P]),
+    "vfmreg_ransac": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int32, _P, C.c_int32, C.c_uint64, C.c_double, C.c_int,
+                                _P, _P, _P, _P, _P]),
+    "vfmreg_register": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(RegisterParams), _P, _P,
+                                  _P, C.POINTER(RegisterResult)]),
+    "vfmreg_register_host": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(RegisterParams), _P,
+                                       _P, _P, C.POINTER(RegisterResult)]),
+    "vfmreg_project_gather": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Camera), C.c_int32, _P, C.POINTER(C.c_int64), _P,
+                                        C.POINTER(C.c_int64), C.c_int32, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def declared_symbols():
+    return sorted(_SIGS)
+
+
+def load():
+    """Load libvfmreg_b200.so; raises VfmRegError (never falls back) when it is absent or broken."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VfmRegError(f"{LIB_PATH} is missing: build it with `python -m vfm_registration_b200.build` "
+                          "(nvcc, sm_100a). There is no CPU fallback.")
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise VfmRegError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in _SIGS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise VfmRegError(f"{LIB_PATH} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != OK:
+        msg = load().vfmreg_last_error().decode(errors="replace")
+        raise VfmRegError(f"{what or 'libvfmreg_b200'} failed (code {rc}): {msg}")

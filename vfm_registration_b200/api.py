@@ -1,0 +1,295 @@
+"""Python host of libvfmreg_b200.so: the call surface BASELINE.json names --
+``extract_features()`` / ``register(source_pcd, target_pcd, src_feats, tgt_feats)`` -- plus the low-level ops.
+
+PyTorch is used for device memory and streams only; every computation happens in the hand-written sm_100a
+kernels behind the C ABI (include/vfmreg_b200.h).  NumPy inputs go through the host-buffer entry point
+(``vfmreg_register_host``: host->device copies inside the call); CUDA tensors are borrowed zero-copy.
+
+Reference call sites these functions replace (paths relative to the reference checkout):
+  register             RegistrationNode.ransac_registration(method='vfm', run_icp=False)
+                       src/vfm-reg/src/registration_node.py:273-328 (+ compute_vfm_correspondences :396-425)
+  match_nn             VoxelHashMap::GetVFMCorrespondences' faiss block, VoxelHashMap.cpp:469-511
+  ransac_kabsch        o3d registration_ransac_based_on_correspondence, registration_node.py:319-327
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import VfmRegError
+
+__all__ = ["Context", "get_context", "match_nn", "filter_correspondences", "ransac_kabsch", "register", "RegResult",
+           "MatchResult", "RansacResult", "VfmRegError"]
+
+_ALGO = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}
+
+
+class Context:
+    """One per (process, device).  Owns the library context (scratch arena, stream binding)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.vfmreg_create(int(device), C.byref(h)), "vfmreg_create")
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vfmreg_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bind_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.vfmreg_set_stream(self.handle, C.c_void_p(s)), "vfmreg_set_stream")
+
+    def sync(self):
+        _lib.check(self.lib.vfmreg_sync(self.handle), "vfmreg_sync")
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.vfmreg_kernel_launches(self.handle))
+
+    def enable_timing(self, on: bool = True):
+        _lib.check(self.lib.vfmreg_enable_timing(self.handle, int(on)))
+
+    def group_time_ms(self, group: int):
+        ms, n = C.c_float(), C.c_int()
+        _lib.check(self.lib.vfmreg_group_time_ms(self.handle, group, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+
+_contexts: dict = {}
+
+
+def get_context(device: Optional[int] = None) -> Context:
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _dev_f32(x, device, name, cols=None) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{name}: expected ndarray or Tensor, got {type(x)}")
+    if x.dim() != 2 or (cols is not None and x.shape[1] != cols):
+        raise ValueError(f"Invalid shape for {name}: {tuple(x.shape)}")  # reference: mapping.py:72-73
+    return x.to(device=device, dtype=torch.float32).contiguous()
+
+
+@dataclass
+class MatchResult:
+    idx01: torch.Tensor
+    sim01: torch.Tensor
+    sec01: torch.Tensor
+    idx10: Optional[torch.Tensor] = None
+    sim10: Optional[torch.Tensor] = None
+    sec10: Optional[torch.Tensor] = None
+
+
+def match_nn(a, b, *, normalize: bool = True, mutual: bool = False, algo: str = "auto", device=None) -> MatchResult:
+    """Inner-product top-1 (+ runner-up value) of every row of ``a`` (N, D) in ``b`` (M, D); with ``mutual`` also b -> a.
+    For L2-normalised rows argmax-IP == argmin-L2, which covers the reference's three matchers."""
+    ctx = get_context(device)
+    dev = torch.device("cuda", ctx.device)
+    a = _dev_f32(a, dev, "a")
+    b = _dev_f32(b, dev, "b", cols=a.shape[1])
+    n, d = a.shape
+    m = b.shape[0]
+    if n == 0 or m == 0:
+        raise ValueError(f"Invalid shape: empty descriptor set (n={n}, m={m})")
+    res = MatchResult(torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float32, device=dev),
+                      torch.empty(n, dtype=torch.float32, device=dev))
+    if mutual:
+        res.idx10 = torch.empty(m, dtype=torch.int32, device=dev)
+        res.sim10 = torch.empty(m, dtype=torch.float32, device=dev)
+        res.sec10 = torch.empty(m, dtype=torch.float32, device=dev)
+    flags = (_lib.NORMALIZE if normalize else 0) | (_lib.MUTUAL if mutual else 0) | _ALGO[algo]
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_match_nn(ctx.handle, _ptr(a), n, _ptr(b), m, d, flags, _ptr(res.idx01), _ptr(res.sim01),
+                                      _ptr(res.sec01), _ptr(res.idx10), _ptr(res.sim10), _ptr(res.sec10)), "vfmreg_match_nn")
+    return res
+
+
+def filter_correspondences(match: MatchResult, *, min_cos: Optional[float] = None, mutual: bool = False,
+                           ratio: Optional[float] = None, device=None) -> torch.Tensor:
+    """(K, 2) int32 correspondences (query, match) in query order: cosine gate / mutual / ratio (see the header)."""
+    ctx = get_context(device)
+    n = match.idx01.shape[0]
+    dev = match.idx01.device
+    corr = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_filter_correspondences(
+        ctx.handle, _ptr(match.idx01), _ptr(match.sim01), _ptr(match.sec01), _ptr(match.idx10 if mutual else None), n,
+        float("nan") if min_cos is None else float(min_cos), float("nan") if ratio is None else float(ratio), int(mutual),
+        _ptr(corr), _ptr(count)), "vfmreg_filter_correspondences")
+    return corr[: int(count.item())]
+
+
+@dataclass
+class RansacResult:
+    T: np.ndarray            # (4, 4) float64
+    best: int
+    n_inliers: int
+    n_corr: int
+    fitness: float
+    rmse: float
+    counts: torch.Tensor     # (H,) int32, -1 for degenerate samples
+    sumq: torch.Tensor       # (H,) int64
+    mask: torch.Tensor       # (K,) bool
+
+
+def ransac_kabsch(src_xyz, tgt_xyz, corr, *, sample_idx=None, n_hyp: Optional[int] = None, thresh: float = 1e4,
+                  seed: int = 42, refit: bool = False, device=None) -> RansacResult:
+    """Batched 3-point-Kabsch RANSAC over a correspondence list (float64 on the device)."""
+    ctx = get_context(device)
+    dev = torch.device("cuda", ctx.device)
+
+    def xyz(x, name):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if x.dim() != 2 or x.shape[1] != 3:
+            raise ValueError(f"Invalid shape for {name}: {tuple(x.shape)}")
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.to(torch.float64)
+        return x.to(dev).contiguous()
+
+    src, tgt = xyz(src_xyz, "src_xyz"), xyz(tgt_xyz, "tgt_xyz")
+    if src.dtype != tgt.dtype:
+        src, tgt = src.to(torch.float64), tgt.to(torch.float64)
+    if isinstance(corr, np.ndarray):
+        corr = torch.from_numpy(np.ascontiguousarray(corr.reshape(-1, 2), dtype=np.int32))
+    corr = corr.to(device=dev, dtype=torch.int32).contiguous()
+    k = corr.shape[0]
+    if sample_idx is not None:
+        if isinstance(sample_idx, np.ndarray):
+            sample_idx = torch.from_numpy(np.ascontiguousarray(sample_idx, dtype=np.int32))
+        sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
+        n_hyp = sample_idx.shape[0]
+    if not n_hyp or n_hyp <= 0:
+        raise ValueError("ransac_kabsch: need sample_idx or a positive n_hyp")
+    count = torch.full((1,), k, dtype=torch.int32, device=dev)
+    t = torch.empty(16, dtype=torch.float64, device=dev)
+    counts = torch.empty(n_hyp, dtype=torch.int32, device=dev)
+    sumq = torch.empty(n_hyp, dtype=torch.int64, device=dev)
+    mask = torch.zeros(max(k, 1), dtype=torch.uint8, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    corr_arg = corr if k > 0 else torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_ransac(ctx.handle, _ptr(src), _ptr(tgt), int(src.dtype == torch.float64), _ptr(corr_arg),
+                                    _ptr(count), k, _ptr(sample_idx), n_hyp, seed & 0xFFFFFFFFFFFFFFFF, float(thresh),
+                                    int(refit), _ptr(t), _ptr(counts), _ptr(sumq), _ptr(mask), _ptr(stats)), "vfmreg_ransac")
+    st = stats.cpu().numpy()
+    n_in = int(st[1])
+    rmse = math.sqrt(float(st[2]) / 2.0 ** 40 * thresh * thresh / n_in) if n_in else 0.0
+    return RansacResult(T=t.cpu().numpy().reshape(4, 4), best=int(st[0]), n_inliers=n_in, n_corr=int(st[3]),
+                        fitness=(n_in / k if k else 0.0), rmse=rmse, counts=counts, sumq=sumq, mask=mask[:k].bool())
+
+
+@dataclass
+class RegResult:
+    T: np.ndarray            # (4, 4) float64, maps source into target
+    corr: np.ndarray         # (K, 2) int32 (source index, target index)
+    inlier_mask: np.ndarray  # (K,) bool, inliers of the returned hypothesis
+    fitness: float
+    rmse: float
+    best_hyp: int
+    n_inliers: int
+
+
+def _params(normalize, min_cos, mutual, ratio, ransac_iters, inlier_thresh, seed, refit, algo):
+    p = _lib.RegisterParams()
+    p.flags = (_lib.NORMALIZE if normalize else 0) | (_lib.MUTUAL if mutual else 0) | _ALGO[algo]
+    p.min_cos = float("nan") if min_cos is None else float(min_cos)
+    p.ratio = float("nan") if ratio is None else float(ratio)
+    p.n_hyp = int(ransac_iters)
+    p.refit = int(refit)
+    p.inlier_thresh = float(inlier_thresh)
+    p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return p
+
+
+def register(source_pcd, target_pcd, src_feats, tgt_feats, *, normalize: bool = True, min_cos: Optional[float] = 0.8,
+             mutual: bool = False, ratio: Optional[float] = None, ransac_iters: int = 50000, inlier_thresh: float = 1e4,
+             sample_idx=None, seed: int = 42, refit: bool = False, algo: str = "auto", device=None) -> RegResult:
+    """Descriptor match -> gate -> batched RANSAC, returning the 4x4 transform that maps ``source_pcd`` into
+    ``target_pcd``.  Defaults are the reference's literals (cosine gate 0.8, 50000 iterations, tau = 10000,
+    registration_node.py:323-326,418).  K < 3 correspondences -> identity transform, fitness 0.
+
+    NumPy inputs run through ``vfmreg_register_host`` (copies inside the call); CUDA tensors are used in place."""
+    ctx = get_context(device)
+    lib = ctx.lib
+    on_host = all(isinstance(x, np.ndarray) or (isinstance(x, torch.Tensor) and not x.is_cuda)
+                  for x in (source_pcd, target_pcd, src_feats, tgt_feats))
+    p = _params(normalize, min_cos, mutual, ratio, ransac_iters, inlier_thresh, seed, refit, algo)
+    res = _lib.RegisterResult()
+    if on_host:
+        def h(x, name, cols=None):
+            x = x.numpy() if isinstance(x, torch.Tensor) else x
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            if x.ndim != 2 or (cols is not None and x.shape[1] != cols):
+                raise ValueError(f"Invalid shape for {name}: {x.shape}")
+            return x
+        sx, tx = h(source_pcd, "source_pcd", 3), h(target_pcd, "target_pcd", 3)
+        sf = h(src_feats, "src_feats")
+        tf = h(tgt_feats, "tgt_feats", sf.shape[1])
+        n, m, d = sx.shape[0], tx.shape[0], sf.shape[1]
+        if sf.shape[0] != n or tf.shape[0] != m:
+            raise ValueError(f"Invalid shape: {n} points vs {sf.shape[0]} descriptors / {m} vs {tf.shape[0]}")
+        si = None
+        if sample_idx is not None:
+            si = np.ascontiguousarray(sample_idx, dtype=np.int32)
+            p.n_hyp = si.shape[0]
+        corr = np.empty((n, 2), dtype=np.int32)
+        mask = np.empty(n, dtype=np.uint8)
+        ctx.bind_stream()
+        _lib.check(lib.vfmreg_register_host(ctx.handle, sx.ctypes.data, tx.ctypes.data, sf.ctypes.data, tf.ctypes.data, n, m,
+                                           d, C.byref(p), si.ctypes.data if si is not None else None, corr.ctypes.data,
+                                           mask.ctypes.data, C.byref(res)), "vfmreg_register_host")
+        k = int(res.n_corr)
+        corr_np, mask_np = corr[:k].copy(), mask[:k].astype(bool)
+    else:
+        dev = torch.device("cuda", ctx.device)
+        sx, tx = _dev_f32(source_pcd, dev, "source_pcd", 3), _dev_f32(target_pcd, dev, "target_pcd", 3)
+        sf = _dev_f32(src_feats, dev, "src_feats")
+        tf = _dev_f32(tgt_feats, dev, "tgt_feats", sf.shape[1])
+        n, m, d = sx.shape[0], tx.shape[0], sf.shape[1]
+        if sf.shape[0] != n or tf.shape[0] != m:
+            raise ValueError(f"Invalid shape: {n} points vs {sf.shape[0]} descriptors / {m} vs {tf.shape[0]}")
+        si = None
+        if sample_idx is not None:
+            if isinstance(sample_idx, np.ndarray):
+                sample_idx = torch.from_numpy(np.ascontiguousarray(sample_idx, dtype=np.int32))
+            si = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
+            p.n_hyp = si.shape[0]
+        corr = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        mask = torch.empty(n, dtype=torch.uint8, device=dev)
+        ctx.bind_stream()
+        _lib.check(lib.vfmreg_register(ctx.handle, _ptr(sx), _ptr(tx), _ptr(sf), _ptr(tf), n, m, d, C.byref(p), _ptr(si),
+                                      _ptr(corr), _ptr(mask), C.byref(res)), "vfmreg_register")
+        k = int(res.n_corr)
+        corr_np, mask_np = corr[:k].cpu().numpy(), mask[:k].cpu().numpy().astype(bool)
+    return RegResult(T=np.array(res.T, dtype=np.float64).reshape(4, 4), corr=corr_np, inlier_mask=mask_np,
+                     fitness=float(res.fitness), rmse=float(res.rmse), best_hyp=int(res.best_hyp),
+                     n_inliers=int(res.n_inliers))

@@ -1,0 +1,114 @@
+// Shared internals of libvfmreg_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vfmreg_b200.h"
+
+namespace vfm {
+
+void set_error(const char* fmt, ...);
+
+#define VFM_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      vfm::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return VFMREG_ERR_CUDA;                                                               \
+    }                                                                                       \
+  } while (0)
+
+#define VFM_CHECK_ARG(cond, ...)   \
+  do {                             \
+    if (!(cond)) {                 \
+      vfm::set_error(__VA_ARGS__); \
+      return VFMREG_ERR_ARG;       \
+    }                              \
+  } while (0)
+
+#define VFM_TRY(expr)                 \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != VFMREG_OK) return rc__; \
+  } while (0)
+
+enum { GROUP_MATCH = 0, GROUP_RANSAC = 1, GROUP_PROJECT = 2, GROUP_VIT = 3, NUM_GROUPS = 4 };
+
+// Bump allocator over one cudaMalloc'd slab.  Scratch is carved per API call and reused by the next call on the
+// same stream (stream order makes that safe); growing the slab synchronises the stream first.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+};
+
+}  // namespace vfm
+
+struct vfmreg_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  vfm::Arena arena;
+  int64_t launches = 0;
+  // optional per-group device timing (CUDA events on the context's stream)
+  int timing = 0;
+  cudaEvent_t ev0[vfm::NUM_GROUPS] = {}, ev1[vfm::NUM_GROUPS] = {};
+  float group_ms[vfm::NUM_GROUPS] = {};
+  int group_launches[vfm::NUM_GROUPS] = {};
+  int group_pending[vfm::NUM_GROUPS] = {};
+  // pinned staging for small results
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  // persistent device buffers for register_host (inputs), grown on demand
+  char* hbuf = nullptr;
+  size_t hbuf_cap = 0;
+};
+
+namespace vfm {
+
+int arena_reserve(vfmreg_ctx* ctx, size_t bytes);  // make sure the slab holds `bytes` in total (call before carving)
+inline void arena_reset(vfmreg_ctx* ctx) { ctx->arena.off = 0; }
+template <typename T>
+inline T* arena_take(vfmreg_ctx* ctx, size_t count) {
+  size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+  if (ctx->arena.off + bytes > ctx->arena.cap) return nullptr;
+  T* p = reinterpret_cast<T*>(ctx->arena.base + ctx->arena.off);
+  ctx->arena.off += bytes;
+  return p;
+}
+inline size_t arena_bytes(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
+
+void group_begin(vfmreg_ctx* ctx, int group);
+void group_end(vfmreg_ctx* ctx, int group, int n_launches);
+
+inline int launch_check(vfmreg_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("kernel launch %s failed: %s", what, cudaGetErrorString(e));
+    return VFMREG_ERR_CUDA;
+  }
+  ctx->launches += 1;
+  return VFMREG_OK;
+}
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- stage entry points (each file implements its own) -------------------------------------------------
+// normalize.cu: rows of x (n x d) -> y (n x dp) zero padded, L2-renormalised when `normalize`
+int normalize_rows(vfmreg_ctx* ctx, const float* x, int64_t n, int d, int dp, int normalize, float* y);
+// match_simt.cu: exact fp32 top-2 of a (n x dp) against b (m x dp)
+int match_simt(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64_t m, int dp, int32_t* idx,
+               float* best, float* sec);
+size_t match_simt_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m);
+// filter.cu
+int filter_corr(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const float* sec01, const int32_t* idx10,
+                int64_t n, float min_cos, float ratio, int mutual, int32_t* corr, int32_t* count);
+// ransac.cu
+size_t ransac_scratch(int32_t max_corr, int32_t n_hyp);
+int ransac_solve(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int xyz_f64, const int32_t* corr,
+                 const int32_t* count, int32_t max_corr, const int32_t* sample_idx, int32_t n_hyp, uint64_t seed,
+                 double thresh, int refit, double* T, int32_t* counts, int64_t* sumq, uint8_t* mask, int64_t* stats);
+
+}  // namespace vfm
