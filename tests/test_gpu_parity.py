@@ -32,8 +32,9 @@ def _cmp_match(g, c, o, key, n_expected_clear=0.9):
     assert np.abs(sim - o["sim" + key]).max() < 1e-5  # fp32 accumulation tolerance vs float64
 
 
-@pytest.mark.parametrize("n,m,d,algo", [(1000, 3000, 384, "simt"), (257, 1031, 100, "simt"), (64, 129, 7, "simt"),
-                                        (1, 5, 384, "simt"), (5, 1, 16, "simt")])
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("n,m,d", [(1000, 3000, 384), (257, 1031, 100), (64, 129, 7), (1, 5, 384), (5, 1, 16), (300, 20000, 384),
+                                   (4096, 4096, 384), (700, 900, 768)])
 def test_match_nn_vs_oracles(vfm, n, m, d, algo):
     rng = np.random.default_rng(n * 7 + m)
     a = rng.standard_normal((n, d)).astype(np.float32)
@@ -47,6 +48,34 @@ def test_match_nn_vs_oracles(vfm, n, m, d, algo):
     o = match.match_nn(a, b, mutual=True)
     _cmp_match(gd, c, o, "01", 0.9 if m > 1 else 0.0)
     _cmp_match(gd, c, o, "10", 0.9 if n > 1 else 0.0)
+
+
+def test_match_tc_pathological_ties(vfm):
+    """All database rows identical (every score ties) + zero rows: the candidate lists overflow and the exact
+    fallback scan must still return the lowest index and the tied runner-up."""
+    rng = np.random.default_rng(8)
+    a = rng.standard_normal((300, 128)).astype(np.float32)
+    a[::7] = 0
+    b = np.tile(rng.standard_normal((1, 128)).astype(np.float32), (2000, 1))
+    b[1500:] = rng.standard_normal((500, 128)).astype(np.float32)
+    b[100] = 0
+    g = vfm.match_nn(a, b, mutual=True, algo="tc")
+    c = cref.match_nn(a, b, mutual=True)
+    for k in ("idx01", "sim01", "sec01", "idx10", "sim10", "sec10"):
+        assert np.array_equal(getattr(g, k).cpu().numpy(), c[k]), k
+
+
+def test_match_tc_equals_simt_full_size(vfm):
+    """BASELINE configs[1] size (10k x 50k x 384): the tensor-core path returns bit-identical indices and values to
+    the exact fp32 kernel (itself pinned to the oracle at smaller sizes); planted matches are recovered."""
+    s = synth.make_pair(2, 50_000, 10_000, 384)
+    a, b = torch.from_numpy(s["scan_feat"]).cuda(), torch.from_numpy(s["map_feat"]).cuda()
+    g = vfm.match_nn(a, b, mutual=True, algo="tc")
+    e = vfm.match_nn(a, b, mutual=True, algo="simt")
+    for k in ("idx01", "sim01", "sec01", "idx10", "sim10", "sec10"):
+        assert torch.equal(getattr(g, k), getattr(e, k)), k
+    inl = np.nonzero(s["perm"] >= 0)[0]
+    assert np.array_equal(g.idx01.cpu().numpy()[inl], s["perm"][inl])
 
 
 def test_match_no_normalize(vfm):

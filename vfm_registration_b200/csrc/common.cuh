@@ -97,7 +97,9 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 
 // ---- stage entry points (each file implements its own) -------------------------------------------------
 // normalize.cu: rows of x (n x d) -> y (n x dp) zero padded, L2-renormalised when `normalize`
-int normalize_rows(vfmreg_ctx* ctx, const float* x, int64_t n, int d, int dp, int normalize, float* y);
+// optional yh: fp16 copy (n x dp halves); optional nz: 1 per row unless the row is all-zero
+int normalize_rows(vfmreg_ctx* ctx, const float* x, int64_t n, int d, int dp, int normalize, float* y, void* yh = nullptr,
+                   uint8_t* nz = nullptr);
 // match_simt.cu: exact fp32 top-2 of a (n x dp) against b (m x dp)
 int match_simt(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64_t m, int dp, int32_t* idx,
                float* best, float* sec);
