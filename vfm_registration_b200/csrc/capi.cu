@@ -63,29 +63,58 @@ static int ensure_pinned(vfmreg_ctx* ctx, size_t bytes) {
 
 static inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
 
+static bool use_tc(uint32_t flags) {
+  const uint32_t algo = flags & VFMREG_ALGO_MASK;
+  // the tcgen05 path's error bound assumes unit-norm rows; un-normalised searches stay on the exact fp32 kernel
+  return (flags & VFMREG_NORMALIZE) && algo != VFMREG_ALGO_SIMT;
+}
+
+static inline int padded_dim(int d, uint32_t flags) { return round_up(d, use_tc(flags) ? 64 : 16); }
+
 // scratch needed by match_nn_impl beyond the caller-visible outputs
-static size_t match_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int dp, bool mutual) {
+static size_t match_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int d, uint32_t flags) {
+  const int dp = padded_dim(d, flags);
+  const bool mutual = (flags & VFMREG_MUTUAL) != 0;
   size_t s = arena_bytes((size_t)n * dp, 4) + arena_bytes((size_t)m * dp, 4);
-  s += match_simt_scratch(ctx, n, m);
-  if (mutual) s += match_simt_scratch(ctx, m, n);
+  if (use_tc(flags)) {
+    s += arena_bytes((size_t)n * dp, 2) + arena_bytes((size_t)m * dp, 2) + arena_bytes(n, 1) + arena_bytes(m, 1);
+    s += match_tc_scratch(ctx, n, m);
+    if (mutual) s += match_tc_scratch(ctx, m, n);
+  } else {
+    s += match_simt_scratch(ctx, n, m);
+    if (mutual) s += match_simt_scratch(ctx, m, n);
+  }
   return s;
 }
 
 static int match_nn_impl(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64_t m, int32_t d, uint32_t flags,
                          int32_t* idx01, float* sim01, float* sec01, int32_t* idx10, float* sim10, float* sec10) {
-  const int dp = round_up(d, 16);
+  const bool tc = use_tc(flags);
+  const int dp = padded_dim(d, flags);
   float* an = arena_take<float>(ctx, (size_t)n * dp);
   float* bn = arena_take<float>(ctx, (size_t)m * dp);
-  if (!an || !bn) {
+  uint16_t *ah = nullptr, *bh = nullptr;
+  uint8_t *nza = nullptr, *nzb = nullptr;
+  if (tc) {
+    ah = arena_take<uint16_t>(ctx, (size_t)n * dp);
+    bh = arena_take<uint16_t>(ctx, (size_t)m * dp);
+    nza = arena_take<uint8_t>(ctx, n);
+    nzb = arena_take<uint8_t>(ctx, m);
+  }
+  if (!an || !bn || (tc && (!ah || !bh || !nza || !nzb))) {
     set_error("match_nn: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
-  VFM_TRY(normalize_rows(ctx, a, n, d, dp, (flags & VFMREG_NORMALIZE) != 0, an));
-  VFM_TRY(normalize_rows(ctx, b, m, d, dp, (flags & VFMREG_NORMALIZE) != 0, bn));
-  VFM_TRY(match_simt(ctx, an, n, bn, m, dp, idx01, sim01, sec01));
-  if (flags & VFMREG_MUTUAL) {
-    VFM_CHECK_ARG(idx10, "match_nn: VFMREG_MUTUAL needs idx10");
-    VFM_TRY(match_simt(ctx, bn, m, an, n, dp, idx10, sim10, sec10));
+  const int norm = (flags & VFMREG_NORMALIZE) != 0;
+  VFM_TRY(normalize_rows(ctx, a, n, d, dp, norm, an, ah, nza));
+  VFM_TRY(normalize_rows(ctx, b, m, d, dp, norm, bn, bh, nzb));
+  if (flags & VFMREG_MUTUAL) VFM_CHECK_ARG(idx10, "match_nn: VFMREG_MUTUAL needs idx10");
+  if (tc) {
+    VFM_TRY(match_tc(ctx, an, ah, nza, n, bn, bh, m, dp, idx01, sim01, sec01));
+    if (flags & VFMREG_MUTUAL) VFM_TRY(match_tc(ctx, bn, bh, nzb, m, an, ah, n, dp, idx10, sim10, sec10));
+  } else {
+    VFM_TRY(match_simt(ctx, an, n, bn, m, dp, idx01, sim01, sec01));
+    if (flags & VFMREG_MUTUAL) VFM_TRY(match_simt(ctx, bn, m, an, n, dp, idx10, sim10, sec10));
   }
   return VFMREG_OK;
 }
@@ -203,9 +232,8 @@ int vfmreg_match_nn(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, 
   VFM_CHECK_ARG(a && b && idx01, "match_nn: null pointer");
   VFM_CHECK_ARG(n > 0 && m > 0 && d > 0, "match_nn: empty input (n=%lld m=%lld d=%d)", (long long)n, (long long)m, d);
   VFM_CUDA(cudaSetDevice(ctx->device));
-  const int dp = round_up(d, 16);
   arena_reset(ctx);
-  VFM_TRY(arena_reserve(ctx, match_scratch(ctx, n, m, dp, flags & VFMREG_MUTUAL)));
+  VFM_TRY(arena_reserve(ctx, match_scratch(ctx, n, m, d, flags)));
   return match_nn_impl(ctx, a, n, b, m, d, flags, idx01, sim01, sec01, idx10, sim10, sec10);
 }
 
@@ -235,8 +263,7 @@ static int register_impl(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt
                          int32_t* corr_host, uint8_t* mask_host, vfmreg_register_result* result) {
   const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
   const bool use_ratio = !(p->ratio != p->ratio);
-  const int dp = round_up(d, 16);
-  const size_t need = match_scratch(ctx, n, m, dp, mutual) + ransac_scratch((int32_t)n, p->n_hyp) +
+  const size_t need = match_scratch(ctx, n, m, d, p->flags) + ransac_scratch((int32_t)n, p->n_hyp) +
                       arena_bytes(n, 4) * 3 + arena_bytes(m, 4) + arena_bytes((size_t)n * 2, 4) + arena_bytes(n, 1) +
                       arena_bytes(16, 8) + arena_bytes(8, 8) + 4096;
   VFM_TRY(arena_reserve(ctx, need));

@@ -104,6 +104,10 @@ int normalize_rows(vfmreg_ctx* ctx, const float* x, int64_t n, int d, int dp, in
 int match_simt(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64_t m, int dp, int32_t* idx,
                float* best, float* sec);
 size_t match_simt_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m);
+// match_tc.cu: tcgen05 fp16 candidate search + exact fp32 re-rank; same results as match_simt (renormalised inputs only)
+int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
+             const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec);
+size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m);
 // filter.cu
 int filter_corr(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const float* sec01, const int32_t* idx10,
                 int64_t n, float min_cos, float ratio, int mutual, int32_t* corr, int32_t* count);

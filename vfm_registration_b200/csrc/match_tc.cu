@@ -39,7 +39,8 @@ constexpr int TC_THREADS = 192;
 constexpr uint32_t A_STAGE_BYTES = TBM * TBK * 2, B_STAGE_BYTES = TBN * TBK * 2;
 constexpr uint32_t SMEM_RING_V = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
 constexpr uint32_t SMEM_RING_I = SMEM_RING_V + 128 * CAP * 4;
-constexpr uint32_t SMEM_BARS = SMEM_RING_I + 128 * CAP * 4;
+constexpr uint32_t SMEM_SCR = SMEM_RING_I + 128 * CAP * 4;   // 32 x 128 floats: slow-path staging of one chunk
+constexpr uint32_t SMEM_BARS = SMEM_SCR + 32 * 128 * 4;
 constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 256 + 1024;  // + slack for 1024-byte alignment
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -104,6 +105,7 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;  // LBO = 1 (canonical value for swizzled K-major, ignored by the hardware)
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
@@ -120,7 +122,6 @@ struct TcParams {
   long long total_tiles; // row_blocks * col_tiles
   int slots;             // candidate slots per row
   const uint8_t* nz;     // per query row: 0 = all-zero descriptor
-  const int* first_cta;  // per row block: the first CTA whose span touches it
   float* cand_v;         // [n][slots][CAP]
   int* cand_i;
   int* cand_n;           // [n][slots]: count | overflow << 30
@@ -129,12 +130,93 @@ struct TcParams {
 __device__ __forceinline__ void flush_slot(const TcParams& P, int rb, int tid, float* ring_v, int* ring_i, int cnt, bool ovf) {
   const int row = rb * TBM + tid;
   if (row >= P.n) return;
-  const int slot = blockIdx.x - P.first_cta[rb];
+  // first CTA whose span [total*c/grid, total*(c+1)/grid) contains this row block's first tile
+  const long long t0 = (long long)rb * P.col_tiles;
+  const long long g = gridDim.x;
+  long long c0 = (t0 * g) / P.total_tiles;
+  while ((P.total_tiles * (c0 + 1)) / g <= t0) ++c0;
+  while (c0 > 0 && (P.total_tiles * c0) / g > t0) --c0;
+  const int slot = (int)(blockIdx.x - c0);
   const long long o = ((long long)row * P.slots + slot);
   P.cand_n[o] = cnt | (ovf ? (1 << 30) : 0);
   for (int e = 0; e < cnt; ++e) {
     P.cand_v[o * CAP + e] = ring_v[e * 128 + tid];
     P.cand_i[o * CAP + e] = ring_i[e * 128 + tid];
+  }
+}
+
+// Record one candidate (approximate score v of column `col`) in the thread's list and raise the recording threshold.
+__device__ __forceinline__ void push_candidate(float v, int col, int tid, float* ring_v, int* ring_i, float& best, float& second,
+                                               float& thr, int& cnt, bool& ovf) {
+  if (cnt == CAP) {  // compact: keep what is still above the (risen) threshold
+    int w = 0;
+#pragma unroll 1
+    for (int e = 0; e < CAP; ++e) {
+      const float ev = ring_v[e * 128 + tid];
+      const int ei = ring_i[e * 128 + tid];
+      if (ev > thr) {
+        ring_v[w * 128 + tid] = ev;
+        ring_i[w * 128 + tid] = ei;
+        ++w;
+      }
+    }
+    cnt = w;
+  }
+  if (cnt < CAP) {
+    ring_v[cnt * 128 + tid] = v;
+    ring_i[cnt * 128 + tid] = col;
+    ++cnt;
+  } else {
+    ovf = true;
+  }
+  if (v > best) {
+    second = best;
+    best = v;
+  } else if (v > second) {
+    second = v;
+  }
+  thr = second - MARGIN;
+}
+
+// One 32-column chunk of a query row (r[i] = approximate score of column col_base + c0 + i).
+// Fast path: a max tree and one compare (register only).  When the maximum clears the recording threshold the lane
+// locates it and counts how many values clear the threshold, still in registers; the usual case (exactly one) is a
+// single push.  Only the rare chunk with several qualifying values is parked in shared memory and walked by a rolled
+// loop, which keeps the kernel small enough for the instruction cache.
+__device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid, int col_base, int tid, float* scr, float* ring_v,
+                                           int* ring_i, float& best, float& second, float& thr, int& cnt, bool& ovf) {
+  if (c0 >= valid) return;  // warp-uniform
+  const bool partial = c0 + 32 > valid;  // warp-uniform: columns >= valid hold zeros (TMA out-of-bounds fill)
+  float m0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), m1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
+  float m2 = fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), m3 = fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7]));
+#pragma unroll
+  for (int i = 8; i < 32; i += 4) {
+    m0 = fmaxf(m0, __uint_as_float(r[i]));
+    m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+    m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+    m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+  }
+  const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  if (mx > thr) {
+    int n_above = 0, imax = 0;
+#pragma unroll
+    for (int i = 31; i >= 0; --i) {
+      const float v = __uint_as_float(r[i]);
+      n_above += (v > thr) ? 1 : 0;
+      imax = (v == mx) ? i : imax;
+    }
+    if (n_above == 1 && !partial) {
+      push_candidate(mx, col_base + c0 + imax, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) scr[i * 128 + tid] = __uint_as_float(r[i]);
+      const int lim = min(32, valid - c0);
+#pragma unroll 1
+      for (int i = 0; i < lim; ++i) {
+        const float v = scr[i * 128 + tid];
+        if (v > thr) push_candidate(v, col_base + c0 + i, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
+      }
+    }
   }
 }
 
@@ -147,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t sA = base, sB = base + STAGES * A_STAGE_BYTES;
   float* ring_v = reinterpret_cast<float*>(smem + SMEM_RING_V);
   int* ring_i = reinterpret_cast<int*>(smem + SMEM_RING_I);
+  float* scr = reinterpret_cast<float*>(smem + SMEM_SCR);
   const uint32_t bars = base + SMEM_BARS;
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 16 * STAGES + 32);
@@ -183,6 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t stage = 0, phase = 0;
       for (long long t = t_begin; t < t_end; ++t) {
         const int rb = (int)(t / P.col_tiles), ct = (int)(t % P.col_tiles);
+#pragma unroll 1
         for (int kb = 0; kb < P.kb; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           mbar_expect_tx(full0 + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
@@ -202,6 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(tempty0 + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * TBN;
+#pragma unroll 1
         for (int kb = 0; kb < P.kb; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
@@ -244,57 +329,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_after();
       const int col_base = ct * TBN;
       const int valid = min(TBN, P.m - col_base);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN;
+      uint32_t ra[32], rbuf[32];
+      tc_ld32(t_addr, ra);
 #pragma unroll 1
-      for (int c = 0; c < TBN / 32; ++c) {
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + c * 32, r);
+      for (int c = 0; c < TBN / 32; c += 2) {
         tc_wait_ld();
-        const int c0 = c * 32;
-        if (c0 >= valid) continue;   // warp-uniform
-        float mx = -INFINITY;
-        if (c0 + 32 <= valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
-        if (mx > thr) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]);
-            if (v > thr && c0 + i < valid) {
-              if (cnt == CAP) {  // compact: keep what is still above the (risen) threshold
-                int w = 0;
-                for (int e = 0; e < CAP; ++e) {
-                  const float ev = ring_v[e * 128 + tid];
-                  const int ei = ring_i[e * 128 + tid];
-                  if (ev > thr) {
-                    ring_v[w * 128 + tid] = ev;
-                    ring_i[w * 128 + tid] = ei;
-                    ++w;
-                  }
-                }
-                cnt = w;
-              }
-              if (cnt < CAP) {
-                ring_v[cnt * 128 + tid] = v;
-                ring_i[cnt * 128 + tid] = col_base + c0 + i;
-                ++cnt;
-              } else {
-                ovf = true;
-              }
-              if (v > best) {
-                second = best;
-                best = v;
-              } else if (v > second) {
-                second = v;
-              }
-              thr = second - MARGIN;
-            }
-          }
-        }
+        tc_ld32(t_addr + (c + 1) * 32, rbuf);  // in flight while chunk c is scanned
+        scan_chunk(ra, c * 32, valid, col_base, tid, scr, ring_v, ring_i, best, second, thr, cnt, ovf);
+        tc_wait_ld();
+        if (c + 2 < TBN / 32) tc_ld32(t_addr + (c + 2) * 32, ra);
+        scan_chunk(rbuf, (c + 1) * 32, valid, col_base, tid, scr, ring_v, ring_i, best, second, thr, cnt, ovf);
       }
       tc_fence_before();
       __syncwarp();
@@ -489,7 +534,7 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m) {
 
 size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m) {
   const TcPlan p = tc_plan(ctx, n, m);
-  return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) + arena_bytes(p.row_blocks, 4) +
+  return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
          arena_bytes((size_t)n + 1, 4) + 1024;
 }
 
@@ -502,30 +547,10 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   float* cand_v = arena_take<float>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_i = arena_take<int>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_n = arena_take<int>(ctx, (size_t)n * plan.slots);
-  int* first_cta = arena_take<int>(ctx, plan.row_blocks);
   int* redo = arena_take<int>(ctx, (size_t)n + 1);  // [0] = count, [1..] = rows
-  if (!cand_v || !cand_i || !cand_n || !first_cta || !redo) {
+  if (!cand_v || !cand_i || !cand_n || !redo) {
     set_error("match_tc: scratch arena too small");
     return VFMREG_ERR_ALLOC;
-  }
-  // first CTA touching each row block (host-side table, tiny)
-  {
-    static thread_local int* host_tab = nullptr;
-    static thread_local int host_cap = 0;
-    if (host_cap < plan.row_blocks) {
-      if (host_tab) cudaFreeHost(host_tab);
-      VFM_CUDA(cudaMallocHost(&host_tab, sizeof(int) * plan.row_blocks * 2));
-      host_cap = plan.row_blocks * 2;
-    } else {
-      VFM_CUDA(cudaStreamSynchronize(ctx->stream));  // the previous async copy from this buffer must have drained
-    }
-    int c = 0;
-    for (int rb = 0; rb < plan.row_blocks; ++rb) {
-      const long long t0 = (long long)rb * plan.col_tiles;
-      while ((plan.total * (c + 1)) / plan.grid <= t0) ++c;  // span c = [total*c/grid, total*(c+1)/grid)
-      host_tab[rb] = c;
-    }
-    VFM_CUDA(cudaMemcpyAsync(first_cta, host_tab, sizeof(int) * plan.row_blocks, cudaMemcpyHostToDevice, ctx->stream));
   }
   VFM_CUDA(cudaMemsetAsync(cand_n, 0, sizeof(int) * (size_t)n * plan.slots, ctx->stream));
   VFM_CUDA(cudaMemsetAsync(redo, 0, sizeof(int), ctx->stream));
@@ -540,7 +565,6 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   P.total_tiles = plan.total;
   P.slots = plan.slots;
   P.nz = nz_a;
-  P.first_cta = first_cta;
   P.cand_v = cand_v;
   P.cand_i = cand_i;
   P.cand_n = cand_n;
