@@ -125,9 +125,11 @@ struct TcParams {
   float* cand_v;         // [n][slots][CAP]
   int* cand_i;
   int* cand_n;           // [n][slots]: count | overflow << 30
+  float2* slot_top2;     // [n][slots]: approximate (best, runner-up) of the slot's column span
 };
 
-__device__ __forceinline__ void flush_slot(const TcParams& P, int rb, int tid, float* ring_v, int* ring_i, int cnt, bool ovf) {
+__device__ __forceinline__ void flush_slot(const TcParams& P, int rb, int tid, float* ring_v, int* ring_i, int cnt, bool ovf,
+                                           float best, float second) {
   const int row = rb * TBM + tid;
   if (row >= P.n) return;
   // first CTA whose span [total*c/grid, total*(c+1)/grid) contains this row block's first tile
@@ -139,6 +141,7 @@ __device__ __forceinline__ void flush_slot(const TcParams& P, int rb, int tid, f
   const int slot = (int)(blockIdx.x - c0);
   const long long o = ((long long)row * P.slots + slot);
   P.cand_n[o] = cnt | (ovf ? (1 << 30) : 0);
+  P.slot_top2[o] = make_float2(best, second);
   for (int e = 0; e < cnt; ++e) {
     P.cand_v[o * CAP + e] = ring_v[e * 128 + tid];
     P.cand_i[o * CAP + e] = ring_i[e * 128 + tid];
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int rb = (int)(t / P.col_tiles), ct = (int)(t % P.col_tiles);
       if (rb != cur_rb) {
-        if (cur_rb >= 0) flush_slot(P, cur_rb, tid, ring_v, ring_i, cnt, ovf);
+        if (cur_rb >= 0) flush_slot(P, cur_rb, tid, ring_v, ring_i, cnt, ovf, best, second);
         cur_rb = rb;
         const int row = rb * TBM + tid;
         active = (row < P.n) && (P.nz[row] != 0);
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
-    if (cur_rb >= 0) flush_slot(P, cur_rb, tid, ring_v, ring_i, cnt, ovf);
+    if (cur_rb >= 0) flush_slot(P, cur_rb, tid, ring_v, ring_i, cnt, ovf, best, second);
   }
   tc_fence_before();
   __syncthreads();
@@ -369,11 +372,47 @@ __device__ __forceinline__ float canon_dot(const float* __restrict__ x, const fl
   return acc;
 }
 
+// Re-rank, step 1: one thread per candidate entry.  The row's recording threshold is rebuilt from the per-slot approximate
+// top-2 (second largest of all slot bests / runner-ups, minus the margin); surviving candidates get their canonical fp32
+// score written over the approximate one, the others are marked -inf.  The fmaf chain over k is sequential by
+// definition, so the parallelism is across (row, candidate) pairs; the query row is a warp-wide broadcast load.
 __global__ void __launch_bounds__(128)
-    rerank_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int m, int dp, int slots,
-                  const uint8_t* __restrict__ nz, const float* __restrict__ cand_v, const int* __restrict__ cand_i,
-                  const int* __restrict__ cand_n, int32_t* __restrict__ idx, float* __restrict__ best, float* __restrict__ sec,
-                  int* __restrict__ redo_list, int* __restrict__ redo_count) {
+    rerank_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int dp, int slots,
+                      const uint8_t* __restrict__ nz, float* __restrict__ cand_v, const int* __restrict__ cand_i,
+                      const int* __restrict__ cand_n, const float2* __restrict__ slot_top2) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_row = (long long)slots * CAP;
+  if (g >= (long long)n * per_row) return;
+  const int row = (int)(g / per_row);
+  const int rem = (int)(g - (long long)row * per_row);
+  const int slot = rem / CAP, e = rem - slot * CAP;
+  if (!nz[row]) return;
+  const int cn = cand_n[(long long)row * slots + slot];
+  if (e >= (cn & 0xFFFF)) return;
+  float t1 = -INFINITY, t2 = -INFINITY;
+  bool overflow = false;
+  for (int s = 0; s < slots; ++s) {
+    const int c = cand_n[(long long)row * slots + s];
+    if ((c & 0xFFFF) == 0 && !((c >> 30) & 1)) continue;
+    overflow |= (c >> 30) & 1;
+    const float2 t = slot_top2[(long long)row * slots + s];
+    if (t.x > t1) { t2 = fmaxf(t1, t.y); t1 = t.x; } else { t2 = fmaxf(t2, t.x); }
+  }
+  if (overflow) return;  // the whole row is redone exactly
+  const float v = cand_v[g];
+  if (!(v >= t2 - MARGIN)) {
+    cand_v[g] = -INFINITY;
+    return;
+  }
+  cand_v[g] = canon_dot(a + (long long)row * dp, b + (long long)cand_i[g] * dp, dp);
+}
+
+// Re-rank, step 2: one thread per query row picks the exact top-2 (lowest index on ties); rows whose list overflowed are
+// queued for exact_rows_kernel.
+__global__ void __launch_bounds__(128)
+    rerank_pick_kernel(int n, int m, int slots, const uint8_t* __restrict__ nz, const float* __restrict__ cand_v,
+                       const int* __restrict__ cand_i, const int* __restrict__ cand_n, int32_t* __restrict__ idx,
+                       float* __restrict__ best, float* __restrict__ sec, int* __restrict__ redo_list, int* __restrict__ redo_count) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   if (!nz[row]) {  // all-zero query: every canonical inner product is exactly +0 -> lowest index wins
@@ -382,8 +421,8 @@ __global__ void __launch_bounds__(128)
     if (sec) sec[row] = (m > 1) ? 0.0f : -INFINITY;
     return;
   }
-  // approximate top-2 over all slots -> threshold
-  float t1 = -INFINITY, t2 = -INFINITY;
+  float b1 = -INFINITY, b2 = -INFINITY;
+  int bi = 0x7fffffff;
   bool overflow = false;
   for (int s = 0; s < slots; ++s) {
     const long long o = (long long)row * slots + s;
@@ -391,31 +430,9 @@ __global__ void __launch_bounds__(128)
     overflow |= (cn >> 30) & 1;
     const int c = cn & 0xFFFF;
     for (int e = 0; e < c; ++e) {
-      const float v = cand_v[o * CAP + e];
-      if (v > t1) {
-        t2 = t1;
-        t1 = v;
-      } else if (v > t2) {
-        t2 = v;
-      }
-    }
-  }
-  if (overflow) {
-    redo_list[atomicAdd(redo_count, 1)] = row;
-    return;
-  }
-  const float thr = t2 - MARGIN;  // -inf when there is a single candidate (m == 1)
-  const float* ar = a + (long long)row * dp;
-  float b1 = -INFINITY, b2 = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int s = 0; s < slots; ++s) {
-    const long long o = (long long)row * slots + s;
-    const int c = cand_n[o] & 0xFFFF;
-    for (int e = 0; e < c; ++e) {
-      const float v = cand_v[o * CAP + e];
-      if (!(v >= thr)) continue;
+      const float x = cand_v[o * CAP + e];
+      if (x == -INFINITY) continue;
       const int j = cand_i[o * CAP + e];
-      const float x = canon_dot(ar, b + (long long)j * dp, dp);
       if (x > b1 || (x == b1 && j < bi)) {
         b2 = b1;
         b1 = x;
@@ -424,6 +441,10 @@ __global__ void __launch_bounds__(128)
         b2 = x;
       }
     }
+  }
+  if (overflow) {
+    redo_list[atomicAdd(redo_count, 1)] = row;
+    return;
   }
   idx[row] = (bi == 0x7fffffff) ? 0 : bi;
   if (best) best[row] = b1;
@@ -535,7 +556,7 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m) {
 size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m) {
   const TcPlan p = tc_plan(ctx, n, m);
   return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
-         arena_bytes((size_t)n + 1, 4) + 1024;
+         arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + 1024;
 }
 
 // a32/b32: renormalised fp32 rows (n x dp), a16/b16: their fp16 copies, nz_a: non-zero flags of the query rows.
@@ -547,8 +568,9 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   float* cand_v = arena_take<float>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_i = arena_take<int>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_n = arena_take<int>(ctx, (size_t)n * plan.slots);
+  float2* slot_top2 = arena_take<float2>(ctx, (size_t)n * plan.slots);
   int* redo = arena_take<int>(ctx, (size_t)n + 1);  // [0] = count, [1..] = rows
-  if (!cand_v || !cand_i || !cand_n || !redo) {
+  if (!cand_v || !cand_i || !cand_n || !slot_top2 || !redo) {
     set_error("match_tc: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
@@ -568,6 +590,7 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   P.cand_v = cand_v;
   P.cand_i = cand_i;
   P.cand_n = cand_n;
+  P.slot_top2 = slot_top2;
   static bool attr_set = false;
   if (!attr_set) {
     VFM_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
@@ -577,9 +600,13 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   match_tc_kernel<<<plan.grid, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(map_a, map_b, P);
   VFM_TRY(launch_check(ctx, "match_tc_kernel"));
   group_end(ctx, GROUP_MATCH, 1);
-  rerank_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(a32, b32, (int)n, (int)m, dp, plan.slots, nz_a, cand_v, cand_i, cand_n,
-                                                          idx, best, sec, redo + 1, redo);
-  VFM_TRY(launch_check(ctx, "rerank_kernel"));
+  const long long entries = (long long)n * plan.slots * CAP;
+  rerank_dot_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>(a32, b32, (int)n, dp, plan.slots, nz_a, cand_v, cand_i, cand_n,
+                                                                    slot_top2);
+  VFM_TRY(launch_check(ctx, "rerank_dot_kernel"));
+  rerank_pick_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(n, (int)m, plan.slots, nz_a, cand_v, cand_i, cand_n, idx, best, sec,
+                                                               redo + 1, redo);
+  VFM_TRY(launch_check(ctx, "rerank_pick_kernel"));
   exact_rows_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(a32, b32, (int)m, dp, redo + 1, redo, idx, best, sec);
   return launch_check(ctx, "exact_rows_kernel");
 }
