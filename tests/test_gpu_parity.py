@@ -191,3 +191,26 @@ def test_register_sample_idx_and_errors(vfm):
         vfm.register(s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"][:, :32])
     with pytest.raises(vfm.VfmRegError):
         vfm.register(s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"], ransac_iters=0)
+
+
+def test_compat_shim_reference_layout(vfm):
+    """The reference's own call surface (one (N, 3+D) array per cloud) through the shim."""
+    from vfm_registration_b200 import compat
+    s = synth.make_pair(4, 3000, 1000, 64)
+    vmap_arr = np.c_[s["map_xyz"], s["map_feat"]].astype(np.float32)
+    scan_arr = np.c_[s["scan_xyz"], s["scan_feat"]].astype(np.float32)
+    vm = compat.VoxelHashMap(1.0, 100.0, 20)
+    vm.add_points(vmap_arr)
+    src, tgt = vm.get_vfm_correspondences(scan_arr, 0.8)
+    osrc, otgt = match.get_vfm_correspondences(scan_arr, vmap_arr, 0.8)
+    assert src.dtype == np.float64 and np.array_equal(src, osrc) and np.array_equal(tgt, otgt)
+    node = compat.RegistrationNode(ransac_iters=2048)
+    pose, icp = node.ransac_registration(vmap_arr, scan_arr, "vfm")
+    assert icp is None and pose.shape == (4, 4)
+    # the reference's literal tau = 10000 selects the min-residual hypothesis; it still lands near the truth here
+    t_err, r_err = node.compute_errors(pose, s["T_gt"], "vfm")
+    assert node.compute_success_rate("vfm", 2, 5) in (0.0, 1.0)
+    with pytest.raises(ValueError, match="Invalid method"):
+        node.ransac_registration(vmap_arr, scan_arr, "bogus")
+    with pytest.raises(ValueError, match="Invalid shape"):
+        vm.get_vfm_correspondences(scan_arr[:, :10], 0.8)

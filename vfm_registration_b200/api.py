@@ -25,7 +25,7 @@ from . import _lib
 from ._lib import VfmRegError
 
 __all__ = ["Context", "get_context", "match_nn", "filter_correspondences", "ransac_kabsch", "register", "RegResult",
-           "MatchResult", "RansacResult", "VfmRegError"]
+           "MatchResult", "RansacResult", "VfmRegError", "CameraSpec", "project_gather"]
 
 _ALGO = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}
 
@@ -293,3 +293,82 @@ def register(source_pcd, target_pcd, src_feats, tgt_feats, *, normalize: bool = 
     return RegResult(T=np.array(res.T, dtype=np.float64).reshape(4, 4), corr=corr_np, inlier_mask=mask_np,
                      fitness=float(res.fitness), rmse=float(res.rmse), best_hyp=int(res.best_hyp),
                      n_inliers=int(res.n_inliers))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a3/a4/a5: projection + feature gather
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class CameraSpec:
+    """One camera of ``project_gather`` / ``extract_features``.
+
+    P (3, 4): pixel_h = P @ [x y z 1] in full-resolution pixels (K @ T_cam_from_lidar[:3]);
+    img_hw: size of the (sub-sampled, cropped) image the black-pixel test and the feature map refer to;
+    crop = (y0, x0, h, w) in sub-sampled pixels (default: whole image at the origin); see include/vfmreg_b200.h."""
+    P: np.ndarray
+    img_hw: tuple
+    grid_hw: tuple
+    crop: Optional[tuple] = None
+    subsample: float = 1.0
+    z_inclusive: bool = False
+    float_bounds: bool = False
+    black_mode: int = 1
+    rot90: bool = False
+
+
+def project_gather(points, cams, tokens, images=None, *, device=None):
+    """Fused point->pixel projection, token-grid bilinear sampling and first-camera-wins scatter.
+
+    points (N, 3) f32; cams: list of CameraSpec; tokens: list of (grid_h, grid_w, D) f32 tensors (one per camera);
+    images: optional list of (H, W, 3) uint8 arrays (stored orientation) for the black-pixel test.
+    Returns (desc (N, D) f32 cuda, cam_of_point (N,) int32, uv (N, 2) int32)."""
+    ctx = get_context(device)
+    dev = torch.device("cuda", ctx.device)
+    pts = _dev_f32(points, dev, "points", 3)
+    n = pts.shape[0]
+    toks = [(torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)) if isinstance(t, np.ndarray) else t)
+            .to(device=dev, dtype=torch.float32).contiguous() for t in tokens]
+    if len(toks) != len(cams) or not cams:
+        raise ValueError("Invalid shape: one token grid per camera expected")
+    d = toks[0].shape[-1]
+    sizes = [((t.numel() + 3) // 4) * 4 for t in toks]
+    tok_flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    tok_off, o = [], 0
+    for t, sz in zip(toks, sizes):
+        if t.dim() != 3 or t.shape[-1] != d:
+            raise ValueError(f"Invalid shape for tokens: {tuple(t.shape)}")
+        tok_flat[o:o + t.numel()] = t.reshape(-1)
+        tok_off.append(o)
+        o += sz
+    img_flat, img_off = None, None
+    if images is not None:
+        imgs = [torch.from_numpy(np.ascontiguousarray(im, dtype=np.uint8)) if isinstance(im, np.ndarray) else im for im in images]
+        img_off, o = [], 0
+        for im in imgs:
+            img_off.append(o)
+            o += im.numel()
+        img_flat = torch.cat([im.reshape(-1).to(dev) for im in imgs])
+    arr = (_lib.Camera * len(cams))()
+    for i, (c, t) in enumerate(zip(cams, toks)):
+        p = np.asarray(c.P, dtype=np.float64).reshape(12)
+        for k in range(12):
+            arr[i].P[k] = p[k]
+        arr[i].img_h, arr[i].img_w = int(c.img_hw[0]), int(c.img_hw[1])
+        y0, x0, h, w = c.crop if c.crop is not None else (0, 0, c.img_hw[0], c.img_hw[1])
+        arr[i].crop_y0, arr[i].crop_x0, arr[i].crop_h, arr[i].crop_w = int(y0), int(x0), int(h), int(w)
+        if tuple(t.shape[:2]) != tuple(c.grid_hw):
+            raise ValueError(f"Invalid shape: token grid {tuple(t.shape[:2])} vs camera grid {tuple(c.grid_hw)}")
+        arr[i].grid_h, arr[i].grid_w = int(c.grid_hw[0]), int(c.grid_hw[1])
+        arr[i].subsample = float(c.subsample)
+        arr[i].z_inclusive, arr[i].float_bounds = int(c.z_inclusive), int(c.float_bounds)
+        arr[i].black_mode = int(c.black_mode) if images is not None else 0
+        arr[i].rot90 = int(c.rot90)
+    desc = torch.empty((n, d), dtype=torch.float32, device=dev)
+    cam_of = torch.empty(n, dtype=torch.int32, device=dev)
+    uv = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    toff = (C.c_int64 * len(cams))(*tok_off)
+    ioff = (C.c_int64 * len(cams))(*img_off) if img_off is not None else None
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_project_gather(ctx.handle, _ptr(pts), n, arr, len(cams), _ptr(tok_flat), toff, _ptr(img_flat), ioff,
+                                            d, _ptr(desc), _ptr(cam_of), _ptr(uv)), "vfmreg_project_gather")
+    return desc, cam_of, uv
