@@ -177,6 +177,35 @@ VFMREG_API int vfmreg_project_gather(vfmreg_ctx* ctx, const float* points, int64
                           const float* tokens, const int64_t* token_offsets, const uint8_t* images,
                           const int64_t* image_offsets, int32_t d, float* desc, int32_t* cam_of_point, int32_t* uv);
 
+/* ---------------------------------------------------------------------------------------------
+ * a1/a2  image features: ImageFeatureGenerator.get_image_features' GPU work (vfm_reg/image_features.py:67-77 transform,
+ * :95-101 `self.model.model(x)` = FeatUp DINOv2 featurizer + ChannelNorm).  ViT-S/14 is what the reference loads
+ * (feature_size 384, image_features.py:43-44); ViT-B/14 and ViT-L/14 are the same code with other dimensions.
+ * GEMMs run on tcgen05 in bf16 with fp32 accumulation; the residual stream and all normalisations are fp32.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vfmreg_vit vfmreg_vit;
+
+typedef struct {
+  int32_t depth, width, heads, mlp_dim;  /* ViT-S 12/384/6/1536, ViT-B 12/768/12/3072, ViT-L 24/1024/16/4096 */
+  int32_t patch;                         /* 14 */
+  int32_t patch_h;                       /* patch rows after the resize: 16 (image_features.py:33) */
+  int32_t channel_norm;                  /* 1: apply FeatUp's ChannelNorm (use_norm=True, image_features.py:41) */
+  float ln_eps;                          /* 1e-6 */
+  float cn_eps;                          /* 1e-4 */
+  float mean[3], std[3];                 /* ImageNet statistics of the Normalize transform (image_features.py:76) */
+} vfmreg_vit_config;
+
+VFMREG_API int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit** vit);
+VFMREG_API void vfmreg_vit_destroy(vfmreg_vit* vit);
+/* float32 host tensor by its dinov2-hub state-dict name (see vit.cu for the list); matrices become bf16 on the device */
+VFMREG_API int vfmreg_vit_set_weight(vfmreg_vit* vit, const char* name, const float* host, int64_t count);
+/* position embedding already interpolated to the patch grid: (1 + grid_h*grid_w, width) float32 host, CLS row first */
+VFMREG_API int vfmreg_vit_set_pos_embed(vfmreg_vit* vit, int32_t grid_h, int32_t grid_w, const float* host);
+/* patch grid create_transform_ would pick for an (img_h, img_w) image (image_features.py:67-69) */
+VFMREG_API int vfmreg_vit_grid(const vfmreg_vit* vit, int32_t img_h, int32_t img_w, int32_t* grid_h, int32_t* grid_w);
+/* images: device uint8 (b, img_h, img_w, 3) RGB; tokens: device float32 (b, grid_h, grid_w, width) */
+VFMREG_API int vfmreg_vit_forward(vfmreg_vit* vit, const uint8_t* images, int32_t b, int32_t img_h, int32_t img_w, float* tokens);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,94 @@
+"""GPU numerics of the DINOv2 forward (bf16 tensor-core GEMMs, fp32 accumulation / residual stream) against the
+torch-CPU float32 oracle with the same seeded random weights (oracle/vit.py, itself checked against
+transformers.Dinov2Model).  Tolerances are for channel-normalised (unit-variance) features and are those of bf16
+operands through `depth` layers; they are written next to each assertion."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from oracle import vit as ovit  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def vfm():
+    assert torch.cuda.is_available()
+    import vfm_registration_b200 as v
+    v.get_context(0)
+    return v
+
+
+def _images(rng, b, h, w):
+    img = rng.integers(0, 255, (b, h, w, 3), dtype=np.uint8)
+    # smooth structure so that the resize matters
+    yy, xx = np.mgrid[0:h, 0:w]
+    img[..., 0] = (128 + 100 * np.sin(xx / 7.0 + yy / 11.0)).astype(np.uint8)
+    img[:, : h // 5, : w // 4] = 0
+    return img
+
+
+@pytest.mark.parametrize("model,depth,hw,b", [("vits14", 12, (224, 224), 2), ("vits14", 12, (70, 82), 1), ("vitb14", 12, (224, 224), 1),
+                                              ("vitl14", 24, (224, 224), 1)])
+def test_vit_forward_vs_oracle(vfm, model, depth, hw, b):
+    cfg = ovit.CONFIGS[model]
+    sd = ovit.make_weights(cfg, seed=11)
+    rng = np.random.default_rng(5)
+    imgs = _images(rng, b, *hw)
+    f = vfm.ViTFeaturizer(model, sd)
+    got = f.forward(imgs).cpu()
+    x = torch.stack([ovit.preprocess(im) for im in imgs])
+    want = ovit.forward(sd, cfg, x)
+    assert got.shape == want.shape == (b, 16, ovit.patch_grid(*hw)[1], cfg.width)
+    err = (got - want).abs()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(0, 2), want.flatten(0, 2), dim=1)
+    # bf16 operands (2^-9 relative) through `depth` residual blocks on unit-variance outputs
+    assert cos.min() > 0.999, float(cos.min())
+    assert err.mean() < 0.02 and err.max() < 0.25, (float(err.mean()), float(err.max()))
+
+
+def test_image_feature_generator_compat(vfm):
+    gen = vfm.ImageFeatureGenerator("dinov2", use_featup=False, seed=1)
+    img = _images(np.random.default_rng(0), 1, 70, 82)[0]
+    f = gen.get_image_features(img)
+    assert f.shape == (16, 18, 384) and f.dtype == np.float32          # (16, patch_w, C) like the reference
+    assert abs(float(f.mean())) < 0.05 and abs(float(f.std()) - 1.0) < 0.05   # identity-affine ChannelNorm output
+    up = gen.get_image_features(img, upsample=True)
+    assert up.shape == (70, 82, 384)
+    with pytest.raises(ValueError, match="Unsupported foundation model"):
+        vfm.ImageFeatureGenerator("maskclip")
+
+
+def test_extract_features_end_to_end(vfm):
+    """BASELINE configs[2] shape: 6 surround images -> ViT -> projection gather; checked against the oracle chain
+    (oracle ViT features -> bilinear upsample -> create_descriptors)."""
+    from oracle import project
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(3)
+    b, h, w, n = 6, 224, 224, 4000
+    imgs = _images(rng, b, h, w)
+    pts = np.c_[rng.uniform(-20, 20, (n, 2)), rng.uniform(-2, 4, n)].astype(np.float32)
+    kmat = np.array([[200.0, 0, 112.0], [0, 200.0, 112.0], [0, 0, 1.0]])
+    ks = np.stack([kmat] * b)
+    ts = []
+    for i in range(b):
+        t = np.eye(4)
+        t[:3, :3] = (R.from_euler("z", 60.0 * i, degrees=True) * R.from_euler("yx", [90, -90], degrees=True)).as_matrix().T
+        ts.append(t)
+    ts = np.stack(ts)
+    cfg = ovit.CONFIGS["vits14"]
+    sd = ovit.make_weights(cfg, seed=2)
+    f = vfm.ViTFeaturizer("vits14", sd)
+    desc = vfm.extract_features(imgs, pts, ks, ts, featurizer=f).cpu().numpy()
+    x = torch.stack([ovit.preprocess(im) for im in imgs])
+    tok = ovit.forward(sd, cfg, x).numpy()
+    feats = {i: np.ascontiguousarray(project.upsample_bilinear(np.ascontiguousarray(tok[i].transpose(2, 0, 1)), h, w).transpose(1, 2, 0))
+             for i in range(b)}
+    images = {i: imgs[i] for i in range(b)}
+    fn = lambda pcl_h, image, cam: project.project_pinhole(pcl_h[:3].T, ks[cam], ts[cam], h, w, image=image)  # noqa: E731
+    want = project.create_descriptors(images, feats, fn, pts)
+    seen = np.abs(want).sum(1) > 0
+    assert 0.3 < seen.mean() <= 1.0
+    assert np.array_equal(np.abs(desc).sum(1) > 0, seen)                 # identical visible set
+    cos = (desc[seen] * want[seen]).sum(1) / (np.linalg.norm(desc[seen], axis=1) * np.linalg.norm(want[seen], axis=1))
+    assert cos.min() > 0.999 and np.abs(desc - want).max() < 0.25        # bf16 ViT tolerance, as above

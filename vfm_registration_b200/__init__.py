@@ -4,3 +4,4 @@ from .api import (CameraSpec, Context, MatchResult, RansacResult, RegResult, Vfm
                   match_nn, project_gather, ransac_kabsch, register)
 
 __version__ = "0.1.0"
+from .features import ImageFeatureGenerator, ViTFeaturizer, create_descriptors, extract_features  # noqa: E402,F401

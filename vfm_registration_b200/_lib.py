@@ -36,6 +36,12 @@ class Camera(C.Structure):
                 ("float_bounds", C.c_int32), ("black_mode", C.c_int32), ("rot90", C.c_int32)]
 
 
+class VitConfig(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("width", C.c_int32), ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("patch", C.c_int32),
+                ("patch_h", C.c_int32), ("channel_norm", C.c_int32), ("ln_eps", C.c_float), ("cn_eps", C.c_float),
+                ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+
+
 _P = C.c_void_p
 _SIGS = {
     "vfmreg_version": (C.c_int, []),
@@ -58,6 +64,12 @@ _SIGS = {
                                        _P, _P, C.POINTER(RegisterResult)]),
     "vfmreg_project_gather": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Camera), C.c_int32, _P, C.POINTER(C.c_int64), _P,
                                         C.POINTER(C.c_int64), C.c_int32, _P, _P, _P]),
+    "vfmreg_vit_create": (C.c_int, [_P, C.POINTER(VitConfig), C.POINTER(_P)]),
+    "vfmreg_vit_destroy": (None, [_P]),
+    "vfmreg_vit_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "vfmreg_vit_set_pos_embed": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "vfmreg_vit_grid": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vfmreg_vit_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
 }
 
 _lib = None

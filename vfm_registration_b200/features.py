@@ -1,0 +1,218 @@
+"""Image-feature producer on libvfmreg_b200.so: the reference's ``ImageFeatureGenerator`` / ``create_descriptors`` call
+surface and BASELINE.json's ``extract_features()``.
+
+Reference (paths relative to the checkout):
+  ImageFeatureGenerator.get_image_features   src/vfm-reg/src/vfm_reg/image_features.py:79-117
+  create_descriptors                         src/vfm-reg/src/prepare_scenes.py:50-107
+
+The DINOv2 weights come from torch.hub in the reference (needs network); here they are passed in as a state dict
+(dinov2-hub or transformers naming) or drawn from a seed for benchmarking.  The position embedding is interpolated
+to the patch grid once per grid size on the host (weight preparation, cached), everything per image runs in the
+CUDA kernels: resize + normalise + im2col, tcgen05 GEMMs with fused epilogues, attention, norms."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib, api
+
+PRESETS = {"vits14": (12, 384, 6), "vitb14": (12, 768, 12), "vitl14": (24, 1024, 16)}
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def random_state_dict(model: str, seed: int = 0, pos_grid: int = 37) -> Dict[str, torch.Tensor]:
+    """Seeded random weights of the right shapes (no checkpoint is reachable offline); dinov2-hub names."""
+    depth, w, heads = PRESETS[model]
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s, std=0.02: torch.randn(*s, generator=g) * std  # noqa: E731
+    un = lambda *s, lo=0.8, hi=1.2: torch.rand(*s, generator=g) * (hi - lo) + lo  # noqa: E731
+    md = 4 * w
+    sd = {"patch_embed.proj.weight": rn(w, 3, 14, 14, std=0.05), "patch_embed.proj.bias": rn(w), "cls_token": rn(1, 1, w, std=0.5),
+          "pos_embed": rn(1, 1 + pos_grid ** 2, w, std=0.2), "norm.weight": un(w), "norm.bias": rn(w, std=0.05)}
+    for l in range(depth):
+        p = f"blocks.{l}."
+        sd.update({p + "norm1.weight": un(w), p + "norm1.bias": rn(w, std=0.05),
+                   p + "attn.qkv.weight": rn(3 * w, w, std=1.5 / math.sqrt(w)), p + "attn.qkv.bias": rn(3 * w, std=0.05),
+                   p + "attn.proj.weight": rn(w, w, std=1.0 / math.sqrt(w)), p + "attn.proj.bias": rn(w),
+                   p + "ls1.gamma": un(w, lo=0.2, hi=1.0), p + "norm2.weight": un(w), p + "norm2.bias": rn(w, std=0.05),
+                   p + "mlp.fc1.weight": rn(md, w, std=1.0 / math.sqrt(w)), p + "mlp.fc1.bias": rn(md, std=0.05),
+                   p + "mlp.fc2.weight": rn(w, md, std=1.0 / math.sqrt(md)), p + "mlp.fc2.bias": rn(w),
+                   p + "ls2.gamma": un(w, lo=0.2, hi=1.0)})
+    return sd
+
+
+def _from_hf(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """transformers.Dinov2Model names -> dinov2-hub names."""
+    out = {"cls_token": sd["embeddings.cls_token"], "pos_embed": sd["embeddings.position_embeddings"],
+           "patch_embed.proj.weight": sd["embeddings.patch_embeddings.projection.weight"],
+           "patch_embed.proj.bias": sd["embeddings.patch_embeddings.projection.bias"],
+           "norm.weight": sd["layernorm.weight"], "norm.bias": sd["layernorm.bias"]}
+    l = 0
+    while f"encoder.layer.{l}.norm1.weight" in sd:
+        q, p = f"encoder.layer.{l}.", f"blocks.{l}."
+        out[p + "attn.qkv.weight"] = torch.cat([sd[q + f"attention.attention.{n}.weight"] for n in ("query", "key", "value")], 0)
+        out[p + "attn.qkv.bias"] = torch.cat([sd[q + f"attention.attention.{n}.bias"] for n in ("query", "key", "value")], 0)
+        out[p + "attn.proj.weight"], out[p + "attn.proj.bias"] = sd[q + "attention.output.dense.weight"], sd[q + "attention.output.dense.bias"]
+        out[p + "ls1.gamma"], out[p + "ls2.gamma"] = sd[q + "layer_scale1.lambda1"], sd[q + "layer_scale2.lambda1"]
+        for n in ("norm1", "norm2"):
+            out[p + n + ".weight"], out[p + n + ".bias"] = sd[q + n + ".weight"], sd[q + n + ".bias"]
+        for n in ("fc1", "fc2"):
+            out[p + f"mlp.{n}.weight"], out[p + f"mlp.{n}.bias"] = sd[q + f"mlp.{n}.weight"], sd[q + f"mlp.{n}.bias"]
+        l += 1
+    return out
+
+
+class ViTFeaturizer:
+    """DINOv2 ViT (+ FeatUp ChannelNorm) on the device: uint8 images in, (B, 16, patch_w, C) float32 token grid out."""
+
+    def __init__(self, model: str = "vits14", state_dict: Optional[Dict[str, torch.Tensor]] = None, *, seed: int = 0,
+                 channel_norm: bool = True, patch_h: int = 16, ln_eps: float = 1e-6, cn_eps: float = 1e-4, device=None):
+        if model not in PRESETS:
+            raise ValueError(f"Unsupported foundation model: {model}")  # image_features.py:52-54
+        self.depth, self.width, self.heads = PRESETS[model]
+        self.model_name, self.patch, self.patch_h = model, 14, patch_h
+        self.ctx = api.get_context(device)
+        cfg = _lib.VitConfig(self.depth, self.width, self.heads, 4 * self.width, 14, patch_h, int(channel_norm), ln_eps, cn_eps,
+                             (C.c_float * 3)(*IMAGENET_MEAN), (C.c_float * 3)(*IMAGENET_STD))
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.vfmreg_vit_create(self.ctx.handle, C.byref(cfg), C.byref(h)), "vfmreg_vit_create")
+        self.handle = h
+        self._grids = set()
+        sd = state_dict if state_dict is not None else random_state_dict(model, seed)
+        if "embeddings.cls_token" in sd:
+            sd = _from_hf(sd)
+        self.load_state_dict(sd)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        self._pos_embed = sd["pos_embed"].detach().float().cpu()
+        self._grids.clear()
+        for name, t in sd.items():
+            if name in ("pos_embed", "mask_token") or name.endswith("mask_token"):
+                continue
+            a = np.ascontiguousarray(t.detach().float().cpu().numpy()).reshape(-1)
+            _lib.check(self.ctx.lib.vfmreg_vit_set_weight(self.handle, name.encode(), a.ctypes.data, a.size), f"set_weight({name})")
+
+    def _ensure_pos(self, gh: int, gw: int) -> None:
+        if (gh, gw) in self._grids:
+            return
+        pe = self._pos_embed
+        g = int(round(math.sqrt(pe.shape[1] - 1)))
+        patch_pos = pe[0, 1:]
+        if (gh, gw) != (g, g):  # bicubic, align_corners=False (dinov2 / transformers interpolate_pos_encoding)
+            patch_pos = F.interpolate(patch_pos.reshape(1, g, g, -1).permute(0, 3, 1, 2), size=(gh, gw), mode="bicubic",
+                                      align_corners=False).permute(0, 2, 3, 1).reshape(gh * gw, -1)
+        table = np.ascontiguousarray(torch.cat([pe[0, :1], patch_pos], 0).numpy(), dtype=np.float32)
+        _lib.check(self.ctx.lib.vfmreg_vit_set_pos_embed(self.handle, gh, gw, table.ctypes.data), "vfmreg_vit_set_pos_embed")
+        self._grids.add((gh, gw))
+
+    def grid(self, img_h: int, img_w: int):
+        gh, gw = C.c_int32(), C.c_int32()
+        _lib.check(self.ctx.lib.vfmreg_vit_grid(self.handle, img_h, img_w, C.byref(gh), C.byref(gw)))
+        return gh.value, gw.value
+
+    def forward(self, images) -> torch.Tensor:
+        """images: (B, H, W, 3) uint8 (ndarray or tensor, host or device) -> (B, gh, gw, C) float32 CUDA tensor."""
+        dev = torch.device("cuda", self.ctx.device)
+        if isinstance(images, np.ndarray):
+            images = torch.from_numpy(np.ascontiguousarray(images))
+        if images.dim() == 3:
+            images = images[None]
+        if images.dim() != 4 or images.shape[-1] != 3 or images.dtype != torch.uint8:
+            raise ValueError(f"Invalid shape for images: {tuple(images.shape)} {images.dtype} (expected (B, H, W, 3) uint8)")
+        images = images.to(dev).contiguous()
+        b, h, w, _ = images.shape
+        gh, gw = self.grid(h, w)
+        self._ensure_pos(gh, gw)
+        out = torch.empty((b, gh, gw, self.width), dtype=torch.float32, device=dev)
+        self.ctx.bind_stream()
+        _lib.check(self.ctx.lib.vfmreg_vit_forward(self.handle, C.c_void_p(images.data_ptr()), b, h, w, C.c_void_p(out.data_ptr())),
+                   "vfmreg_vit_forward")
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.vfmreg_vit_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ImageFeatureGenerator:
+    """Drop-in for vfm_reg.image_features.ImageFeatureGenerator (image_features.py:23-117), dinov2 only.
+
+    ``get_image_features(image, upsample=False)`` returns the (16, patch_w, C) token grid as a NumPy array like the
+    reference; ``upsample=True`` returns the (H, W, C) bilinear map of :104-108 -- kept for compatibility, but the
+    B200 path never needs it: ``create_descriptors`` / ``extract_features`` sample the token grid directly."""
+
+    def __init__(self, foundation_model: str = "dinov2", use_featup: bool = False, *, model: str = "vits14",
+                 state_dict=None, seed: int = 0, device=None):
+        if foundation_model != "dinov2":
+            raise ValueError(f"Unsupported foundation model: {foundation_model}")
+        if use_featup:
+            raise NotImplementedError("the FeatUp upsampler is not on the hot path (use_featup=False, registration_node.py:57)")
+        self.foundation_model_name, self.use_featup = foundation_model, use_featup
+        self.patch_size, self.patch_h = 14, 16
+        self.vit = ViTFeaturizer(model, state_dict, seed=seed, device=device)
+        self.feature_size = self.vit.width
+
+    def get_image_features(self, image: np.ndarray, upsample: bool = False, cache_file: str = "") -> np.ndarray:
+        tok = self.vit.forward(image)[0]
+        if upsample:
+            tok = F.interpolate(tok.permute(2, 0, 1)[None], image.shape[:2], mode="bilinear", align_corners=False)[0].permute(1, 2, 0)
+        return tok.cpu().numpy()
+
+
+def extract_features(images, points, K, T_cam_from_lidar, *, featurizer: Optional[ViTFeaturizer] = None, model: str = "vits14",
+                     crop=None, reject_black: bool = True, state_dict=None, seed: int = 0, device=None) -> torch.Tensor:
+    """Per-point descriptors (N, D) float32 (CUDA tensor): DINOv2 patch features of B surround images sampled at the
+    projection of every LiDAR point; zeros for unseen points; the first camera that sees a point wins
+    (prepare_scenes.py:50-107 with project_pcl_to_image of dataloader/nclt.py:311-366).
+
+    images (B, H, W, 3) uint8; points (N, 3) float32 in the LiDAR frame; K (B, 3, 3); T_cam_from_lidar (B, 4, 4)."""
+    if featurizer is None:
+        featurizer = ViTFeaturizer(model, state_dict, seed=seed, device=device)
+    if isinstance(images, torch.Tensor):
+        images_np = None
+        imgs_t = images
+    else:
+        images_np = np.ascontiguousarray(images, dtype=np.uint8)
+        imgs_t = torch.from_numpy(images_np)
+    if imgs_t.dim() != 4 or imgs_t.shape[-1] != 3:
+        raise ValueError(f"Invalid shape for images: {tuple(imgs_t.shape)}")
+    b, h, w, _ = imgs_t.shape
+    K = np.asarray(K, dtype=np.float64).reshape(b, 3, 3)
+    T = np.asarray(T_cam_from_lidar, dtype=np.float64).reshape(b, 4, 4)
+    tokens = featurizer.forward(imgs_t)
+    gh, gw = tokens.shape[1:3]
+    cams = [api.CameraSpec(P=K[i] @ T[i][:3], img_hw=(h, w), grid_hw=(gh, gw), crop=crop, black_mode=1 if reject_black else 0)
+            for i in range(b)]
+    dev_imgs = imgs_t.to(tokens.device)
+    desc, _, _ = api.project_gather(points, cams, [tokens[i] for i in range(b)], [dev_imgs[i] for i in range(b)] if reject_black else None,
+                                    device=featurizer.ctx.device)
+    return desc
+
+
+def create_descriptors(images: Dict[str, np.ndarray], project_params: Dict[str, api.CameraSpec], feature_generator, pcl: np.ndarray,
+                       ) -> np.ndarray:
+    """prepare_scenes.py:50-107 on a dict of camera images: returns (N, C) float32 descriptors (zeros where unseen).
+    ``project_params[camera]`` carries what ``sequence.project_pcl_to_image`` would compute (projection, crop, rot90 ...)."""
+    vit = feature_generator.vit if isinstance(feature_generator, ImageFeatureGenerator) else feature_generator
+    cams, toks, imgs = [], [], []
+    for cam, image in images.items():
+        t = vit.forward(image)[0]
+        spec = project_params[cam]
+        spec.grid_hw = tuple(t.shape[:2])
+        cams.append(spec)
+        toks.append(t)
+        imgs.append(image)
+    desc, _, _ = api.project_gather(np.asarray(pcl, dtype=np.float32)[:, :3], cams, toks, imgs, device=vit.ctx.device)
+    return desc.cpu().numpy()
