@@ -214,3 +214,22 @@ def test_compat_shim_reference_layout(vfm):
         node.ransac_registration(vmap_arr, scan_arr, "bogus")
     with pytest.raises(ValueError, match="Invalid shape"):
         vm.get_vfm_correspondences(scan_arr[:, :10], 0.8)
+
+
+def test_register_batch_equals_sequential(vfm):
+    """The double-buffered batch entry point returns exactly what per-pair calls return (different sizes per pair)."""
+    pairs, want = [], []
+    for i, (m, n) in enumerate(((3000, 1000), (2000, 1500), (4096, 700), (1000, 1000), (2500, 300))):
+        s = synth.make_pair(50 + i, m, n, 128)
+        pr = (s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"])
+        pairs.append(pr)
+        want.append(vfm.register(*pr, min_cos=0.8, mutual=True, ransac_iters=1024, inlier_thresh=1.0, seed=9))
+    got = vfm.register_batch(pairs, min_cos=0.8, mutual=True, ransac_iters=1024, inlier_thresh=1.0, seed=9)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert np.array_equal(g.T, w.T) and np.array_equal(g.corr, w.corr) and np.array_equal(g.inlier_mask, w.inlier_mask)
+        assert g.best_hyp == w.best_hyp and g.fitness == w.fitness and g.rmse == w.rmse
+    # run it twice more: stage reuse across batches
+    again = vfm.register_batch(pairs[::-1], min_cos=0.8, mutual=True, ransac_iters=1024, inlier_thresh=1.0, seed=9)
+    for g, w in zip(again, want[::-1]):
+        assert np.array_equal(g.T, w.T) and np.array_equal(g.corr, w.corr)

@@ -25,7 +25,7 @@ from . import _lib
 from ._lib import VfmRegError
 
 __all__ = ["Context", "get_context", "match_nn", "filter_correspondences", "ransac_kabsch", "register", "RegResult",
-           "MatchResult", "RansacResult", "VfmRegError", "CameraSpec", "project_gather"]
+           "MatchResult", "RansacResult", "VfmRegError", "CameraSpec", "project_gather", "register_batch"]
 
 _ALGO = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}
 
@@ -293,6 +293,54 @@ def register(source_pcd, target_pcd, src_feats, tgt_feats, *, normalize: bool = 
     return RegResult(T=np.array(res.T, dtype=np.float64).reshape(4, 4), corr=corr_np, inlier_mask=mask_np,
                      fitness=float(res.fitness), rmse=float(res.rmse), best_hyp=int(res.best_hyp),
                      n_inliers=int(res.n_inliers))
+
+
+def register_batch(pairs, *, normalize: bool = True, min_cos: Optional[float] = 0.8, mutual: bool = False,
+                   ratio: Optional[float] = None, ransac_iters: int = 50000, inlier_thresh: float = 1e4, seed: int = 42,
+                   refit: bool = False, algo: str = "auto", device=None):
+    """``register`` over a list of (source_pcd, target_pcd, src_feats, tgt_feats) HOST arrays with the copy of pair i+1
+    overlapped with the solve of pair i (``vfmreg_register_batch_host``).  Returns a list of RegResult.  Pinned inputs
+    (``torch.Tensor.pin_memory().numpy()``) make the copies asynchronous."""
+    ctx = get_context(device)
+    k = len(pairs)
+    if k == 0:
+        return []
+    p = _params(normalize, min_cos, mutual, ratio, ransac_iters, inlier_thresh, seed, refit, algo)
+
+    def h(x, name, cols=None):
+        x = x.numpy() if isinstance(x, torch.Tensor) else x
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or (cols is not None and x.shape[1] != cols):
+            raise ValueError(f"Invalid shape for {name}: {x.shape}")
+        return x
+
+    keep, ns, ms = [], [], []
+    d = None
+    for (sx, tx, sf, tf) in pairs:
+        sx, tx, sf = h(sx, "source_pcd", 3), h(tx, "target_pcd", 3), h(sf, "src_feats")
+        d = sf.shape[1] if d is None else d
+        tf = h(tf, "tgt_feats", d)
+        if sf.shape != (sx.shape[0], d) or tf.shape[0] != tx.shape[0]:
+            raise ValueError("Invalid shape: points / descriptors mismatch")
+        keep.append((sx, tx, sf, tf))
+        ns.append(sx.shape[0])
+        ms.append(tx.shape[0])
+    corr = [torch.empty((n, 2), dtype=torch.int32).pin_memory() for n in ns]
+    mask = [torch.empty(n, dtype=torch.uint8).pin_memory() for n in ns]
+    arr = lambda ptrs: (C.c_void_p * k)(*ptrs)  # noqa: E731
+    res = (_lib.RegisterResult * k)()
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_register_batch_host(
+        ctx.handle, k, arr([x[0].ctypes.data for x in keep]), arr([x[1].ctypes.data for x in keep]),
+        arr([x[2].ctypes.data for x in keep]), arr([x[3].ctypes.data for x in keep]), (C.c_int64 * k)(*ns), (C.c_int64 * k)(*ms), d,
+        C.byref(p), None, arr([t.data_ptr() for t in corr]), arr([t.data_ptr() for t in mask]), res), "vfmreg_register_batch_host")
+    out = []
+    for i in range(k):
+        kc = int(res[i].n_corr)
+        out.append(RegResult(T=np.array(res[i].T, dtype=np.float64).reshape(4, 4), corr=corr[i][:kc].numpy().copy(),
+                             inlier_mask=mask[i][:kc].numpy().astype(bool), fitness=float(res[i].fitness), rmse=float(res[i].rmse),
+                             best_hyp=int(res[i].best_hyp), n_inliers=int(res[i].n_inliers)))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -175,6 +175,14 @@ void vfmreg_destroy(vfmreg_ctx* ctx) {
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->hbuf) cudaFree(ctx->hbuf);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(ctx->ev_ready[i]);
+      cudaEventDestroy(ctx->ev_consumed[i]);
+    }
+  }
   for (int g = 0; g < NUM_GROUPS; ++g) {
     cudaEventDestroy(ctx->ev0[g]);
     cudaEventDestroy(ctx->ev1[g]);
@@ -257,44 +265,43 @@ int vfmreg_ransac(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int
                       counts, sumq, mask, stats);
 }
 
-static int register_impl(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
-                         const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p,
-                         const int32_t* sample_idx, int32_t* corr_dev, uint8_t* mask_dev, bool outputs_on_host,
-                         int32_t* corr_host, uint8_t* mask_host, vfmreg_register_result* result) {
+struct RegOut {
+  double* T;        // device, 16
+  int64_t* stats;   // device, 8 (stats[0..3] + correspondence count as int32 at [4])
+  int32_t* corr;    // device, n x 2
+  uint8_t* mask;    // device, n
+};
+
+static size_t register_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p) {
+  const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
+  (void)mutual;
+  return match_scratch(ctx, n, m, d, p->flags) + ransac_scratch((int32_t)n, p->n_hyp) + arena_bytes(n, 4) * 3 + arena_bytes(m, 4) +
+         arena_bytes((size_t)n * 2, 4) + arena_bytes(n, 1) + arena_bytes(16, 8) + arena_bytes(8, 8) + 4096;
+}
+
+// Enqueue the whole path on ctx->stream (no host synchronisation).  The arena must already be reserved.
+static int register_enqueue(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
+                            const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p,
+                            const int32_t* sample_idx, const RegOut& out) {
   const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
   const bool use_ratio = !(p->ratio != p->ratio);
-  const size_t need = match_scratch(ctx, n, m, d, p->flags) + ransac_scratch((int32_t)n, p->n_hyp) +
-                      arena_bytes(n, 4) * 3 + arena_bytes(m, 4) + arena_bytes((size_t)n * 2, 4) + arena_bytes(n, 1) +
-                      arena_bytes(16, 8) + arena_bytes(8, 8) + 4096;
-  VFM_TRY(arena_reserve(ctx, need));
   int32_t* idx01 = arena_take<int32_t>(ctx, n);
   float* sim01 = arena_take<float>(ctx, n);
   float* sec01 = arena_take<float>(ctx, n);
   int32_t* idx10 = mutual ? arena_take<int32_t>(ctx, m) : nullptr;
-  int32_t* corr = corr_dev ? corr_dev : arena_take<int32_t>(ctx, (size_t)n * 2);
-  uint8_t* mask = mask_dev ? mask_dev : arena_take<uint8_t>(ctx, n);
-  double* T = arena_take<double>(ctx, 16);
-  int64_t* stats = arena_take<int64_t>(ctx, 8);  // stats[0..3] + count at [4] (int32 view)
-  if (!idx01 || !sim01 || !sec01 || !corr || !mask || !T || !stats || (mutual && !idx10)) {
+  if (!idx01 || !sim01 || !sec01 || (mutual && !idx10)) {
     set_error("register: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
-  int32_t* count = reinterpret_cast<int32_t*>(stats + 4);
+  int32_t* count = reinterpret_cast<int32_t*>(out.stats + 4);
   VFM_TRY(match_nn_impl(ctx, src_feats, n, tgt_feats, m, d, p->flags, idx01, sim01, use_ratio ? sec01 : nullptr, idx10,
                         nullptr, nullptr));
-  VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, idx10, n, p->min_cos, p->ratio, mutual, corr, count));
-  VFM_TRY(ransac_solve(ctx, src_xyz, tgt_xyz, 0, corr, count, (int32_t)n, sample_idx, p->n_hyp, p->seed, p->inlier_thresh,
-                       p->refit, T, nullptr, nullptr, mask, stats));
-  // small results -> pinned host staging -> caller
-  VFM_TRY(ensure_pinned(ctx, 256));
-  char* pin = static_cast<char*>(ctx->pinned);
-  VFM_CUDA(cudaMemcpyAsync(pin, T, 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  VFM_CUDA(cudaMemcpyAsync(pin + 128, stats, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (outputs_on_host) {
-    if (corr_host) VFM_CUDA(cudaMemcpyAsync(corr_host, corr, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (mask_host) VFM_CUDA(cudaMemcpyAsync(mask_host, mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, idx10, n, p->min_cos, p->ratio, mutual, out.corr, count));
+  return ransac_solve(ctx, src_xyz, tgt_xyz, 0, out.corr, count, (int32_t)n, sample_idx, p->n_hyp, p->seed, p->inlier_thresh,
+                      p->refit, out.T, nullptr, nullptr, out.mask, out.stats);
+}
+
+static void fill_result(vfmreg_register_result* result, const char* pin, double thresh) {
   memcpy(result->T, pin, 16 * sizeof(double));
   const int64_t* st = reinterpret_cast<const int64_t*>(pin + 128);
   result->best_hyp = st[0];
@@ -302,8 +309,36 @@ static int register_impl(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt
   result->sumq = st[2];
   result->n_corr = st[3];
   result->fitness = st[3] > 0 ? (double)st[1] / (double)st[3] : 0.0;
-  const double tau2 = p->inlier_thresh * p->inlier_thresh;
+  const double tau2 = thresh * thresh;
   result->rmse = st[1] > 0 ? sqrt(((double)st[2] / 1099511627776.0) * tau2 / (double)st[1]) : 0.0;
+}
+
+static int register_impl(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
+                         const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p,
+                         const int32_t* sample_idx, int32_t* corr_dev, uint8_t* mask_dev, bool outputs_on_host,
+                         int32_t* corr_host, uint8_t* mask_host, vfmreg_register_result* result) {
+  VFM_TRY(arena_reserve(ctx, register_scratch(ctx, n, m, d, p)));
+  RegOut out;
+  out.corr = corr_dev ? corr_dev : arena_take<int32_t>(ctx, (size_t)n * 2);
+  out.mask = mask_dev ? mask_dev : arena_take<uint8_t>(ctx, n);
+  out.T = arena_take<double>(ctx, 16);
+  out.stats = arena_take<int64_t>(ctx, 8);
+  if (!out.corr || !out.mask || !out.T || !out.stats) {
+    set_error("register: scratch arena too small");
+    return VFMREG_ERR_ALLOC;
+  }
+  VFM_TRY(register_enqueue(ctx, src_xyz, tgt_xyz, src_feats, tgt_feats, n, m, d, p, sample_idx, out));
+  // small results -> pinned host staging -> caller
+  VFM_TRY(ensure_pinned(ctx, 256));
+  char* pin = static_cast<char*>(ctx->pinned);
+  VFM_CUDA(cudaMemcpyAsync(pin, out.T, 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  VFM_CUDA(cudaMemcpyAsync(pin + 128, out.stats, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (outputs_on_host) {
+    if (corr_host) VFM_CUDA(cudaMemcpyAsync(corr_host, out.corr, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask_host) VFM_CUDA(cudaMemcpyAsync(mask_host, out.mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  fill_result(result, pin, p->inlier_thresh);
   return VFMREG_OK;
 }
 
@@ -366,6 +401,104 @@ int vfmreg_register_host(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt
   arena_reset(ctx);
   return register_impl(ctx, d_sx, d_tx, d_sf, d_tf, n, m, d, params, d_si, nullptr, nullptr, true, corr_out, mask_out,
                        result);
+}
+
+
+int vfmreg_register_batch_host(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* src_xyz, const float* const* tgt_xyz,
+                               const float* const* src_feats, const float* const* tgt_feats, const int64_t* n, const int64_t* m,
+                               int32_t d, const vfmreg_register_params* params, const int32_t* const* sample_idx,
+                               int32_t* const* corr_out, uint8_t* const* mask_out, vfmreg_register_result* results) {
+  VFM_CHECK_ARG(ctx && n_pairs > 0 && src_xyz && tgt_xyz && src_feats && tgt_feats && n && m && params && results,
+                "register_batch_host: null pointer / empty batch");
+  size_t stage_bytes = 0, scratch = 0;
+  int64_t n_max = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    VFM_TRY(check_register_args(ctx, src_xyz[i], tgt_xyz[i], src_feats[i], tgt_feats[i], n[i], m[i], d, params, results + i));
+    const size_t b = arena_bytes((size_t)n[i] * 3, 4) + arena_bytes((size_t)m[i] * 3, 4) + arena_bytes((size_t)n[i] * d, 4) +
+                     arena_bytes((size_t)m[i] * d, 4) + (sample_idx ? arena_bytes((size_t)params->n_hyp * 3, 4) : 0);
+    stage_bytes = b > stage_bytes ? b : stage_bytes;
+    const size_t sc = register_scratch(ctx, n[i], m[i], d, params);
+    scratch = sc > scratch ? sc : scratch;
+    n_max = n[i] > n_max ? n[i] : n_max;
+  }
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    VFM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+      VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+    }
+  }
+  // persistent device buffer: 2 input stages + 2 (corr, mask) output stages + per-pair (T, stats) slots
+  const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
+  const size_t total = 2 * stage_bytes + 2 * out_bytes + (size_t)n_pairs * 256;
+  if (total > ctx->hbuf_cap) {
+    VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    VFM_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->hbuf) VFM_CUDA(cudaFree(ctx->hbuf));
+    ctx->hbuf = nullptr;
+    ctx->hbuf_cap = 0;
+    cudaError_t e = cudaMalloc(&ctx->hbuf, total);
+    if (e != cudaSuccess) {
+      set_error("register_batch_host: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+      return VFMREG_ERR_ALLOC;
+    }
+    ctx->hbuf_cap = total;
+  }
+  arena_reset(ctx);
+  VFM_TRY(arena_reserve(ctx, scratch));
+  VFM_TRY(ensure_pinned(ctx, (size_t)n_pairs * 256));
+  char* slots = ctx->hbuf + 2 * stage_bytes + 2 * out_bytes;
+
+  struct Staged { float *sx, *tx, *sf, *tf; int32_t* si; };
+  auto stage_ptrs = [&](int i, int buf) {
+    char* p = ctx->hbuf + (size_t)buf * stage_bytes;
+    Staged s;
+    s.sx = (float*)p; p += arena_bytes((size_t)n[i] * 3, 4);
+    s.tx = (float*)p; p += arena_bytes((size_t)m[i] * 3, 4);
+    s.sf = (float*)p; p += arena_bytes((size_t)n[i] * d, 4);
+    s.tf = (float*)p; p += arena_bytes((size_t)m[i] * d, 4);
+    s.si = (sample_idx && sample_idx[i]) ? (int32_t*)p : nullptr;
+    return s;
+  };
+  auto enqueue_h2d = [&](int i) -> int {
+    const int buf = i & 1;
+    if (i >= 2) VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));  // stage free again
+    const Staged s = stage_ptrs(i, buf);
+    VFM_CUDA(cudaMemcpyAsync(s.sx, src_xyz[i], (size_t)n[i] * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VFM_CUDA(cudaMemcpyAsync(s.tx, tgt_xyz[i], (size_t)m[i] * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VFM_CUDA(cudaMemcpyAsync(s.sf, src_feats[i], (size_t)n[i] * d * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VFM_CUDA(cudaMemcpyAsync(s.tf, tgt_feats[i], (size_t)m[i] * d * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (s.si) VFM_CUDA(cudaMemcpyAsync(s.si, sample_idx[i], (size_t)params->n_hyp * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VFM_CUDA(cudaEventRecord(ctx->ev_ready[buf], ctx->copy_stream));
+    return VFMREG_OK;
+  };
+  // the previous batch may still be reading the stages: order this batch's first copies after everything enqueued so far
+  VFM_CUDA(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
+  VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[0], 0));
+  VFM_TRY(enqueue_h2d(0));
+  for (int i = 0; i < n_pairs; ++i) {
+    const int buf = i & 1;
+    if (i + 1 < n_pairs) VFM_TRY(enqueue_h2d(i + 1));  // overlaps with the compute of pair i
+    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[buf], 0));
+    const Staged s = stage_ptrs(i, buf);
+    RegOut out;
+    char* ob = ctx->hbuf + 2 * stage_bytes + (size_t)buf * out_bytes;
+    out.corr = (int32_t*)ob;
+    out.mask = (uint8_t*)(ob + arena_bytes((size_t)n_max * 2, 4));
+    out.T = (double*)(slots + (size_t)i * 256);
+    out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
+    arena_reset(ctx);
+    VFM_TRY(register_enqueue(ctx, s.sx, s.tx, s.sf, s.tf, n[i], m[i], d, params, s.si, out));
+    VFM_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+    if (corr_out && corr_out[i])
+      VFM_CUDA(cudaMemcpyAsync(corr_out[i], out.corr, (size_t)n[i] * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask_out && mask_out[i]) VFM_CUDA(cudaMemcpyAsync(mask_out[i], out.mask, (size_t)n[i], cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, (size_t)n_pairs * 256, cudaMemcpyDeviceToHost, ctx->stream));
+  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_pairs; ++i) fill_result(results + i, static_cast<const char*>(ctx->pinned) + (size_t)i * 256, params->inlier_thresh);
+  return VFMREG_OK;
 }
 
 }  // extern "C"

@@ -64,6 +64,9 @@ struct vfmreg_ctx {
   // persistent device buffers for register_host (inputs), grown on demand
   char* hbuf = nullptr;
   size_t hbuf_cap = 0;
+  // register_batch_host: second stream + events for the double-buffered H2D / compute pipeline
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready[2] = {}, ev_consumed[2] = {};
 };
 
 namespace vfm {

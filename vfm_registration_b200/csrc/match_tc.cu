@@ -302,39 +302,69 @@ __device__ __forceinline__ float canon_dot(const float* __restrict__ x, const fl
   return acc;
 }
 
-// Re-rank, step 1: one thread per candidate entry.  The row's recording threshold is rebuilt from the per-slot approximate
-// top-2 (second largest of all slot bests / runner-ups, minus the margin); surviving candidates get their canonical fp32
-// score written over the approximate one, the others are marked -inf.  The fmaf chain over k is sequential by
-// definition, so the parallelism is across (row, candidate) pairs; the query row is a warp-wide broadcast load.
+// Re-rank, step 1a: one thread per (query row, slot) rebuilds the row's recording threshold from the per-slot approximate
+// top-2 (second largest of all slot bests / runner-ups, minus the margin), marks the candidates below it -inf and appends
+// the survivors (typically 1-3 per row) to a compact work list (one atomic per warp).
 __global__ void __launch_bounds__(128)
-    rerank_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int dp, int slots,
-                      const uint8_t* __restrict__ nz, float* __restrict__ cand_v, const int* __restrict__ cand_i,
-                      const int* __restrict__ cand_n, const float2* __restrict__ slot_top2) {
+    rerank_select_kernel(int n, int slots, const uint8_t* __restrict__ nz, float* __restrict__ cand_v, const int* __restrict__ cand_n,
+                         const float2* __restrict__ slot_top2, int* __restrict__ work, int* __restrict__ work_count) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long per_row = (long long)slots * CAP;
-  if (g >= (long long)n * per_row) return;
-  const int row = (int)(g / per_row);
-  const int rem = (int)(g - (long long)row * per_row);
-  const int slot = rem / CAP, e = rem - slot * CAP;
-  if (!nz[row]) return;
-  const int cn = cand_n[(long long)row * slots + slot];
-  if (e >= (cn & 0xFFFF)) return;
-  float t1 = -INFINITY, t2 = -INFINITY;
-  bool overflow = false;
-  for (int s = 0; s < slots; ++s) {
-    const int c = cand_n[(long long)row * slots + s];
-    if ((c & 0xFFFF) == 0 && !((c >> 30) & 1)) continue;
-    overflow |= (c >> 30) & 1;
-    const float2 t = slot_top2[(long long)row * slots + s];
-    if (t.x > t1) { t2 = fmaxf(t1, t.y); t1 = t.x; } else { t2 = fmaxf(t2, t.x); }
+  const int lane = threadIdx.x & 31;
+  int keep[CAP];
+  int n_keep = 0;
+  if (g < (long long)n * slots) {
+    const int cnt = cand_n[g] & 0xFFFF;
+    const int row = (int)(g / slots);
+    if (cnt > 0 && nz[row]) {
+      float t1 = -INFINITY, t2 = -INFINITY;
+      bool overflow = false;
+      for (int s = 0; s < slots; ++s) {
+        const int c = cand_n[(long long)row * slots + s];
+        if ((c & 0xFFFF) == 0 && !((c >> 30) & 1)) continue;
+        overflow |= (c >> 30) & 1;
+        const float2 t = slot_top2[(long long)row * slots + s];
+        if (t.x > t1) { t2 = fmaxf(t1, t.y); t1 = t.x; } else { t2 = fmaxf(t2, t.x); }
+      }
+      if (!overflow) {  // overflowed rows are redone exactly
+        const float thr = t2 - MARGIN;
+#pragma unroll
+        for (int e = 0; e < CAP; ++e) {
+          if (e < cnt) {
+            if (cand_v[g * CAP + e] >= thr) keep[n_keep++] = e;
+            else cand_v[g * CAP + e] = -INFINITY;
+          }
+        }
+      }
+    }
   }
-  if (overflow) return;  // the whole row is redone exactly
-  const float v = cand_v[g];
-  if (!(v >= t2 - MARGIN)) {
-    cand_v[g] = -INFINITY;
-    return;
+  // warp-aggregated append
+  int incl = n_keep;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
   }
-  cand_v[g] = canon_dot(a + (long long)row * dp, b + (long long)cand_i[g] * dp, dp);
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 31 && total > 0) base = atomicAdd(work_count, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  int o = base + incl - n_keep;
+#pragma unroll
+  for (int e = 0; e < CAP; ++e)
+    if (e < n_keep) work[o + e] = (int)(g * CAP + keep[e]);
+}
+
+// Re-rank, step 1b: one thread per surviving candidate computes its canonical fp32 score (the fmaf chain over k is
+// sequential by definition; the parallelism is across candidates) and writes it over the approximate one.
+__global__ void __launch_bounds__(128)
+    rerank_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int dp, int slots, float* __restrict__ cand_v,
+                      const int* __restrict__ cand_i, const int* __restrict__ work, const int* __restrict__ work_count) {
+  const int count = *work_count;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
+    const int ent = work[w];
+    const int row = ent / (slots * CAP);
+    cand_v[ent] = canon_dot(a + (long long)row * dp, b + (long long)cand_i[ent] * dp, dp);
+  }
 }
 
 // Re-rank, step 2: one thread per query row picks the exact top-2 (lowest index on ties); rows whose list overflowed are
@@ -486,7 +516,7 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m) {
 size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m) {
   const TcPlan p = tc_plan(ctx, n, m);
   return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
-         arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + 1024;
+         arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + arena_bytes((size_t)n * p.slots * CAP + 1, 4) + 1024;
 }
 
 // a32/b32: renormalised fp32 rows (n x dp), a16/b16: their fp16 copies, nz_a: non-zero flags of the query rows.
@@ -500,12 +530,14 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   int* cand_n = arena_take<int>(ctx, (size_t)n * plan.slots);
   float2* slot_top2 = arena_take<float2>(ctx, (size_t)n * plan.slots);
   int* redo = arena_take<int>(ctx, (size_t)n + 1);  // [0] = count, [1..] = rows
-  if (!cand_v || !cand_i || !cand_n || !slot_top2 || !redo) {
+  int* work = arena_take<int>(ctx, (size_t)n * plan.slots * CAP + 1);  // [0] = count, [1..] = candidate entries to re-score
+  if (!cand_v || !cand_i || !cand_n || !slot_top2 || !redo || !work) {
     set_error("match_tc: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
   VFM_CUDA(cudaMemsetAsync(cand_n, 0, sizeof(int) * (size_t)n * plan.slots, ctx->stream));
   VFM_CUDA(cudaMemsetAsync(redo, 0, sizeof(int), ctx->stream));
+  VFM_CUDA(cudaMemsetAsync(work, 0, sizeof(int), ctx->stream));
   CUtensorMap map_a, map_b;
   VFM_TRY(make_map_f16(&map_a, a16, n, dp, TBM));
   VFM_TRY(make_map_f16(&map_b, b16, m, dp, TBN));
@@ -530,9 +562,10 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   match_tc_kernel<<<plan.grid, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(map_a, map_b, P);
   VFM_TRY(launch_check(ctx, "match_tc_kernel"));
   group_end(ctx, GROUP_MATCH, 1);
-  const long long entries = (long long)n * plan.slots * CAP;
-  rerank_dot_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>(a32, b32, (int)n, dp, plan.slots, nz_a, cand_v, cand_i, cand_n,
-                                                                    slot_top2);
+  const long long entries = (long long)n * plan.slots;
+  rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, plan.slots, nz_a, cand_v, cand_n, slot_top2, work + 1, work);
+  VFM_TRY(launch_check(ctx, "rerank_select_kernel"));
+  rerank_dot_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work + 1, work);
   VFM_TRY(launch_check(ctx, "rerank_dot_kernel"));
   rerank_pick_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(n, (int)m, plan.slots, nz_a, cand_v, cand_i, cand_n, idx, best, sec,
                                                                redo + 1, redo);
