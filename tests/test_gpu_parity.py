@@ -233,3 +233,63 @@ def test_register_batch_equals_sequential(vfm):
     again = vfm.register_batch(pairs[::-1], min_cos=0.8, mutual=True, ransac_iters=1024, inlier_thresh=1.0, seed=9)
     for g, w in zip(again, want[::-1]):
         assert np.array_equal(g.T, w.T) and np.array_equal(g.corr, w.corr)
+
+
+def test_config1_full_vs_oracle(vfm):
+    """BASELINE configs[0]: 4096 x 4096 points, 384-d, 1024 RANSAC iterations, no mutual filter -- the reference's own
+    CPU-runnable case, compared end to end with the oracle (C restatement bit-exact, NumPy float64 within 1e-4)."""
+    s = synth.make_pair(1, 4096, 4096, 384)
+    r = vfm.register(s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"], min_cos=0.8, ransac_iters=1024, inlier_thresh=1.0, seed=1)
+    m = cref.match_nn(s["scan_feat"], s["map_feat"])
+    o = match.match_nn(s["scan_feat"], s["map_feat"])
+    clear = (o["sim01"] - o["sec01"]) > 1e-5
+    assert clear.mean() > 0.99 and np.array_equal(m["idx01"][clear], o["idx01"][clear])
+    corr = match.filter_correspondences(m["idx01"], m["sim01"], min_cos=0.8)
+    assert np.array_equal(r.corr, corr)
+    c = cref.ransac(s["scan_xyz"], s["map_xyz"], corr, None, 1.0, seed=1, n_hyp=1024)
+    assert r.best_hyp == c["best"] and np.array_equal(r.T, c["T"]) and np.array_equal(r.inlier_mask, c["mask"])
+    on = ransac.ransac(s["scan_xyz"], s["map_xyz"], corr, ransac.sample_indices(1, 1024, len(corr)), 1.0)
+    assert np.linalg.norm(r.T - on["T"]) < 1e-4 and np.array_equal(r.inlier_mask, on["mask"])
+    rte, rre = synth.pose_errors(r.T, s["T_gt"])
+    assert rte < 1.0 and rre < 5.0
+
+
+def test_config4_shape_ratio_test_768d(vfm):
+    """BASELINE configs[3] semantics (768-d, ratio test, many hypotheses) at a size the oracle finishes in seconds, plus
+    the full 200k x 20k x 768 size through a size-independent property: tensor-core path == exact fp32 path, bit for bit."""
+    s = synth.make_pair(4, 20000, 4000, 768, sigma_f=0.02)
+    kw = dict(min_cos=None, ratio=0.9, ransac_iters=16384, inlier_thresh=1.0, seed=4)
+    r = vfm.register(s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"], **kw)
+    m = cref.match_nn(s["scan_feat"], s["map_feat"])
+    corr = match.filter_correspondences(m["idx01"], m["sim01"], m["sec01"], ratio=0.9)
+    assert np.array_equal(r.corr, corr) and 800 < len(corr) < 4000
+    c = cref.ransac(s["scan_xyz"], s["map_xyz"], corr, None, 1.0, seed=4, n_hyp=16384)
+    assert r.best_hyp == c["best"] and np.array_equal(r.T, c["T"]) and np.array_equal(r.inlier_mask, c["mask"])
+    rte, rre = synth.pose_errors(r.T, s["T_gt"])
+    assert rte < 1.0 and rre < 5.0
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn(20000, 768, device="cuda", generator=g)
+    b = torch.randn(200000, 768, device="cuda", generator=g)
+    t = vfm.match_nn(a, b, algo="tc")
+    e = vfm.match_nn(a, b, algo="simt")
+    assert torch.equal(t.idx01, e.idx01) and torch.equal(t.sim01, e.sim01) and torch.equal(t.sec01, e.sec01)
+
+
+def test_full_size_ransac_properties(vfm):
+    """configs[1]/[3] RANSAC sizes through size-independent properties: planted SE(3) is recovered, the winner's count equals
+    the mask population, re-running is deterministic, and doubling the hypothesis budget never lowers the best count."""
+    s = synth.make_pair(6, 200_000, 20_000, 16)
+    inl = np.nonzero(s["perm"] >= 0)[0]
+    rng = np.random.default_rng(0)
+    k = 20_000
+    j = np.where(s["perm"] >= 0, s["perm"], rng.integers(0, 200_000, k))
+    corr = np.stack([np.arange(k), j], 1).astype(np.int32)
+    r1 = vfm.ransac_kabsch(s["scan_xyz"], s["map_xyz"], corr, n_hyp=32768, seed=7, thresh=1.0)
+    r2 = vfm.ransac_kabsch(s["scan_xyz"], s["map_xyz"], corr, n_hyp=65536, seed=7, thresh=1.0)
+    r3 = vfm.ransac_kabsch(s["scan_xyz"], s["map_xyz"], corr, n_hyp=65536, seed=7, thresh=1.0)
+    assert r2.n_inliers >= r1.n_inliers and int(r2.mask.sum()) == r2.n_inliers
+    assert r2.best == r3.best and np.array_equal(r2.T, r3.T) and torch.equal(r2.counts, r3.counts)
+    assert torch.equal(r2.counts[:32768], r1.counts)
+    assert r2.n_inliers >= 0.95 * len(inl)
+    rte, rre = synth.pose_errors(r2.T, s["T_gt"])
+    assert rte < 0.2 and rre < 0.5
