@@ -242,9 +242,15 @@ def main():
     # warm-up launches are included in the event total, so divide by the launches actually recorded
     avg_ms = match_ms / max(match_launches, 1)
     achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_match_tc.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     roofline = {"bound": "tensor", "kernel": "descriptor N x M match (one search direction per launch)",
                 "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
-                "peak_source": f"{peaks['source']} bf16 burst", "traffic": None, "avg_launch_ms": avg_ms,
+                "peak_source": f"{peaks['source']} bf16 burst", "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                "algorithmic_bytes": alg_bytes_per_launch, "avg_launch_ms": avg_ms,
                 "launches_timed": match_launches, "algorithmic_gbs": alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9,
                 "share_of_step": (match_ms / max(match_launches, 1)) * 2 * P / (ms_dev / args.steps),
                 "ransac_score_avg_ms": ransac_ms / max(ransac_launches, 1)}

@@ -20,6 +20,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
           "-Xptxas", "-v"]
 # per-file extra flags; ransac.cu spells every fused multiply-add explicitly (bit parity with the C oracle)
 EXTRA = {"ransac.cu": ["-fmad=false"], "project.cu": ["-fmad=false"]}
+# tuning knobs: VFM_NVCC_DEFS="-DVFM_TBN=128 -DVFM_EPI_WARPS=4" python -m vfm_registration_b200.build --force
+EXTRA_ALL = os.environ.get("VFM_NVCC_DEFS", "").split()
 
 
 def _nvcc() -> str:
@@ -54,7 +56,7 @@ def build_all(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, src[:-3] + ".o")
         if not force and not _stale(obj, [os.path.join(CSRC, src)] + headers):
             return obj, ""
-        cmd = [nvcc, "-c", os.path.join(CSRC, src), "-o", obj, "-ccbin", "/usr/bin/g++"] + ARCH + COMMON + EXTRA.get(src, [])
+        cmd = [nvcc, "-c", os.path.join(CSRC, src), "-o", obj, "-ccbin", "/usr/bin/g++"] + ARCH + COMMON + EXTRA.get(src, []) + EXTRA_ALL
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -27,21 +27,36 @@
 // 64-wide K chunk per tile (both operands streamed).
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace vfm {
 
-constexpr int TBM = 128, TBN = 256, TBK = 64, STAGES = 4, UMMA_K = 16;
+#ifndef VFM_TBN
+#define VFM_TBN 256
+#endif
+#ifndef VFM_EPI_WARPS
+#define VFM_EPI_WARPS 4
+#endif
+constexpr int TBM = 128, TBN = VFM_TBN, TBK = 64, UMMA_K = 16;
+constexpr int STAGES = (TBN == 256) ? 4 : 6;
+constexpr int NBUF = 512 / TBN;          // accumulator buffers in TMEM
 constexpr int CAP = 16;                 // candidate list entries per (row, slot)
 constexpr float MARGIN = 3e-3f;
-constexpr int TC_THREADS = 192;
+// Epilogue warps: 4 (one per TMEM lane quarter) or 8 (warps w and w+4 share a lane quarter -- the hardware ties lanes
+// to warp_id % 4 -- and split the tile's columns; each (row, column group) then keeps its own candidate list, i.e.
+// HALVES device slots per (row, CTA span)).  Measured on B200: 4 and 8 warps perform alike (the epilogue cost is the
+// candidate bookkeeping, not issue bandwidth), so the default is 4.
+constexpr int EPI_WARPS = VFM_EPI_WARPS, EPI_THREADS = EPI_WARPS * 32;
+constexpr int HALVES = EPI_WARPS / 4;     // column groups per tile (warps sharing a TMEM lane quarter split the columns)
+constexpr int COLS_PER_WARP = TBN / HALVES;
+constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr uint32_t A_STAGE_BYTES = TBM * TBK * 2, B_STAGE_BYTES = TBN * TBK * 2;
 constexpr uint32_t SMEM_RING_V = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-constexpr uint32_t SMEM_RING_I = SMEM_RING_V + 128 * CAP * 4;
-constexpr uint32_t SMEM_SCR = SMEM_RING_I + 128 * CAP * 4;   // 32 x 128 floats: slow-path staging of one chunk
-constexpr uint32_t SMEM_BARS = SMEM_SCR + 32 * 128 * 4;
+constexpr uint32_t SMEM_RING_I = SMEM_RING_V + EPI_THREADS * CAP * 4;
+constexpr uint32_t SMEM_BARS = SMEM_RING_I + EPI_THREADS * CAP * 4;
 constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 256 + 1024;  // + slack for 1024-byte alignment
 
 constexpr uint32_t IDESC = umma_idesc_f16(TBM, TBN, 0);  // fp16 operands
@@ -57,10 +72,13 @@ struct TcParams {
   int* cand_i;
   int* cand_n;           // [n][slots]: count | overflow << 30
   float2* slot_top2;     // [n][slots]: approximate (best, runner-up) of the slot's column span
+  long long* dbg;        // optional per-CTA cycle counters (tuning aid): [cta][8]
+  int top1;              // 1: only the best match is needed (runner-up value not requested): threshold = best - margin
 };
 
-__device__ __forceinline__ void flush_slot(const TcParams& P, int rb, int tid, float* ring_v, int* ring_i, int cnt, bool ovf,
-                                           float best, float second) {
+__device__ __forceinline__ void flush_slot(const TcParams& P, int rb, int tid, int half, float* ring_v, int* ring_i, int cnt,
+                                           bool ovf, float best, float second) {
+  const int etid = half * 128 + tid;
   const int row = rb * TBM + tid;
   if (row >= P.n) return;
   // first CTA whose span [total*c/grid, total*(c+1)/grid) contains this row block's first tile
@@ -69,36 +87,37 @@ __device__ __forceinline__ void flush_slot(const TcParams& P, int rb, int tid, f
   long long c0 = (t0 * g) / P.total_tiles;
   while ((P.total_tiles * (c0 + 1)) / g <= t0) ++c0;
   while (c0 > 0 && (P.total_tiles * c0) / g > t0) --c0;
-  const int slot = (int)(blockIdx.x - c0);
+  const int slot = (int)(blockIdx.x - c0) * HALVES + half;
   const long long o = ((long long)row * P.slots + slot);
   P.cand_n[o] = cnt | (ovf ? (1 << 30) : 0);
   P.slot_top2[o] = make_float2(best, second);
   for (int e = 0; e < cnt; ++e) {
-    P.cand_v[o * CAP + e] = ring_v[e * 128 + tid];
-    P.cand_i[o * CAP + e] = ring_i[e * 128 + tid];
+    P.cand_v[o * CAP + e] = ring_v[e * EPI_THREADS + etid];
+    P.cand_i[o * CAP + e] = ring_i[e * EPI_THREADS + etid];
   }
 }
 
 // Record one candidate (approximate score v of column `col`) in the thread's list and raise the recording threshold.
+template <bool TOP1>
 __device__ __forceinline__ void push_candidate(float v, int col, int tid, float* ring_v, int* ring_i, float& best, float& second,
                                                float& thr, int& cnt, bool& ovf) {
   if (cnt == CAP) {  // compact: keep what is still above the (risen) threshold
     int w = 0;
 #pragma unroll 1
     for (int e = 0; e < CAP; ++e) {
-      const float ev = ring_v[e * 128 + tid];
-      const int ei = ring_i[e * 128 + tid];
+      const float ev = ring_v[e * EPI_THREADS + tid];
+      const int ei = ring_i[e * EPI_THREADS + tid];
       if (ev > thr) {
-        ring_v[w * 128 + tid] = ev;
-        ring_i[w * 128 + tid] = ei;
+        ring_v[w * EPI_THREADS + tid] = ev;
+        ring_i[w * EPI_THREADS + tid] = ei;
         ++w;
       }
     }
     cnt = w;
   }
   if (cnt < CAP) {
-    ring_v[cnt * 128 + tid] = v;
-    ring_i[cnt * 128 + tid] = col;
+    ring_v[cnt * EPI_THREADS + tid] = v;
+    ring_i[cnt * EPI_THREADS + tid] = col;
     ++cnt;
   } else {
     ovf = true;
@@ -109,16 +128,25 @@ __device__ __forceinline__ void push_candidate(float v, int col, int tid, float*
   } else if (v > second) {
     second = v;
   }
-  thr = second - MARGIN;
+  thr = (TOP1 ? best : second) - MARGIN;
 }
 
-// One 32-column chunk of a query row (r[i] = approximate score of column col_base + c0 + i).
-// Fast path: a max tree and one compare (register only).  When the maximum clears the recording threshold the lane
-// locates it and counts how many values clear the threshold, still in registers; the usual case (exactly one) is a
-// single push.  Only the rare chunk with several qualifying values is parked in shared memory and walked by a rolled
-// loop, which keeps the kernel small enough for the instruction cache.
-__device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid, int col_base, int tid, float* scr, float* ring_v,
-                                           int* ring_i, float& best, float& second, float& thr, int& cnt, bool& ovf) {
+__device__ __forceinline__ float tc_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __uint_as_float(r);
+}
+
+// One 32-column chunk of a query row (r[i] = approximate score of column col_base + c0 + i; the chunk sits at TMEM
+// address `t_chunk`).  Fast path: a 3-input max tree and one compare, registers only.  When the maximum clears the
+// recording threshold the lane locates it and counts how many values clear the threshold, still in registers; the usual
+// case (exactly one) is a single push.  The rare chunk with several qualifying values is re-read from TMEM one column at
+// a time by the whole warp (tcgen05.ld is warp-collective), which keeps the kernel small enough for the instruction cache
+// and needs no shared-memory staging.  `tid` is the thread's index among the epilogue threads.
+template <bool TOP1>
+__device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid, int col_base, int tid, uint32_t t_chunk,
+                                           float* ring_v, int* ring_i, float& best, float& second, float& thr, int& cnt, bool& ovf) {
   if (c0 >= valid) return;  // warp-uniform
   const bool partial = c0 + 32 > valid;  // warp-uniform: columns >= valid hold zeros (TMA out-of-bounds fill)
   float m0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), m1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
@@ -131,6 +159,13 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid,
     m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
   }
   const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  bool multi = false;
+  if (thr == -INFINITY && !partial) {
+    // Nothing recorded yet in this span: seed the threshold from this chunk.  TOP1: its maximum.  Otherwise a lower bound
+    // of its second largest value: the smaller of two disjoint group maxima (m0/m2 cover i % 4 in {0, 2}, m1/m3 the rest).
+    const float seed = TOP1 ? mx : fminf(fmaxf(m0, m2), fmaxf(m1, m3));
+    thr = seed - MARGIN;   // strictly below `seed`, so the values that define it are still recorded below
+  }
   if (mx > thr) {
     int n_above = 0, imax = 0;
 #pragma unroll
@@ -139,19 +174,46 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid,
       n_above += (v > thr) ? 1 : 0;
       imax = (v == mx) ? i : imax;
     }
-    if (n_above == 1 && !partial) {
-      push_candidate(mx, col_base + c0 + imax, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) scr[i * 128 + tid] = __uint_as_float(r[i]);
-      const int lim = min(32, valid - c0);
+    if (n_above == 1 && !partial)
+      push_candidate<TOP1>(mx, col_base + c0 + imax, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
+    else
+      multi = true;
+  }
+  if (__any_sync(0xffffffffu, multi)) {  // warp-uniform slow path
+    const int lim = min(32, valid - c0);
 #pragma unroll 1
-      for (int i = 0; i < lim; ++i) {
-        const float v = scr[i * 128 + tid];
-        if (v > thr) push_candidate(v, col_base + c0 + i, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
-      }
+    for (int i = 0; i < lim; ++i) {
+      const float v = tc_ld1(t_chunk + i);
+      if (multi && v > thr) push_candidate<TOP1>(v, col_base + c0 + i, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
     }
   }
+}
+
+// The epilogue of one warp's share of an accumulator tile (COLS_PER_WARP columns starting at TMEM address t_addr /
+// database column col_base): 32-column chunks, the next one in flight while the current one is scanned.
+template <bool TOP1>
+__device__ __forceinline__ void epilogue_half(uint32_t t_addr, int col_base, int m, int etid, float* ring_v, int* ring_i,
+                                              float& best, float& second, float& thr, int& cnt, bool& ovf) {
+  const int valid = min(COLS_PER_WARP, m - col_base);   // may be <= 0 for the padded part of the last tile
+  uint32_t ra[32], rbuf[32];
+  tc_ld32(t_addr, ra);
+#pragma unroll 1
+  for (int c = 0; c < COLS_PER_WARP / 32; c += 2) {
+    tc_wait_ld();
+    tc_ld32(t_addr + (c + 1) * 32, rbuf);  // in flight while chunk c is scanned
+    scan_chunk<TOP1>(ra, c * 32, valid, col_base, etid, t_addr + c * 32, ring_v, ring_i, best, second, thr, cnt, ovf);
+    tc_wait_ld();
+    if (c + 2 < COLS_PER_WARP / 32) tc_ld32(t_addr + (c + 2) * 32, ra);
+    scan_chunk<TOP1>(rbuf, (c + 1) * 32, valid, col_base, etid, t_addr + (c + 1) * 32, ring_v, ring_i, best, second, thr, cnt, ovf);
+  }
+}
+
+__device__ __forceinline__ void epilogue_tile(bool top1, uint32_t t_addr, int col_base, int m, int etid, float* ring_v, int* ring_i,
+                                              float& best, float& second, float& thr, int& cnt, bool& ovf) {
+  if (top1)
+    epilogue_half<true>(t_addr, col_base, m, etid, ring_v, ring_i, best, second, thr, cnt, ovf);
+  else
+    epilogue_half<false>(t_addr, col_base, m, etid, ring_v, ring_i, best, second, thr, cnt, ovf);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -163,10 +225,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t sA = base, sB = base + STAGES * A_STAGE_BYTES;
   float* ring_v = reinterpret_cast<float*>(smem + SMEM_RING_V);
   int* ring_i = reinterpret_cast<int*>(smem + SMEM_RING_I);
-  float* scr = reinterpret_cast<float*>(smem + SMEM_SCR);
   const uint32_t bars = base + SMEM_BARS;
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 16 * STAGES + 32);
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 8 * NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 16 * STAGES + 16 * NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_begin = (P.total_tiles * blockIdx.x) / gridDim.x;
@@ -179,9 +240,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, 4);
+      mbar_init(tempty0 + 8 * b, EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -194,61 +255,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
+    {
       uint32_t stage = 0, phase = 0;
       for (long long t = t_begin; t < t_end; ++t) {
         const int rb = (int)(t / P.col_tiles), ct = (int)(t % P.col_tiles);
 #pragma unroll 1
         for (int kb = 0; kb < P.kb; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          mbar_expect_tx(full0 + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_2d(sA + stage * A_STAGE_BYTES, &map_a, full0 + 8 * stage, kb * TBK, rb * TBM);
-          tma_load_2d(sB + stage * B_STAGE_BYTES, &map_b, full0 + 8 * stage, kb * TBK, ct * TBN);
+          if (elect_one()) {
+            mbar_expect_tx(full0 + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
+            tma_load_2d(sA + stage * A_STAGE_BYTES, &map_a, full0 + 8 * stage, kb * TBK, rb * TBM);
+            tma_load_2d(sB + stage * B_STAGE_BYTES, &map_b, full0 + 8 * stage, kb * TBK, ct * TBN);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    {
       uint32_t stage = 0, phase = 0;
       long long it = 0;
+      const uint64_t da0 = umma_desc_k_sw128(sA), db0 = umma_desc_k_sw128(sB);
+      long long w_tempty = 0, w_full = 0, t_start = clock64();
       for (long long t = t_begin; t < t_end; ++t, ++it) {
-        const uint32_t buf = (uint32_t)(it & 1);
-        mbar_wait(tempty0 + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1);
+        const uint32_t buf = (uint32_t)(it % NBUF);
+        long long c0 = clock64();
+        mbar_wait(tempty0 + 8 * buf, (uint32_t)((it / NBUF) & 1) ^ 1);
+        w_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * TBN;
 #pragma unroll 1
         for (int kb = 0; kb < P.kb; ++kb) {
+          c0 = clock64();
           mbar_wait(full0 + 8 * stage, phase);
+          w_full += clock64() - c0;
           tc_fence_after();
-          const uint64_t da = umma_desc_k_sw128(sA + stage * A_STAGE_BYTES);
-          const uint64_t db = umma_desc_k_sw128(sB + stage * B_STAGE_BYTES);
+          if (elect_one()) {
+            const uint64_t da = da0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+            const uint64_t db = db0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < TBK / UMMA_K; ++k) {
-            // advancing 16 fp16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
-            tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TBK / UMMA_K; ++k) {
+              // advancing 16 fp16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
+              tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
+            if (kb == P.kb - 1) tc_commit(tfull0 + 8 * buf);  // accumulator complete -> epilogue
           }
-          tc_commit(empty0 + 8 * stage);  // frees the smem stage once these MMAs have read it
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull0 + 8 * buf);      // accumulator complete -> epilogue
+      }
+      if (P.dbg && lane == 0) {
+        P.dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
+        P.dbg[blockIdx.x * 8 + 1] = w_tempty;
+        P.dbg[blockIdx.x * 8 + 2] = w_full;
+        P.dbg[blockIdx.x * 8 + 3] = it;
       }
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
-    const int tid = q * 32 + lane;  // row inside the block == TMEM lane
+    // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int tid = q * 32 + lane;        // row inside the block == TMEM lane
+    const int etid = half * 128 + tid;    // index among the epilogue threads
     int cur_rb = -1;
     float best = -INFINITY, second = -INFINITY, thr = -INFINITY;
     int cnt = 0;
     bool ovf = false, active = false;
     long long it = 0;
+    long long w_tfull = 0, e_start = clock64();
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int rb = (int)(t / P.col_tiles), ct = (int)(t % P.col_tiles);
       if (rb != cur_rb) {
-        if (cur_rb >= 0) flush_slot(P, cur_rb, tid, ring_v, ring_i, cnt, ovf, best, second);
+        if (cur_rb >= 0) flush_slot(P, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second);
         cur_rb = rb;
         const int row = rb * TBM + tid;
         active = (row < P.n) && (P.nz[row] != 0);
@@ -257,31 +338,222 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         cnt = 0;
         ovf = false;
       }
-      const uint32_t buf = (uint32_t)(it & 1);
-      mbar_wait(tfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
+      const uint32_t buf = (uint32_t)(it % NBUF);
+      const long long c0 = clock64();
+      mbar_wait(tfull0 + 8 * buf, (uint32_t)((it / NBUF) & 1));
+      w_tfull += clock64() - c0;
       tc_fence_after();
-      const int col_base = ct * TBN;
-      const int valid = min(TBN, P.m - col_base);
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN;
-      uint32_t ra[32], rbuf[32];
-      tc_ld32(t_addr, ra);
-#pragma unroll 1
-      for (int c = 0; c < TBN / 32; c += 2) {
-        tc_wait_ld();
-        tc_ld32(t_addr + (c + 1) * 32, rbuf);  // in flight while chunk c is scanned
-        scan_chunk(ra, c * 32, valid, col_base, tid, scr, ring_v, ring_i, best, second, thr, cnt, ovf);
-        tc_wait_ld();
-        if (c + 2 < TBN / 32) tc_ld32(t_addr + (c + 2) * 32, ra);
-        scan_chunk(rbuf, (c + 1) * 32, valid, col_base, tid, scr, ring_v, ring_i, best, second, thr, cnt, ovf);
-      }
+      epilogue_tile(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * COLS_PER_WARP, ct * TBN + half * COLS_PER_WARP,
+                    P.m, etid, ring_v, ring_i, best, second, thr, cnt, ovf);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
-    if (cur_rb >= 0) flush_slot(P, cur_rb, tid, ring_v, ring_i, cnt, ovf, best, second);
+    if (P.dbg && warp == 2 && lane == 0) {
+      P.dbg[blockIdx.x * 8 + 4] = clock64() - e_start;
+      P.dbg[blockIdx.x * 8 + 5] = w_tfull;
+    }
+    if (cur_rb >= 0) flush_slot(P, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second);
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Version 2 of the candidate search for dp <= 384: CTA PAIRS (thread-block cluster of 2).
+//   * each CTA keeps its own 128-row query block RESIDENT in shared memory (dp/64 chunks of 16 KB, reloaded only when
+//     the row block changes), so only the database operand is streamed;
+//   * the two CTAs of a pair work on the same 256-column database tile at the same time; each TMA-loads one half of the
+//     tile (128 rows) and MULTICASTS it into both CTAs' shared memory, so every database byte crosses L2->SM once per pair;
+//   * L2->SM traffic per CTA and 64-wide K chunk drops from (128 + 256) x 128 B to 128 x 128 B.
+// Stage release needs both consumers: the MMA warps commit with a multicast arrive onto both CTAs' `empty` barriers
+// (count 2).  Everything after the MMA (TMEM double buffering, epilogue, candidate lists, slots) is as in version 1, with
+// "cluster" in place of "CTA" for the span / slot arithmetic.
+constexpr int STAGES2 = (TBN == 256) ? 3 : 5;
+constexpr int A_MAX_KB = 6;  // resident query block: up to 384 columns
+constexpr uint32_t B_HALF_BYTES = B_STAGE_BYTES / 2;
+constexpr uint32_t S2_A = 0;
+constexpr uint32_t S2_B = A_MAX_KB * A_STAGE_BYTES;
+constexpr uint32_t S2_RING_V = S2_B + STAGES2 * B_STAGE_BYTES;
+constexpr uint32_t S2_RING_I = S2_RING_V + EPI_THREADS * CAP * 4;
+constexpr uint32_t S2_BARS = S2_RING_I + EPI_THREADS * CAP * 4;
+constexpr uint32_t S2_TOTAL = S2_BARS + 256 + 1024;
+
+__device__ __forceinline__ void flush_slot2(const TcParams& P, int rb, int tid, int half, float* ring_v, int* ring_i, int cnt,
+                                            bool ovf, float best, float second, long long total_units, int units_per_rp) {
+  const int etid = half * 128 + tid;
+  const int row = rb * TBM + tid;
+  if (row >= P.n) return;
+  const long long t0 = (long long)(rb >> 1) * units_per_rp;   // first unit of this row-block pair
+  const long long g = gridDim.x >> 1;                        // clusters
+  long long c0 = (t0 * g) / total_units;
+  while ((total_units * (c0 + 1)) / g <= t0) ++c0;
+  while (c0 > 0 && (total_units * c0) / g > t0) --c0;
+  const int slot = (int)((blockIdx.x >> 1) - c0) * HALVES + half;
+  const long long o = ((long long)row * P.slots + slot);
+  P.cand_n[o] = cnt | (ovf ? (1 << 30) : 0);
+  P.slot_top2[o] = make_float2(best, second);
+  for (int e = 0; e < cnt; ++e) {
+    P.cand_v[o * CAP + e] = ring_v[e * EPI_THREADS + etid];
+    P.cand_i[o * CAP + e] = ring_i[e * EPI_THREADS + etid];
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    match_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sA = base + S2_A, sB = base + S2_B;
+  float* ring_v = reinterpret_cast<float*>(smem + S2_RING_V);
+  int* ring_i = reinterpret_cast<int*>(smem + S2_RING_I);
+  const uint32_t bars = base + S2_BARS;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES2, tfull0 = bars + 16 * STAGES2, tempty0 = tfull0 + 8 * NBUF;
+  const uint32_t afull = tempty0 + 8 * NBUF, aempty = afull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S2_BARS + 16 * STAGES2 + 16 * NBUF + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_cta_rank();
+  const long long clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int row_pairs = (P.n + 2 * TBM - 1) / (2 * TBM);
+  const long long total_units = (long long)row_pairs * P.col_tiles;
+  const long long u_begin = (total_units * cid) / clusters, u_end = (total_units * (cid + 1)) / clusters;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 2);   // both CTAs of the pair read every stage
+    }
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, EPI_WARPS);
+    }
+    mbar_init(afull, 1);
+    mbar_init(aempty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers must be initialised before any multicast can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
+    {
+      uint32_t stage = 0, phase = 0, aphase = 0;
+      int cur_rp = -1;
+      for (long long u = u_begin; u < u_end; ++u) {
+        const int rp = (int)(u / P.col_tiles), ct = (int)(u % P.col_tiles);
+        if (rp != cur_rp) {   // new resident query block
+          cur_rp = rp;
+          mbar_wait(aempty, aphase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(afull, (uint32_t)P.kb * A_STAGE_BYTES);
+            for (int kb = 0; kb < P.kb; ++kb)
+              tma_load_2d(sA + kb * A_STAGE_BYTES, &map_a, afull, kb * TBK, (2 * rp + (int)rank) * TBM);
+          }
+          __syncwarp();
+          aphase ^= 1;
+        }
+#pragma unroll 1
+        for (int kb = 0; kb < P.kb; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(full0 + 8 * stage, B_STAGE_BYTES);   // my half + the peer's half
+            tma_load_2d_mc(sB + stage * B_STAGE_BYTES + rank * B_HALF_BYTES, &map_b, full0 + 8 * stage, kb * TBK,
+                           ct * TBN + (int)rank * (TBN / 2), (uint16_t)3);
+          }
+          __syncwarp();
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    {
+      uint32_t stage = 0, phase = 0, aphase = 0;
+      long long it = 0;
+      int cur_rp = -1;
+      const uint64_t da0 = umma_desc_k_sw128(sA), db0 = umma_desc_k_sw128(sB);
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int rp = (int)(u / P.col_tiles);
+        const uint32_t buf = (uint32_t)(it % NBUF);
+        mbar_wait(tempty0 + 8 * buf, (uint32_t)((it / NBUF) & 1) ^ 1);
+        if (rp != cur_rp) {
+          cur_rp = rp;
+          mbar_wait(afull, aphase);
+          aphase ^= 1;
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * TBN;
+        const bool last_of_rp = (u + 1 == u_end) || ((int)((u + 1) / P.col_tiles) != rp);
+#pragma unroll 1
+        for (int kb = 0; kb < P.kb; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = da0 + (uint64_t)(kb * (A_STAGE_BYTES >> 4));
+            const uint64_t db = db0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < TBK / UMMA_K; ++k)
+              tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_mc(empty0 + 8 * stage, (uint16_t)3);   // frees the stage in both CTAs once these MMAs have read it
+            if (kb == P.kb - 1) {
+              tc_commit(tfull0 + 8 * buf);
+              if (last_of_rp) tc_commit(aempty);   // resident block may be overwritten after these MMAs
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (as in version 1) =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int tid = q * 32 + lane;
+    const int etid = half * 128 + tid;
+    int cur_rb = -1;
+    float best = -INFINITY, second = -INFINITY, thr = -INFINITY;
+    int cnt = 0;
+    bool ovf = false, active = false;
+    long long it = 0;
+    for (long long u = u_begin; u < u_end; ++u, ++it) {
+      const int rp = (int)(u / P.col_tiles), ct = (int)(u % P.col_tiles);
+      const int rb = 2 * rp + (int)rank;
+      if (rb != cur_rb) {
+        if (cur_rb >= 0) flush_slot2(P, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second, total_units, P.col_tiles);
+        cur_rb = rb;
+        const int row = rb * TBM + tid;
+        active = (row < P.n) && (P.nz[row] != 0);
+        best = second = -INFINITY;
+        thr = active ? -INFINITY : INFINITY;
+        cnt = 0;
+        ovf = false;
+      }
+      const uint32_t buf = (uint32_t)(it % NBUF);
+      mbar_wait(tfull0 + 8 * buf, (uint32_t)((it / NBUF) & 1));
+      tc_fence_after();
+      epilogue_tile(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * COLS_PER_WARP, ct * TBN + half * COLS_PER_WARP,
+                    P.m, etid, ring_v, ring_i, best, second, thr, cnt, ovf);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+    }
+    if (cur_rb >= 0) flush_slot2(P, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second, total_units, P.col_tiles);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
@@ -306,7 +578,7 @@ __device__ __forceinline__ float canon_dot(const float* __restrict__ x, const fl
 // top-2 (second largest of all slot bests / runner-ups, minus the margin), marks the candidates below it -inf and appends
 // the survivors (typically 1-3 per row) to a compact work list (one atomic per warp).
 __global__ void __launch_bounds__(128)
-    rerank_select_kernel(int n, int slots, const uint8_t* __restrict__ nz, float* __restrict__ cand_v, const int* __restrict__ cand_n,
+    rerank_select_kernel(int n, int slots, int top1, const uint8_t* __restrict__ nz, float* __restrict__ cand_v, const int* __restrict__ cand_n,
                          const float2* __restrict__ slot_top2, int* __restrict__ work, int* __restrict__ work_count) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -326,7 +598,7 @@ __global__ void __launch_bounds__(128)
         if (t.x > t1) { t2 = fmaxf(t1, t.y); t1 = t.x; } else { t2 = fmaxf(t2, t.x); }
       }
       if (!overflow) {  // overflowed rows are redone exactly
-        const float thr = t2 - MARGIN;
+        const float thr = (top1 ? t1 : t2) - MARGIN;
 #pragma unroll
         for (int e = 0; e < CAP; ++e) {
           if (e < cnt) {
@@ -498,23 +770,44 @@ static int make_map_f16(CUtensorMap* map, const void* ptr, int64_t rows, int dp,
 struct TcPlan {
   int row_blocks, col_tiles, grid, slots;
   long long total;
+  bool paired;   // version 2: CTA pairs, resident query block, multicast database tiles
 };
 
-static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m) {
+// VFMREG_MATCH_V1=1 in the environment keeps the single-CTA streaming kernel (A/B comparison while tuning)
+static bool g_force_v1 = [] { const char* e = getenv("VFMREG_MATCH_V1"); return e && e[0] == '1'; }();
+
+static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, int dp) {
   TcPlan p;
   p.row_blocks = ceil_div(n, TBM);
   p.col_tiles = ceil_div(m, TBN);
+  p.paired = !g_force_v1 && dp <= A_MAX_KB * TBK && p.row_blocks >= 2;
+  if (p.paired) {
+    const int row_pairs = ceil_div(n, 2 * TBM);
+    p.total = (long long)row_pairs * p.col_tiles;          // units of (row-block pair, column tile)
+    const int clusters = (int)((p.total < ctx->sm_count / 2) ? p.total : ctx->sm_count / 2);
+    p.grid = 2 * clusters;
+    const long long min_span = p.total / clusters;
+    p.slots = (int)((p.col_tiles + min_span - 1) / min_span) + 1;
+    if (p.slots > clusters) p.slots = clusters;
+    p.slots *= HALVES;   // column groups per span
+    return p;
+  }
   p.total = (long long)p.row_blocks * p.col_tiles;
   p.grid = (int)((p.total < ctx->sm_count) ? p.total : ctx->sm_count);
   // a row block of col_tiles consecutive tiles is cut by at most ceil(col_tiles / floor(total/grid)) + 1 spans
   const long long min_span = p.total / p.grid;
   p.slots = (int)((p.col_tiles + min_span - 1) / min_span) + 1;
   if (p.slots > p.grid) p.slots = p.grid;
+  p.slots *= HALVES;   // column groups per span
   return p;
 }
 
+void match_tc_force_v1(bool on) { g_force_v1 = on; }
+
 size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m) {
-  const TcPlan p = tc_plan(ctx, n, m);
+  TcPlan p = tc_plan(ctx, n, m, 64);
+  const TcPlan p1 = tc_plan(ctx, n, m, 1 << 20);
+  if (p1.slots > p.slots) p.slots = p1.slots;
   return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
          arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + arena_bytes((size_t)n * p.slots * CAP + 1, 4) + 1024;
 }
@@ -524,7 +817,7 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
              const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec) {
   VFM_CHECK_ARG(dp % TBK == 0, "match_tc: padded dim %d not a multiple of %d", dp, TBK);
   VFM_CHECK_ARG(n > 0 && m > 0 && n < (1LL << 30) && m < (1LL << 30), "match_tc: bad sizes");
-  const TcPlan plan = tc_plan(ctx, n, m);
+  const TcPlan plan = tc_plan(ctx, n, m, dp);
   float* cand_v = arena_take<float>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_i = arena_take<int>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_n = arena_take<int>(ctx, (size_t)n * plan.slots);
@@ -540,7 +833,7 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   VFM_CUDA(cudaMemsetAsync(work, 0, sizeof(int), ctx->stream));
   CUtensorMap map_a, map_b;
   VFM_TRY(make_map_f16(&map_a, a16, n, dp, TBM));
-  VFM_TRY(make_map_f16(&map_b, b16, m, dp, TBN));
+  VFM_TRY(make_map_f16(&map_b, b16, m, dp, plan.paired ? TBN / 2 : TBN));
   TcParams P;
   P.n = (int)n;
   P.m = (int)m;
@@ -553,17 +846,33 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   P.cand_i = cand_i;
   P.cand_n = cand_n;
   P.slot_top2 = slot_top2;
+  P.dbg = nullptr;
+  static const bool force_top1 = [] { const char* e = getenv("VFMREG_TC_TOP1"); return e && e[0] == '1'; }();  // tuning aid
+  P.top1 = (sec == nullptr || force_top1) ? 1 : 0;
+  static const bool want_dbg = [] { const char* e = getenv("VFMREG_TC_DEBUG"); return e && e[0] == '1'; }();
+  static long long* dbg_dev = nullptr;
+  if (want_dbg) {
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 1024 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, 1024 * 8 * sizeof(long long), ctx->stream);
+    P.dbg = dbg_dev;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     VFM_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    VFM_CUDA(cudaFuncSetAttribute(match_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_TOTAL));
     attr_set = true;
   }
   group_begin(ctx, GROUP_MATCH);
-  match_tc_kernel<<<plan.grid, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(map_a, map_b, P);
-  VFM_TRY(launch_check(ctx, "match_tc_kernel"));
+  if (plan.paired) {
+    match_tc2_kernel<<<plan.grid, TC_THREADS, S2_TOTAL, ctx->stream>>>(map_a, map_b, P);
+    VFM_TRY(launch_check(ctx, "match_tc2_kernel"));
+  } else {
+    match_tc_kernel<<<plan.grid, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(map_a, map_b, P);
+    VFM_TRY(launch_check(ctx, "match_tc_kernel"));
+  }
   group_end(ctx, GROUP_MATCH, 1);
   const long long entries = (long long)n * plan.slots;
-  rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, plan.slots, nz_a, cand_v, cand_n, slot_top2, work + 1, work);
+  rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, plan.slots, P.top1, nz_a, cand_v, cand_n, slot_top2, work + 1, work);
   VFM_TRY(launch_check(ctx, "rerank_select_kernel"));
   rerank_dot_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work + 1, work);
   VFM_TRY(launch_check(ctx, "rerank_dot_kernel"));
@@ -571,7 +880,18 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
                                                                redo + 1, redo);
   VFM_TRY(launch_check(ctx, "rerank_pick_kernel"));
   exact_rows_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(a32, b32, (int)m, dp, redo + 1, redo, idx, best, sec);
-  return launch_check(ctx, "exact_rows_kernel");
+  VFM_TRY(launch_check(ctx, "exact_rows_kernel"));
+  if (want_dbg) {
+    static long long host[1024 * 8];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(host, dbg_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    double acc[8] = {0};
+    for (int c = 0; c < plan.grid; ++c)
+      for (int k = 0; k < 8; ++k) acc[k] += (double)host[c * 8 + k] / plan.grid;
+    fprintf(stderr, "[tc dbg] grid=%d tiles/cta=%.1f | mma warp: total %.0f cyc, wait tempty %.0f, wait full %.0f | epi warp: total %.0f, wait tfull %.0f\n",
+            plan.grid, acc[3], acc[0], acc[1], acc[2], acc[4], acc[5]);
+  }
+  return VFMREG_OK;
 }
 
 }  // namespace vfm

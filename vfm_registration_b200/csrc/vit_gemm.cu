@@ -58,33 +58,36 @@ __global__ void __launch_bounds__(192, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0;
 #pragma unroll 1
-      for (int kb = 0; kb < kb_count; ++kb) {
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+    for (int kb = 0; kb < kb_count; ++kb) {
+      mbar_wait(empty0 + 8 * stage, phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(full0 + 8 * stage, GA_BYTES + GB_BYTES);
         tma_load_2d(sA + stage * GA_BYTES, &map_a, full0 + 8 * stage, kb * GBK, rb * GBM);
         tma_load_2d(sB + stage * GB_BYTES, &map_w, full0 + 8 * stage, kb * GBK, nb * GBN);
-        if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0;
+    const uint64_t da0 = umma_desc_k_sw128(sA), db0 = umma_desc_k_sw128(sB);
 #pragma unroll 1
-      for (int kb = 0; kb < kb_count; ++kb) {
-        mbar_wait(full0 + 8 * stage, phase);
-        tc_fence_after();
-        const uint64_t da = umma_desc_k_sw128(sA + stage * GA_BYTES);
-        const uint64_t db = umma_desc_k_sw128(sB + stage * GB_BYTES);
+    for (int kb = 0; kb < kb_count; ++kb) {
+      mbar_wait(full0 + 8 * stage, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = da0 + (uint64_t)(stage * (GA_BYTES >> 4));
+        const uint64_t db = db0 + (uint64_t)(stage * (GB_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < GBK / 16; ++k)
           tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), G_IDESC, (kb | k) != 0 ? 1u : 0u);
         tc_commit(empty0 + 8 * stage);
-        if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
+        if (kb == kb_count - 1) tc_commit(tfull);
       }
-      tc_commit(tfull);
+      __syncwarp();
+      if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = warp & 3;
