@@ -46,7 +46,101 @@ def bench_match(shapes=((10000, 50000, 384), (50000, 10000, 384), (4096, 4096, 3
                   f"= {fl / (gms / max(gl, 1)) / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def bench_ransac(shapes=((8192, 3000), (8192, 10000), (65536, 20000), (50000, 300))):
+    from vfm_registration_b200 import synth
+    ctx = v.get_context(0)
+    for h, k in shapes:
+        s = synth.make_pair(1, max(k, 4000), k, 8, inlier_frac=0.3)
+        rng = np.random.default_rng(0)
+        j = np.where(s["perm"] >= 0, s["perm"], rng.integers(0, len(s["map_xyz"]), k))
+        corr = torch.from_numpy(np.stack([np.arange(k), j], 1).astype(np.int32)).cuda()
+        sx, tx = torch.from_numpy(s["scan_xyz"]).cuda(), torch.from_numpy(s["map_xyz"]).cuda()
+        ctx.enable_timing(True)
+        ms = time_fn(lambda: v.ransac_kabsch(sx, tx, corr, n_hyp=h, seed=3, thresh=1.0), iters=5)
+        gms, gl = ctx.group_time_ms(1)
+        ctx.enable_timing(False)
+        sc = gms / max(gl, 1)
+        print(f"ransac H={h} K={k}: call {ms:.3f} ms, score kernel {sc:.3f} ms = {h * k / sc / 1e6:.1f} G(hyp*corr)/s, "
+              f"{h * k * 32 / sc / 1e9:.1f} TFLOP/s fp64-equivalent (16 DFMA-class ops per test), {h / ms / 1e3:.0f} M hyp/s", flush=True)
+
+
+def bench_project(n=2_000_000, d=384):
+    rng = np.random.default_rng(0)
+    pts = torch.from_numpy(np.c_[rng.uniform(-20, 20, (n, 2)), rng.uniform(-2, 4, n)].astype(np.float32)).cuda()
+    from scipy.spatial.transform import Rotation as R
+    cams, toks, imgs = [], [], []
+    for i in range(6):
+        t = np.eye(4)
+        t[:3, :3] = (R.from_euler("z", 60.0 * i, degrees=True) * R.from_euler("yx", [90, -90], degrees=True)).as_matrix().T
+        kmat = np.array([[200.0, 0, 112.0], [0, 200.0, 112.0], [0, 0, 1.0]])
+        cams.append(v.CameraSpec(P=kmat @ t[:3], img_hw=(224, 224), grid_hw=(16, 16), black_mode=1))
+        toks.append(torch.randn(16, 16, d, device="cuda"))
+        imgs.append(torch.randint(1, 255, (224, 224, 3), dtype=torch.uint8, device="cuda"))
+    ctx = v.get_context(0)
+    ctx.enable_timing(True)
+    ms = time_fn(lambda: v.project_gather(pts, cams, toks, imgs), iters=10)
+    gms, gl = ctx.group_time_ms(2)
+    ctx.enable_timing(False)
+    k = gms / max(gl, 1)
+    by = n * (12 + 4 * d + 12) + 6 * 256 * d * 4
+    print(f"project_gather N={n} D={d}: call {ms:.3f} ms, kernel {k:.3f} ms = {by / k / 1e6:.0f} GB/s algorithmic "
+          f"(12 B read + {4 * d} B desc + 12 B index written per point)", flush=True)
+
+
+def vit_flops(depth, w, t, tp, b):
+    """L (24 T W^2 + 4 T^2 W) + 2 T_p 588 W per image."""
+    return b * (depth * (24.0 * t * w * w + 4.0 * t * t * w) + 2.0 * tp * 588 * w)
+
+
+def bench_vit(batches=(6, 48)):
+    from vfm_registration_b200 import features
+    ctx = v.get_context(0)
+    rng = np.random.default_rng(0)
+    for model in ("vits14", "vitb14", "vitl14"):
+        depth, w, heads = features.PRESETS[model]
+        f = v.ViTFeaturizer(model, seed=1)
+        for b in batches:
+            imgs = torch.from_numpy(rng.integers(0, 255, (b, 224, 224, 3), dtype=np.uint8)).cuda()
+            ctx.enable_timing(True)
+            ms = time_fn(lambda: f.forward(imgs), iters=10)
+            gms, gl = ctx.group_time_ms(3)
+            ctx.enable_timing(False)
+            fl = vit_flops(depth, w, 257, 256, b)
+            print(f"vit {model} B={b} (224x224): forward {ms:.3f} ms = {b / ms * 1e3:.0f} img/s, {fl / ms / 1e9:.1f} TFLOP/s "
+                  f"({gl // 13} launches per forward)", flush=True)
+        del f
+
+
+def bench_extract(n=10000):
+    """BASELINE configs[2]: 6 x (224 x 224) surround images -> ViT -> projection gather for n points."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(0)
+    imgs = rng.integers(1, 255, (6, 224, 224, 3), dtype=np.uint8)
+    pts = np.c_[rng.uniform(-20, 20, (n, 2)), rng.uniform(-2, 4, n)].astype(np.float32)
+    k = np.stack([np.array([[200.0, 0, 112.0], [0, 200.0, 112.0], [0, 0, 1.0]])] * 6)
+    ts = []
+    for i in range(6):
+        t = np.eye(4)
+        t[:3, :3] = (R.from_euler("z", 60.0 * i, degrees=True) * R.from_euler("yx", [90, -90], degrees=True)).as_matrix().T
+        ts.append(t)
+    ts = np.stack(ts)
+    for model in ("vits14", "vitl14"):
+        f = v.ViTFeaturizer(model, seed=1)
+        imgs_d, pts_d = torch.from_numpy(imgs).cuda(), torch.from_numpy(pts).cuda()
+        ms = time_fn(lambda: v.extract_features(imgs_d, pts_d, k, ts, featurizer=f), iters=10)
+        ms_h = time_fn(lambda: v.extract_features(imgs, pts, k, ts, featurizer=f).cpu(), iters=10)
+        print(f"extract_features {model}: 6 images + {n} points: {ms:.3f} ms device-resident, {ms_h:.3f} ms from/to host", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "match"
     if what == "match":
         bench_match()
+    elif what == "ransac":
+        bench_ransac()
+    elif what == "project":
+        bench_project()
+    elif what == "vit":
+        bench_vit()
+    elif what == "extract":
+        bench_extract()

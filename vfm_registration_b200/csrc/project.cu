@@ -4,8 +4,8 @@
 // reference materialises (F.interpolate to (H, W, C), image_features.py:104-108: ~0.9 GB per NCLT image) is never built:
 // the value that map would hold at the integer pixel is computed from the 4 surrounding tokens.
 //
-// One warp per point.  The projection (float64, as NumPy does) is evaluated redundantly by all lanes for cameras in
-// order until one sees the point (first camera wins, prepare_scenes.py:97-101); the lanes then stride the channel
+// One warp per point.  Lane c evaluates the projection (float64, as NumPy does) into camera c, a ballot picks the first
+// camera that sees the point (first camera wins, prepare_scenes.py:97-101); the lanes then stride the channel
 // dimension with 128-bit loads of the L2-resident token grid and 128-bit streaming stores of the descriptor row.
 // HBM-bound: 12 B read + 4 d B written per point (unseen points are written as zeros, prepare_scenes.py:102-104).
 #include "common.cuh"
@@ -42,39 +42,39 @@ __global__ void __launch_bounds__(256)
   const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
   const double x = (double)points[i * 3 + 0], y = (double)points[i * 3 + 1], z = (double)points[i * 3 + 2];
-  int found = -1, fu = 0, fv = 0;
-  bool zero_feat = false;
-  for (int c = 0; c < n_cam && found < 0; ++c) {
-    const vfmreg_camera& cam = pack.cam[c].c;
+  // lane c projects the point into camera c (all cameras in parallel); the first camera that sees it wins
+  bool ok = false, black = false;
+  int u = 0, v = 0;
+  if (lane < n_cam) {
+    const vfmreg_camera& cam = pack.cam[lane].c;
     // q = P [x y z 1]^T, accumulated left to right like a NumPy row-times-column product
     const double q0 = ((cam.P[0] * x + cam.P[1] * y) + cam.P[2] * z) + cam.P[3];
     const double q1 = ((cam.P[4] * x + cam.P[5] * y) + cam.P[6] * z) + cam.P[7];
     const double q2 = ((cam.P[8] * x + cam.P[9] * y) + cam.P[10] * z) + cam.P[11];
-    if (cam.z_inclusive ? !(q2 >= 0.0) : !(q2 > 0.0)) continue;
+    ok = cam.z_inclusive ? (q2 >= 0.0) : (q2 > 0.0);
     const double xf = q0 / q2 / cam.subsample;
     const double yf = q1 / q2 / cam.subsample;
-    if (!(fabs(xf) < 1073741824.0) || !(fabs(yf) < 1073741824.0)) continue;  // also drops NaN / inf (z == 0)
-    if (cam.float_bounds) {
-      if (xf < 0.0 || xf > (double)cam.crop_w || yf < 0.0 || yf > (double)cam.crop_h) continue;
-    }
-    const int xi = (int)xf, yi = (int)yf;  // truncation toward zero == ndarray.astype(int)
-    if (xi < cam.crop_x0 || xi >= cam.crop_x0 + cam.crop_w || yi < cam.crop_y0 || yi >= cam.crop_y0 + cam.crop_h) continue;
-    const int u = xi - cam.crop_x0, v = yi - cam.crop_y0;
-    bool black = false;
-    if (cam.black_mode && images) {
+    ok = ok && (fabs(xf) < 1073741824.0) && (fabs(yf) < 1073741824.0);  // also drops NaN / inf (z == 0)
+    if (ok && cam.float_bounds) ok = !(xf < 0.0 || xf > (double)cam.crop_w || yf < 0.0 || yf > (double)cam.crop_h);
+    const int xi = ok ? (int)xf : 0, yi = ok ? (int)yf : 0;  // truncation toward zero == ndarray.astype(int)
+    ok = ok && !(xi < cam.crop_x0 || xi >= cam.crop_x0 + cam.crop_w || yi < cam.crop_y0 || yi >= cam.crop_y0 + cam.crop_h);
+    u = xi - cam.crop_x0;
+    v = yi - cam.crop_y0;
+    if (ok && cam.black_mode && images) {
       // (u, v) index the frame the projection lives in; the stored image is un-rotated
       const int r = cam.rot90 ? u : v;
       const int cc = cam.rot90 ? (cam.img_h - 1 - v) : u;
       const int stored_w = cam.rot90 ? cam.img_h : cam.img_w;
-      const uint8_t* px = images + pack.cam[c].img_off + ((int64_t)r * stored_w + cc) * 3;
+      const uint8_t* px = images + pack.cam[lane].img_off + ((int64_t)r * stored_w + cc) * 3;
       black = (px[0] | px[1] | px[2]) == 0;
     }
-    if (black && cam.black_mode == 1) continue;
-    found = c;
-    fu = u;
-    fv = v;
-    zero_feat = black;
+    if (black && cam.black_mode == 1) ok = false;   // a black pixel hides the point from this camera
   }
+  const unsigned seen = __ballot_sync(0xffffffffu, ok);
+  const int found = seen ? (__ffs(seen) - 1) : -1;
+  const int src_lane = found < 0 ? 0 : found;
+  const int fu = __shfl_sync(0xffffffffu, u, src_lane), fv = __shfl_sync(0xffffffffu, v, src_lane);
+  const bool zero_feat = __shfl_sync(0xffffffffu, (int)black, src_lane) != 0;
   if (lane == 0) {
     if (cam_of_point) cam_of_point[i] = found;
     if (uv) {

@@ -121,7 +121,9 @@ extern "C" {
 int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit** out) {
   VFM_CHECK_ARG(ctx && cfg && out, "vit_create: null pointer");
   VFM_CHECK_ARG(cfg->depth > 0 && cfg->heads > 0 && cfg->width == cfg->heads * 64, "vit_create: width must be heads * 64");
-  VFM_CHECK_ARG(cfg->width % 128 == 0 && cfg->width <= 1024 && cfg->mlp_dim % 128 == 0, "vit_create: unsupported width/mlp_dim");
+  VFM_CHECK_ARG(cfg->width % 128 == 0 && cfg->width <= 1024 && cfg->mlp_dim % 64 == 0, "vit_create: unsupported width/mlp_dim");
+  VFM_CHECK_ARG(vit_gemm_tile_n(cfg->width) && vit_gemm_tile_n(3 * cfg->width) && vit_gemm_tile_n(cfg->mlp_dim),
+                "vit_create: width, 3*width and mlp_dim must be multiples of 192 or 256");
   VFM_CHECK_ARG(cfg->patch > 0 && cfg->patch_h > 0, "vit_create: bad patch geometry");
   VFM_CUDA(cudaSetDevice(ctx->device));
   vfmreg_vit* v = new vfmreg_vit();
@@ -139,13 +141,13 @@ int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit*
     A(&l.ln2_g, w); A(&l.ln2_b, w); A(&l.fc1_b, md); A(&l.fc2_b, w); A(&l.ls2, w);
     A(&l.qkv_w, (size_t)3 * w * w); A(&l.proj_w, (size_t)w * w); A(&l.fc1_w, (size_t)md * w); A(&l.fc2_w, (size_t)w * md);
   }
-  if (rc == VFMREG_OK) rc = make_tmap_16bit(&v->m_pe, v->pe_w, w, v->kp, v->kp, 128, true);
+  if (rc == VFMREG_OK) rc = make_tmap_16bit(&v->m_pe, v->pe_w, w, v->kp, v->kp, vit_gemm_tile_n(w), true);
   for (Layer& l : v->layers) {
     if (rc != VFMREG_OK) break;
-    rc = make_tmap_16bit(&l.m_qkv, l.qkv_w, 3 * w, w, w, 128, true);
-    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_proj, l.proj_w, w, w, w, 128, true);
-    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc1, l.fc1_w, md, w, w, 128, true);
-    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc2, l.fc2_w, w, md, md, 128, true);
+    rc = make_tmap_16bit(&l.m_qkv, l.qkv_w, 3 * w, w, w, vit_gemm_tile_n(3 * w), true);
+    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_proj, l.proj_w, w, w, w, vit_gemm_tile_n(w), true);
+    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc1, l.fc1_w, md, w, w, vit_gemm_tile_n(md), true);
+    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc2, l.fc2_w, w, md, md, vit_gemm_tile_n(w), true);
   }
   if (rc != VFMREG_OK) {
     vfmreg_vit_destroy(v);

@@ -21,6 +21,8 @@ struct GemmEpilogue {
 };
 
 int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep);
+// output-tile width the GEMM uses for an N-column weight (256 or 192; 0 = unsupported): the weight's TMA box has that many rows
+int vit_gemm_tile_n(int n);
 
 // uint8 HWC images -> resized, normalised, im2col'ed bf16 patch matrix (B*np x kp) + CLS rows of the residual stream
 int vit_preprocess(vfmreg_ctx* ctx, const uint8_t* images, int b, int h, int w, int gh, int gw, int patch, const float* mean_std,
