@@ -180,10 +180,9 @@ def main():
     t_loc = torch.zeros((P, 4, 4), dtype=torch.float64, device=dev)
 
     def step(inputs, host=False):
-        if host:   # public host-buffer API: H2D of pair i+1 overlaps the solve of pair i inside the library
-            res = v.register_batch(inputs, **kw)
-        else:
-            res = [v.register(*inputs[p], **kw) for p in range(P)]
+        # host=True: pinned host buffers, H2D of pair i+1 overlaps the solve of pair i inside the library;
+        # host=False: device-resident inputs, all pairs enqueued back to back (one synchronisation per step)
+        res = v.register_batch(inputs, **kw)
         for p in range(P):
             t_loc[p].copy_(torch.from_numpy(res[p].T), non_blocking=False)
         if world > 1:

@@ -145,6 +145,14 @@ VFMREG_API int vfmreg_register_host(vfmreg_ctx* ctx, const float* src_xyz, const
                          const int32_t* sample_idx, int32_t* corr_out, uint8_t* mask_out,
                          vfmreg_register_result* result);
 
+/* A batch of independent pairs with DEVICE-resident inputs: all pairs are enqueued back to back on the context's stream
+ * and the host synchronises once at the end (no per-pair round trip).  corr_out[i] (n[i] x 2) / mask_out[i] (n[i]) are
+ * device pointers or NULL. */
+VFMREG_API int vfmreg_register_batch(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* src_xyz, const float* const* tgt_xyz,
+                          const float* const* src_feats, const float* const* tgt_feats, const int64_t* n, const int64_t* m,
+                          int32_t d, const vfmreg_register_params* params, const int32_t* const* sample_idx,
+                          int32_t* const* corr_out, uint8_t* const* mask_out, vfmreg_register_result* results);
+
 /* A batch of independent pairs with HOST buffers (what registration_node.py's scene loop, :587-588, iterates serially):
  * the host->device copy of pair i+1 runs on a second stream while pair i is being matched and solved (double-buffered
  * staging), results come back in one transfer at the end.  Arrays of n_pairs pointers / sizes; sample_idx, corr_out,

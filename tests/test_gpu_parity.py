@@ -229,6 +229,11 @@ def test_register_batch_equals_sequential(vfm):
     for g, w in zip(got, want):
         assert np.array_equal(g.T, w.T) and np.array_equal(g.corr, w.corr) and np.array_equal(g.inlier_mask, w.inlier_mask)
         assert g.best_hyp == w.best_hyp and g.fitness == w.fitness and g.rmse == w.rmse
+    dev_pairs = [tuple(torch.from_numpy(x).cuda() for x in pr) for pr in pairs]
+    gd = vfm.register_batch(dev_pairs, min_cos=0.8, mutual=True, ransac_iters=1024, inlier_thresh=1.0, seed=9)
+    for g, w in zip(gd, want):
+        assert np.array_equal(g.T, w.T) and np.array_equal(g.corr.cpu().numpy(), w.corr)
+        assert np.array_equal(g.inlier_mask.cpu().numpy(), w.inlier_mask) and g.best_hyp == w.best_hyp
     # run it twice more: stage reuse across batches
     again = vfm.register_batch(pairs[::-1], min_cos=0.8, mutual=True, ransac_iters=1024, inlier_thresh=1.0, seed=9)
     for g, w in zip(again, want[::-1]):

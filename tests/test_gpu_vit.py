@@ -92,3 +92,40 @@ def test_extract_features_end_to_end(vfm):
     assert np.array_equal(np.abs(desc).sum(1) > 0, seen)                 # identical visible set
     cos = (desc[seen] * want[seen]).sum(1) / (np.linalg.norm(desc[seen], axis=1) * np.linalg.norm(want[seen], axis=1))
     assert cos.min() > 0.999 and np.abs(desc - want).max() < 0.25        # bf16 ViT tolerance, as above
+
+
+def test_config3_images_to_transform(vfm):
+    """BASELINE configs[2] plumbing end to end: 6 surround images -> ViT -> projection gather for a 'map' cloud and for a
+    'scan' (a rigidly moved, noisy subset of it seen by the same rig) -> match -> RANSAC recovers the planted SE(3)."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(12)
+    b, h, w = 6, 224, 224
+    imgs = rng.integers(1, 255, (b, h, w, 3), dtype=np.uint8)
+    kmat = np.array([[200.0, 0, 112.0], [0, 200.0, 112.0], [0, 0, 1.0]])
+    ts = []
+    for i in range(b):
+        t = np.eye(4)
+        t[:3, :3] = (R.from_euler("z", 60.0 * i, degrees=True) * R.from_euler("yx", [90, -90], degrees=True)).as_matrix().T
+        ts.append(t)
+    ks, ts = np.stack([kmat] * b), np.stack(ts)
+    n_map, n_scan = 6000, 2000
+    map_xyz = np.c_[rng.uniform(-20, 20, (n_map, 2)), rng.uniform(-2, 4, n_map)].astype(np.float32)
+    f = vfm.ViTFeaturizer("vits14", seed=4)
+    map_desc = vfm.extract_features(imgs, map_xyz, ks, ts, featurizer=f)
+    sel = rng.permutation(n_map)[:n_scan]
+    t_gt = np.eye(4)
+    t_gt[:3, :3] = R.from_euler("zyx", [25.0, 1.0, -2.0], degrees=True).as_matrix()
+    t_gt[:3, 3] = [4.0, -3.0, 0.5]
+    t_inv = np.linalg.inv(t_gt)
+    # the scan is the same physical points expressed in the moved sensor frame; its descriptors come from the same pixels
+    scan_xyz = (map_xyz[sel].astype(np.float64) @ t_inv[:3, :3].T + t_inv[:3, 3] + rng.normal(0, 0.01, (n_scan, 3))).astype(np.float32)
+    scan_desc = map_desc[torch.from_numpy(sel).cuda()]
+    seen = (scan_desc.abs().sum(1) > 0).cpu().numpy()
+    assert seen.mean() > 0.3
+    r = vfm.register(torch.from_numpy(scan_xyz).cuda(), torch.from_numpy(map_xyz).cuda(), scan_desc, map_desc, min_cos=0.8,
+                     ransac_iters=4096, inlier_thresh=0.5, seed=3)
+    # unseen points carry zero descriptors: they can never pass the 0.8 cosine gate (VoxelHashMap.cpp:503)
+    assert set(r.corr[:, 0].tolist()) <= set(np.nonzero(seen)[0].tolist())
+    rte = np.linalg.norm(r.T[:3, 3] - t_gt[:3, 3])
+    rre = np.degrees(np.arccos(np.clip((np.trace(r.T[:3, :3].T @ t_gt[:3, :3]) - 1) / 2, -1, 1)))
+    assert rte < 0.2 and rre < 0.5, (rte, rre)

@@ -62,6 +62,7 @@ _SIGS = {
                                   _P, C.POINTER(RegisterResult)]),
     "vfmreg_register_host": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(RegisterParams), _P,
                                        _P, _P, C.POINTER(RegisterResult)]),
+    "vfmreg_register_batch": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(RegisterParams), _P, _P, _P, _P]),
     "vfmreg_register_batch_host": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(RegisterParams), _P, _P, _P,
                                              _P]),
     "vfmreg_project_gather": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Camera), C.c_int32, _P, C.POINTER(C.c_int64), _P,

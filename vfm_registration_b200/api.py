@@ -295,17 +295,55 @@ def register(source_pcd, target_pcd, src_feats, tgt_feats, *, normalize: bool = 
                      n_inliers=int(res.n_inliers))
 
 
+def _register_batch_device(ctx, pairs, p):
+    """CUDA-tensor inputs: everything is enqueued back to back, one host synchronisation per batch."""
+    dev = torch.device("cuda", ctx.device)
+    k = len(pairs)
+    keep, ns, ms = [], [], []
+    d = None
+    for (sx, tx, sf, tf) in pairs:
+        sx, tx, sf = _dev_f32(sx, dev, "source_pcd", 3), _dev_f32(tx, dev, "target_pcd", 3), _dev_f32(sf, dev, "src_feats")
+        d = sf.shape[1] if d is None else d
+        tf = _dev_f32(tf, dev, "tgt_feats", d)
+        if tuple(sf.shape) != (sx.shape[0], d) or tf.shape[0] != tx.shape[0]:
+            raise ValueError("Invalid shape: points / descriptors mismatch")
+        keep.append((sx, tx, sf, tf))
+        ns.append(sx.shape[0])
+        ms.append(tx.shape[0])
+    corr = [torch.empty((n, 2), dtype=torch.int32, device=dev) for n in ns]
+    mask = [torch.empty(n, dtype=torch.uint8, device=dev) for n in ns]
+    arr = lambda ptrs: (C.c_void_p * k)(*ptrs)  # noqa: E731
+    res = (_lib.RegisterResult * k)()
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_register_batch(
+        ctx.handle, k, arr([x[0].data_ptr() for x in keep]), arr([x[1].data_ptr() for x in keep]),
+        arr([x[2].data_ptr() for x in keep]), arr([x[3].data_ptr() for x in keep]), (C.c_int64 * k)(*ns), (C.c_int64 * k)(*ms), d,
+        C.byref(p), None, arr([t.data_ptr() for t in corr]), arr([t.data_ptr() for t in mask]), res), "vfmreg_register_batch")
+    out = []
+    for i in range(k):
+        kc = int(res[i].n_corr)
+        out.append(RegResult(T=np.array(res[i].T, dtype=np.float64).reshape(4, 4), corr=corr[i][:kc], inlier_mask=mask[i][:kc].bool(),
+                             fitness=float(res[i].fitness), rmse=float(res[i].rmse), best_hyp=int(res[i].best_hyp),
+                             n_inliers=int(res[i].n_inliers)))
+    return out
+
+
 def register_batch(pairs, *, normalize: bool = True, min_cos: Optional[float] = 0.8, mutual: bool = False,
                    ratio: Optional[float] = None, ransac_iters: int = 50000, inlier_thresh: float = 1e4, seed: int = 42,
                    refit: bool = False, algo: str = "auto", device=None):
-    """``register`` over a list of (source_pcd, target_pcd, src_feats, tgt_feats) HOST arrays with the copy of pair i+1
-    overlapped with the solve of pair i (``vfmreg_register_batch_host``).  Returns a list of RegResult.  Pinned inputs
-    (``torch.Tensor.pin_memory().numpy()``) make the copies asynchronous."""
+    """``register`` over a list of (source_pcd, target_pcd, src_feats, tgt_feats).
+
+    HOST arrays: the copy of pair i+1 is overlapped with the solve of pair i (``vfmreg_register_batch_host``); pinned inputs
+    (``torch.Tensor.pin_memory().numpy()``) make the copies asynchronous.  CUDA tensors: all pairs are enqueued back to
+    back with a single host synchronisation (``vfmreg_register_batch``); ``corr`` / ``inlier_mask`` then stay on the device.
+    Returns a list of RegResult."""
     ctx = get_context(device)
     k = len(pairs)
     if k == 0:
         return []
     p = _params(normalize, min_cos, mutual, ratio, ransac_iters, inlier_thresh, seed, refit, algo)
+    if all(isinstance(x, torch.Tensor) and x.is_cuda for pr in pairs for x in pr):
+        return _register_batch_device(ctx, pairs, p)
 
     def h(x, name, cols=None):
         x = x.numpy() if isinstance(x, torch.Tensor) else x

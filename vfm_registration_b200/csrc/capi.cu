@@ -501,4 +501,50 @@ int vfmreg_register_batch_host(vfmreg_ctx* ctx, int32_t n_pairs, const float* co
   return VFMREG_OK;
 }
 
+
+int vfmreg_register_batch(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* src_xyz, const float* const* tgt_xyz,
+                          const float* const* src_feats, const float* const* tgt_feats, const int64_t* n, const int64_t* m,
+                          int32_t d, const vfmreg_register_params* params, const int32_t* const* sample_idx,
+                          int32_t* const* corr_out, uint8_t* const* mask_out, vfmreg_register_result* results) {
+  VFM_CHECK_ARG(ctx && n_pairs > 0 && src_xyz && tgt_xyz && src_feats && tgt_feats && n && m && params && results,
+                "register_batch: null pointer / empty batch");
+  size_t scratch = 0;
+  int64_t n_max = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    VFM_TRY(check_register_args(ctx, src_xyz[i], tgt_xyz[i], src_feats[i], tgt_feats[i], n[i], m[i], d, params, results + i));
+    const size_t sc = register_scratch(ctx, n[i], m[i], d, params);
+    scratch = sc > scratch ? sc : scratch;
+    n_max = n[i] > n_max ? n[i] : n_max;
+  }
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  // scratch arena: [per-pair (T, stats) slots | fallback corr/mask | per-pair scratch (reused in stream order)]
+  const size_t slots_bytes = (size_t)n_pairs * 256;
+  const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
+  arena_reset(ctx);
+  VFM_TRY(arena_reserve(ctx, slots_bytes + out_bytes + scratch + 4096));
+  VFM_TRY(ensure_pinned(ctx, slots_bytes));
+  char* slots = arena_take<char>(ctx, slots_bytes);
+  int32_t* corr_fb = arena_take<int32_t>(ctx, (size_t)n_max * 2);
+  uint8_t* mask_fb = arena_take<uint8_t>(ctx, n_max);
+  if (!slots || !corr_fb || !mask_fb) {
+    set_error("register_batch: scratch arena too small");
+    return VFMREG_ERR_ALLOC;
+  }
+  const size_t mark = ctx->arena.off;
+  for (int i = 0; i < n_pairs; ++i) {
+    RegOut out;
+    out.corr = (corr_out && corr_out[i]) ? corr_out[i] : corr_fb;
+    out.mask = (mask_out && mask_out[i]) ? mask_out[i] : mask_fb;
+    out.T = (double*)(slots + (size_t)i * 256);
+    out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
+    ctx->arena.off = mark;   // every pair reuses the same scratch region (stream order)
+    VFM_TRY(register_enqueue(ctx, src_xyz[i], tgt_xyz[i], src_feats[i], tgt_feats[i], n[i], m[i], d, params,
+                             sample_idx ? sample_idx[i] : nullptr, out));
+  }
+  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, slots_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_pairs; ++i) fill_result(results + i, static_cast<const char*>(ctx->pinned) + (size_t)i * 256, params->inlier_thresh);
+  return VFMREG_OK;
+}
+
 }  // extern "C"

@@ -3,9 +3,10 @@
 //   preprocess_kernel   ToTensor -> bilinear Resize(antialias=False, align_corners=False) -> Normalize, written straight
 //                       into the im2col patch matrix in bf16 (the resized image is never materialised); HBM-bound.
 //   layernorm kernels   one warp per token, 128-bit loads, two-pass statistics in registers; HBM-bound.
-//   attention_kernel    softmax(Q K^T / sqrt(64)) V per (image, head, 64-query tile): K/V of the head staged once in
-//                       shared memory, flash-style online softmax over 64-key chunks, bf16 mma.sync m16n8k16 with fp32
-//                       accumulation.  (~4 % of the model's FLOPs; the GEMMs that carry the rest run on tcgen05.)
+//   attention_kernel    softmax(Q K^T / sqrt(64)) V, one CTA per (image, head): K/V of the head staged once in shared
+//                       memory, 8 warps walk 16-query tiles with a flash-style online softmax over 64-key chunks, bf16
+//                       mma.sync m16n8k16 with fp32 accumulation.  (~4 % of the model's FLOPs; the GEMMs that carry
+//                       the rest run on tcgen05.)
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -201,18 +202,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int ATT_WARPS = 8;
+
+// One CTA per (image, head): K and V of the head are staged in shared memory ONCE, then each of the 8 warps walks
+// 16-query tiles (tile = warp, warp + 8, ...) with a flash-style online softmax over 64-key chunks.
+__global__ void __launch_bounds__(ATT_WARPS * 32)
     attention_kernel(const __nv_bfloat16* __restrict__ qkv, int t, int width, int tp, __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(att_smem);
   __nv_bfloat16* vs = ks + (size_t)tp * ATT_LD;
-  __nv_bfloat16* qs = vs + (size_t)tp * ATT_LD;
+  __nv_bfloat16* qs_all = vs + (size_t)tp * ATT_LD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * ATT_Q, head = blockIdx.y, img = blockIdx.z;
+  const int head = blockIdx.x, img = blockIdx.y;
   const long long ld = 3LL * width;
   const __nv_bfloat16* base = qkv + (long long)img * t * ld + head * ATT_DH;
   const uint4 z4 = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < tp * 8; i += 128) {
+  for (int i = tid; i < tp * 8; i += ATT_WARPS * 32) {
     const int r = i >> 3, ch = i & 7;
     uint4 kv = z4, vv = z4;
     if (r < t) {
@@ -222,124 +227,128 @@ __global__ void __launch_bounds__(128)
     *reinterpret_cast<uint4*>(ks + r * ATT_LD + ch * 8) = kv;
     *reinterpret_cast<uint4*>(vs + r * ATT_LD + ch * 8) = vv;
   }
-  for (int i = tid; i < ATT_Q * 8; i += 128) {
-    const int r = i >> 3, ch = i & 7;
-    uint4 qv = z4;
-    if (q0 + r < t) qv = *reinterpret_cast<const uint4*>(base + (long long)(q0 + r) * ld + ch * 8);
-    *reinterpret_cast<uint4*>(qs + r * ATT_LD + ch * 8) = qv;
-  }
   __syncthreads();
+  __nv_bfloat16* qs = qs_all + warp * 16 * ATT_LD;   // this warp's private 16 x 64 query tile
   const int g = lane >> 2, tq = lane & 3;
-  // Q fragments of this warp's 16 rows: 4 k-steps
-  uint32_t qa[4][4];
-  {
-    const int row = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const uint32_t addr = (uint32_t)__cvta_generic_to_shared(qs + row * ATT_LD + kk * 16 + 8 * (lane >> 4));
-      ldsm_x4(addr, qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3]);
-    }
-  }
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  for (int kc = 0; kc < tp / 64; ++kc) {
-    float s[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int np2 = 0; np2 < 4; ++np2) {  // two key tiles (16 keys) per ldmatrix.x4
-        const int key = kc * 64 + np2 * 16 + (lane & 7) + 8 * (lane >> 4);
-        const int col = kk * 16 + 8 * ((lane >> 3) & 1);
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4((uint32_t)__cvta_generic_to_shared(ks + key * ATT_LD + col), b0, b1, b2, b3);
-        mma_bf16(s[np2 * 2], qa[kk], b0, b1);
-        mma_bf16(s[np2 * 2 + 1], qa[kk], b2, b3);
-      }
-    }
-    // mask keys beyond t, running max
-    float mx[2] = {m_run[0], m_run[1]};
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int key = kc * 64 + nt * 8 + tq * 2;
-      if (key >= t) s[nt][0] = s[nt][2] = -INFINITY;
-      if (key + 1 >= t) s[nt][1] = s[nt][3] = -INFINITY;
-      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-    }
-    float alpha[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      alpha[r] = exp2f((m_run[r] - mx[r]) * sl2);  // first chunk: exp2(-inf) = 0
-      m_run[r] = mx[r];
-      l_run[r] *= alpha[r];
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      o[nt][0] *= alpha[0];
-      o[nt][1] *= alpha[0];
-      o[nt][2] *= alpha[1];
-      o[nt][3] *= alpha[1];
-    }
-    uint32_t pa[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f((s[nt][0] - mx[0]) * sl2), p1 = exp2f((s[nt][1] - mx[0]) * sl2);
-      const float p2 = exp2f((s[nt][2] - mx[1]) * sl2), p3 = exp2f((s[nt][3] - mx[1]) * sl2);
-      l_run[0] += p0 + p1;
-      l_run[1] += p2 + p3;
-      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
-      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {      // 16 keys per step
-#pragma unroll
-      for (int dp2 = 0; dp2 < 4; ++dp2) {  // two dh tiles (16 channels) per ldmatrix.x4.trans
-        const int key = kc * 64 + j * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-        const int col = dp2 * 16 + 8 * (lane >> 4);
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_trans((uint32_t)__cvta_generic_to_shared(vs + key * ATT_LD + col), b0, b1, b2, b3);
-        mma_bf16(o[dp2 * 2], pa[j], b0, b1);
-        mma_bf16(o[dp2 * 2 + 1], pa[j], b2, b3);
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
-    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
-  }
-  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
-  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
   __nv_bfloat16* ob = out + (long long)img * t * width + head * ATT_DH;
+  for (int q0 = warp * 16; q0 < t; q0 += ATT_WARPS * 16) {
+    __syncwarp();
+    for (int i = lane; i < 16 * 8; i += 32) {
+      const int r = i >> 3, ch = i & 7;
+      uint4 qv = z4;
+      if (q0 + r < t) qv = *reinterpret_cast<const uint4*>(base + (long long)(q0 + r) * ld + ch * 8);
+      *reinterpret_cast<uint4*>(qs + r * ATT_LD + ch * 8) = qv;
+    }
+    __syncwarp();
+    uint32_t qa[4][4];
+    {
+      const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int c = nt * 8 + tq * 2;
-    if (r0 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * width + c) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
-    if (r1 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * width + c) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(qs + row * ATT_LD + kk * 16 + 8 * (lane >> 4));
+        ldsm_x4(addr, qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3]);
+      }
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    for (int kc = 0; kc < tp / 64; ++kc) {
+      float s[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int np2 = 0; np2 < 4; ++np2) {  // two key tiles (16 keys) per ldmatrix.x4
+          const int key = kc * 64 + np2 * 16 + (lane & 7) + 8 * (lane >> 4);
+          const int col = kk * 16 + 8 * ((lane >> 3) & 1);
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4((uint32_t)__cvta_generic_to_shared(ks + key * ATT_LD + col), b0, b1, b2, b3);
+          mma_bf16(s[np2 * 2], qa[kk], b0, b1);
+          mma_bf16(s[np2 * 2 + 1], qa[kk], b2, b3);
+        }
+      }
+      // mask keys beyond t, running max
+      float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = kc * 64 + nt * 8 + tq * 2;
+        if (key >= t) s[nt][0] = s[nt][2] = -INFINITY;
+        if (key + 1 >= t) s[nt][1] = s[nt][3] = -INFINITY;
+        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      }
+      float alpha[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        alpha[r] = exp2f((m_run[r] - mx[r]) * sl2);  // first chunk: exp2(-inf) = 0
+        m_run[r] = mx[r];
+        l_run[r] *= alpha[r];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        o[nt][0] *= alpha[0];
+        o[nt][1] *= alpha[0];
+        o[nt][2] *= alpha[1];
+        o[nt][3] *= alpha[1];
+      }
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = exp2f((s[nt][0] - mx[0]) * sl2), p1 = exp2f((s[nt][1] - mx[0]) * sl2);
+        const float p2 = exp2f((s[nt][2] - mx[1]) * sl2), p3 = exp2f((s[nt][3] - mx[1]) * sl2);
+        l_run[0] += p0 + p1;
+        l_run[1] += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {      // 16 keys per step
+#pragma unroll
+        for (int dp2 = 0; dp2 < 4; ++dp2) {  // two dh tiles (16 channels) per ldmatrix.x4.trans
+          const int key = kc * 64 + j * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+          const int col = dp2 * 16 + 8 * (lane >> 4);
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans((uint32_t)__cvta_generic_to_shared(vs + key * ATT_LD + col), b0, b1, b2, b3);
+          mma_bf16(o[dp2 * 2], pa[j], b0, b1);
+          mma_bf16(o[dp2 * 2 + 1], pa[j], b2, b3);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+    const int r0 = q0 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = nt * 8 + tq * 2;
+      if (r0 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * width + c) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
+      if (r1 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * width + c) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
   }
 }
 
 int vit_attention(vfmreg_ctx* ctx, const __nv_bfloat16* qkv, int b, int t, int heads, int width, __nv_bfloat16* out) {
   VFM_CHECK_ARG(width == heads * ATT_DH, "attention: head dim must be 64 (width %d, heads %d)", width, heads);
   const int tp = (t + 63) / 64 * 64;
-  const size_t smem = (size_t)(2 * tp + ATT_Q) * ATT_LD * 2;
+  const size_t smem = (size_t)(2 * tp + ATT_WARPS * 16) * ATT_LD * 2;
   VFM_CHECK_ARG(smem <= 200 * 1024, "attention: %d tokens per image do not fit the shared-memory K/V staging", t);
   static size_t attr = 0;
   if (smem > attr) {
     VFM_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  attention_kernel<<<dim3(ceil_div(t, ATT_Q), heads, b), 128, smem, ctx->stream>>>(qkv, t, width, tp, out);
+  attention_kernel<<<dim3(heads, b), ATT_WARPS * 32, smem, ctx->stream>>>(qkv, t, width, tp, out);
   return launch_check(ctx, "attention_kernel");
 }
 
