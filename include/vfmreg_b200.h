@@ -220,6 +220,8 @@ VFMREG_API int vfmreg_vit_set_weight(vfmreg_vit* vit, const char* name, const fl
 VFMREG_API int vfmreg_vit_set_pos_embed(vfmreg_vit* vit, int32_t grid_h, int32_t grid_w, const float* host);
 /* patch grid create_transform_ would pick for an (img_h, img_w) image (image_features.py:67-69) */
 VFMREG_API int vfmreg_vit_grid(const vfmreg_vit* vit, int32_t img_h, int32_t img_w, int32_t* grid_h, int32_t* grid_w);
+/* 1 (default): from the second call with a given (b, img_h, img_w) the kernel sequence is replayed as one CUDA graph */
+VFMREG_API int vfmreg_vit_set_graphs(vfmreg_vit* vit, int32_t on);
 /* images: device uint8 (b, img_h, img_w, 3) RGB; tokens: device float32 (b, grid_h, grid_w, width) */
 VFMREG_API int vfmreg_vit_forward(vfmreg_vit* vit, const uint8_t* images, int32_t b, int32_t img_h, int32_t img_w, float* tokens);
 

@@ -129,3 +129,24 @@ def test_config3_images_to_transform(vfm):
     rte = np.linalg.norm(r.T[:3, 3] - t_gt[:3, 3])
     rre = np.degrees(np.arccos(np.clip((np.trace(r.T[:3, :3].T @ t_gt[:3, :3]) - 1) / 2, -1, 1)))
     assert rte < 0.2 and rre < 0.5, (rte, rre)
+
+
+def test_vit_graph_replay_matches_eager(vfm):
+    """The second and later calls with a given shape replay a captured CUDA graph: results must be bit-identical to the
+    eager first call, for changing inputs, interleaved shapes and a batch that forces the staging buffers to grow."""
+    rng = np.random.default_rng(2)
+    f = vfm.ViTFeaturizer("vits14", seed=5)
+    a = torch.from_numpy(_images(rng, 2, 224, 224)).cuda()
+    b = torch.from_numpy(_images(rng, 2, 224, 224)).cuda()
+    c = torch.from_numpy(_images(rng, 1, 70, 82)).cuda()
+    ea, ec = f.forward(a).clone(), f.forward(c).clone()       # eager
+    ga1 = f.forward(a).clone()                                 # captures + replays
+    gb = f.forward(b).clone()                                  # replay, other input
+    gc = f.forward(c).clone()                                  # second shape: captures
+    ga2 = f.forward(a).clone()
+    assert torch.equal(ea, ga1) and torch.equal(ea, ga2) and torch.equal(ec, gc)
+    assert not torch.equal(ga1, gb)
+    big = torch.from_numpy(_images(rng, 5, 224, 224)).cuda()
+    e_big = f.forward(big).clone()
+    g_big = f.forward(big).clone()
+    assert torch.equal(e_big, g_big) and torch.equal(f.forward(a), ea)

@@ -72,6 +72,7 @@ _SIGS = {
     "vfmreg_vit_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "vfmreg_vit_set_pos_embed": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "vfmreg_vit_grid": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vfmreg_vit_set_graphs": (C.c_int, [_P, C.c_int32]),
     "vfmreg_vit_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
 }
 

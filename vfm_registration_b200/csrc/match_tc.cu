@@ -73,6 +73,7 @@ struct TcParams {
   int* cand_n;           // [n][slots]: count | overflow << 30
   float2* slot_top2;     // [n][slots]: approximate (best, runner-up) of the slot's column span
   long long* dbg;        // optional per-CTA cycle counters (tuning aid): [cta][8]
+  int experiment;        // tuning aid: 1 = producer stops issuing TMA after the first ring fill (timing only, garbage results)
   int top1;              // 1: only the best match is needed (runner-up value not requested): threshold = best - margin
 };
 
@@ -264,9 +265,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int kb = 0; kb < P.kb; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(full0 + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
-            tma_load_2d(sA + stage * A_STAGE_BYTES, &map_a, full0 + 8 * stage, kb * TBK, rb * TBM);
-            tma_load_2d(sB + stage * B_STAGE_BYTES, &map_b, full0 + 8 * stage, kb * TBK, ct * TBN);
+            if (P.experiment && (t > t_begin || kb >= STAGES)) {
+              mbar_arrive(full0 + 8 * stage);   // no data movement: MMAs re-read stale shared memory
+            } else {
+              mbar_expect_tx(full0 + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
+              tma_load_2d(sA + stage * A_STAGE_BYTES, &map_a, full0 + 8 * stage, kb * TBK, rb * TBM);
+              tma_load_2d(sB + stage * B_STAGE_BYTES, &map_b, full0 + 8 * stage, kb * TBK, ct * TBN);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         long long c0 = clock64();
         mbar_wait(tempty0 + 8 * buf, (uint32_t)((it / NBUF) & 1) ^ 1);
         w_tempty += clock64() - c0;
+        if (P.dbg && blockIdx.x == 0 && it >= 8 && it < 24 && lane == 0) P.dbg[1200 + (it - 8) * 16 + 0] = clock64();  // tempty acquired
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * TBN;
 #pragma unroll 1
@@ -305,6 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (kb == P.kb - 1) tc_commit(tfull0 + 8 * buf);  // accumulator complete -> epilogue
           }
           __syncwarp();
+          if (kb == P.kb - 1 && P.dbg && blockIdx.x == 0 && it >= 8 && it < 24 && lane == 0) P.dbg[1200 + (it - 8) * 16 + 1] = clock64();  // commit issued
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -342,12 +349,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const long long c0 = clock64();
       mbar_wait(tfull0 + 8 * buf, (uint32_t)((it / NBUF) & 1));
       w_tfull += clock64() - c0;
+      if (P.dbg && blockIdx.x == 0 && it >= 8 && it < 24 && lane == 0) P.dbg[1200 + (it - 8) * 16 + 2 + (warp - 2) * 2] = clock64();  // tfull seen
       tc_fence_after();
       epilogue_tile(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * COLS_PER_WARP, ct * TBN + half * COLS_PER_WARP,
                     P.m, etid, ring_v, ring_i, best, second, thr, cnt, ovf);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      if (P.dbg && blockIdx.x == 0 && it >= 8 && it < 24 && lane == 0) P.dbg[1200 + (it - 8) * 16 + 3 + (warp - 2) * 2] = clock64();  // released
     }
     if (P.dbg && warp == 2 && lane == 0) {
       P.dbg[blockIdx.x * 8 + 4] = clock64() - e_start;
@@ -847,13 +856,15 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   P.cand_n = cand_n;
   P.slot_top2 = slot_top2;
   P.dbg = nullptr;
+  static const int experiment = [] { const char* e = getenv("VFMREG_TC_EXPERIMENT"); return e ? atoi(e) : 0; }();
+  P.experiment = experiment;
   static const bool force_top1 = [] { const char* e = getenv("VFMREG_TC_TOP1"); return e && e[0] == '1'; }();  // tuning aid
   P.top1 = (sec == nullptr || force_top1) ? 1 : 0;
   static const bool want_dbg = [] { const char* e = getenv("VFMREG_TC_DEBUG"); return e && e[0] == '1'; }();
   static long long* dbg_dev = nullptr;
   if (want_dbg) {
-    if (!dbg_dev) cudaMalloc(&dbg_dev, 1024 * 8 * sizeof(long long));
-    cudaMemsetAsync(dbg_dev, 0, 1024 * 8 * sizeof(long long), ctx->stream);
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 2048 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, 2048 * 8 * sizeof(long long), ctx->stream);
     P.dbg = dbg_dev;
   }
   static bool attr_set = false;
@@ -882,12 +893,21 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   exact_rows_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(a32, b32, (int)m, dp, redo + 1, redo, idx, best, sec);
   VFM_TRY(launch_check(ctx, "exact_rows_kernel"));
   if (want_dbg) {
-    static long long host[1024 * 8];
+    static long long host[2048 * 8];
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpy(host, dbg_dev, sizeof(host), cudaMemcpyDeviceToHost);
     double acc[8] = {0};
     for (int c = 0; c < plan.grid; ++c)
       for (int k = 0; k < 8; ++k) acc[k] += (double)host[c * 8 + k] / plan.grid;
+    if (host[1200]) {
+      const long long t0 = host[1200];
+      for (int i = 0; i < 16; ++i) {
+        const long long* r = host + 1200 + i * 16;
+        fprintf(stderr, "[tc dbg] tile %2d: mma got tempty %7lld, commit issued %7lld | epi seen/released", i + 8, r[0] - t0, r[1] - t0);
+        for (int w = 0; w < 4; ++w) fprintf(stderr, " w%d %7lld/%7lld", w, r[2 + 2 * w] - t0, r[3 + 2 * w] - t0);
+        fprintf(stderr, "\n");
+      }
+    }
     fprintf(stderr, "[tc dbg] grid=%d tiles/cta=%.1f | mma warp: total %.0f cyc, wait tempty %.0f, wait full %.0f | epi warp: total %.0f, wait tfull %.0f\n",
             plan.grid, acc[3], acc[0], acc[1], acc[2], acc[4], acc[5]);
   }

@@ -42,6 +42,19 @@ struct vfmreg_vit {
   CUtensorMap m_xn, m_ao, m_h, m_patches;
   int map_rows = -1, map_prow = -1;
   std::map<std::string, bool> loaded;
+  // CUDA-graph replay of the per-forward kernel sequence (launch-bound at small batch): one graph per (b, h, w), captured on
+  // the second call with that shape; images / tokens go through fixed staging buffers so the graph has no changing pointers
+  struct Graph {
+    cudaGraphExec_t exec = nullptr;
+    int calls = 0;
+    int launches = 0;
+  };
+  std::map<long long, Graph> graphs;
+  uint8_t* img_stage = nullptr;
+  float* tok_stage = nullptr;
+  size_t img_stage_cap = 0, tok_stage_cap = 0;
+  int use_graphs = 1;
+  cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the legacy default stream cannot capture)
 };
 
 namespace {
@@ -93,6 +106,11 @@ int ensure_activations(vfmreg_vit* v, int rows, int prows) {
     VFM_CUDA(cudaStreamSynchronize(v->ctx->stream));
     for (void* p : {(void*)v->x, (void*)v->xn, (void*)v->qkv, (void*)v->ao, (void*)v->hbuf, (void*)v->patches})
       if (p) cudaFree(p);
+    for (auto& kv : v->graphs)   // captured graphs hold the old activation pointers
+      if (kv.second.exec) {
+        cudaGraphExecDestroy(kv.second.exec);
+        kv.second.exec = nullptr;
+      }
     const int cap = rows + rows / 4;
     VFM_CUDA(cudaMalloc(&v->x, (size_t)cap * w * sizeof(float)));
     VFM_CUDA(cudaMalloc(&v->xn, (size_t)cap * w * 2));
@@ -167,6 +185,11 @@ void vfmreg_vit_destroy(vfmreg_vit* v) {
   cudaStreamSynchronize(v->ctx->stream);
   for (void* p : v->allocs) cudaFree(p);
   for (auto& kv : v->pos) cudaFree(kv.second);
+  for (auto& kv : v->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (v->img_stage) cudaFree(v->img_stage);
+  if (v->tok_stage) cudaFree(v->tok_stage);
+  if (v->cap_stream) cudaStreamDestroy(v->cap_stream);
   for (void* p : {(void*)v->x, (void*)v->xn, (void*)v->qkv, (void*)v->ao, (void*)v->hbuf, (void*)v->patches})
     if (p) cudaFree(p);
   delete v;
@@ -253,22 +276,12 @@ int vfmreg_vit_grid(const vfmreg_vit* v, int32_t img_h, int32_t img_w, int32_t* 
   return VFMREG_OK;
 }
 
-int vfmreg_vit_forward(vfmreg_vit* v, const uint8_t* images, int32_t b, int32_t img_h, int32_t img_w, float* tokens) {
-  VFM_CHECK_ARG(v && images && tokens && b > 0, "vit_forward: bad arguments");
+static int vit_enqueue(vfmreg_vit* v, const uint8_t* images, int b, int img_h, int img_w, int gh, int gw, const float* pos,
+                       float* tokens) {
   vfmreg_ctx* ctx = v->ctx;
-  VFM_CUDA(cudaSetDevice(ctx->device));
-  int32_t gh, gw;
-  VFM_TRY(vfmreg_vit_grid(v, img_h, img_w, &gh, &gw));
-  VFM_CHECK_ARG(gw > 0, "vit_forward: image %dx%d is too narrow for one patch column", img_h, img_w);
-  auto it = v->pos.find(((long long)gh << 20) | gw);
-  VFM_CHECK_ARG(it != v->pos.end(), "vit_forward: no position embedding set for the %dx%d patch grid", gh, gw);
-  const float* pos = it->second;
   const int w = v->cfg.width, md = v->cfg.mlp_dim, np = gh * gw, t = np + 1;
   const int rows = b * t, prows = b * np;
-  VFM_TRY(ensure_activations(v, rows, prows));
   const float ms[6] = {v->cfg.mean[0], v->cfg.mean[1], v->cfg.mean[2], v->cfg.std[0], v->cfg.std[1], v->cfg.std[2]};
-  group_begin(ctx, GROUP_VIT);
-  const int64_t l0 = ctx->launches;
   VFM_TRY(vit_preprocess(ctx, images, b, img_h, img_w, gh, gw, v->cfg.patch, ms, v->patches, v->kp, v->x, v->cls, pos, w));
   GemmEpilogue ep{};
   ep = GemmEpilogue{prows, w, v->kp, np, w, v->pe_b, nullptr, pos, v->x, nullptr};
@@ -286,9 +299,85 @@ int vfmreg_vit_forward(vfmreg_vit* v, const uint8_t* images, int32_t b, int32_t 
     ep = GemmEpilogue{rows, w, md, 0, w, l.fc2_b, l.ls2, nullptr, v->x, nullptr};
     VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_h, l.m_fc2, ep));
   }
-  VFM_TRY(vit_final_norm(ctx, v->x, b, t, w, v->norm_g, v->norm_b, v->cfg.ln_eps, v->cn_g, v->cn_b, v->cfg.cn_eps,
-                         v->cfg.channel_norm, tokens));
-  group_end(ctx, GROUP_VIT, (int)(ctx->launches - l0));
+  return vit_final_norm(ctx, v->x, b, t, w, v->norm_g, v->norm_b, v->cfg.ln_eps, v->cn_g, v->cn_b, v->cfg.cn_eps, v->cfg.channel_norm,
+                        tokens);
+}
+
+int vfmreg_vit_set_graphs(vfmreg_vit* v, int32_t on) {
+  VFM_CHECK_ARG(v, "vit_set_graphs: null pointer");
+  v->use_graphs = on;
+  return VFMREG_OK;
+}
+
+int vfmreg_vit_forward(vfmreg_vit* v, const uint8_t* images, int32_t b, int32_t img_h, int32_t img_w, float* tokens) {
+  VFM_CHECK_ARG(v && images && tokens && b > 0, "vit_forward: bad arguments");
+  vfmreg_ctx* ctx = v->ctx;
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  int32_t gh, gw;
+  VFM_TRY(vfmreg_vit_grid(v, img_h, img_w, &gh, &gw));
+  VFM_CHECK_ARG(gw > 0, "vit_forward: image %dx%d is too narrow for one patch column", img_h, img_w);
+  auto it = v->pos.find(((long long)gh << 20) | gw);
+  VFM_CHECK_ARG(it != v->pos.end(), "vit_forward: no position embedding set for the %dx%d patch grid", gh, gw);
+  const float* pos = it->second;
+  const int np = gh * gw, t = np + 1;
+  VFM_TRY(ensure_activations(v, b * t, b * np));
+  const size_t img_bytes = (size_t)b * img_h * img_w * 3, tok_bytes = (size_t)b * np * v->cfg.width * sizeof(float);
+  const long long key = ((long long)b << 40) | ((long long)img_h << 20) | img_w;
+  vfmreg_vit::Graph& g = v->graphs[key];
+  g.calls += 1;
+  group_begin(ctx, GROUP_VIT);
+  int rc = VFMREG_OK;
+  if (!v->use_graphs || g.calls == 1) {
+    // first call with this shape: plain launches (also sets kernel attributes, which cannot happen during capture)
+    const int64_t l0 = ctx->launches;
+    rc = vit_enqueue(v, images, b, img_h, img_w, gh, gw, pos, tokens);
+    g.launches = (int)(ctx->launches - l0);
+    group_end(ctx, GROUP_VIT, g.launches);
+    return rc;
+  }
+  if (img_bytes > v->img_stage_cap || tok_bytes > v->tok_stage_cap) {
+    // staging buffers are baked into captured graphs: growing them invalidates every graph
+    VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto& kv : v->graphs)
+      if (kv.second.exec) {
+        cudaGraphExecDestroy(kv.second.exec);
+        kv.second.exec = nullptr;
+      }
+    if (v->img_stage) cudaFree(v->img_stage);
+    if (v->tok_stage) cudaFree(v->tok_stage);
+    v->img_stage_cap = img_bytes + img_bytes / 2;
+    v->tok_stage_cap = tok_bytes + tok_bytes / 2;
+    VFM_CUDA(cudaMalloc(&v->img_stage, v->img_stage_cap));
+    VFM_CUDA(cudaMalloc(&v->tok_stage, v->tok_stage_cap));
+  }
+  if (!g.exec) {
+    cudaGraph_t graph = nullptr;
+    if (!v->cap_stream) VFM_CUDA(cudaStreamCreateWithFlags(&v->cap_stream, cudaStreamNonBlocking));
+    const int timing = ctx->timing;
+    cudaStream_t user_stream = ctx->stream;
+    ctx->timing = 0;  // no event records inside the capture
+    ctx->stream = v->cap_stream;
+    cudaError_t e = cudaStreamBeginCapture(v->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      rc = vit_enqueue(v, v->img_stage, b, img_h, img_w, gh, gw, pos, v->tok_stage);
+      e = cudaStreamEndCapture(v->cap_stream, &graph);
+    }
+    ctx->stream = user_stream;
+    ctx->timing = timing;
+    if (rc != VFMREG_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    VFM_CUDA(e);
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    VFM_CUDA(e);
+  }
+  VFM_CUDA(cudaMemcpyAsync(v->img_stage, images, img_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  VFM_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+  VFM_CUDA(cudaMemcpyAsync(tokens, v->tok_stage, tok_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->launches += g.launches;  // kernels replayed by the graph
+  group_end(ctx, GROUP_VIT, g.launches);
   return VFMREG_OK;
 }
 
