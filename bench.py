@@ -268,13 +268,17 @@ def main():
             "gpu_launches": int(launches)}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cref
-        rows = 1250
-        tm, tr, rc, _ = cpu_path(pairs[-1], rows)
-        per_pair = tm * (N_SCAN / rows) + tr
+        # bounded sample: ONE full pair on the host cores (~0.5-1 s with 16+ threads), best of 2
+        best = None
+        for _ in range(2):
+            tm, tr, rc, _ = cpu_path(pairs[-1], N_SCAN)
+            best = (tm, tr) if best is None or tm + tr < sum(best) else best
+        tm, tr = best
+        per_pair = tm + tr
         rte, rre = synth.pose_errors(rc["T"], pairs[-1]["T_gt"])
         line["cpu_baseline"] = {"value": 1.0 / per_pair, "unit": UNIT, "cores": cref.num_threads(), "kind": "port",
-                                "sample": f"1 pair, scan rows {rows}/{N_SCAN} vs full map, both directions (match "
-                                          f"{tm:.2f}s scaled x{N_SCAN / rows:.0f}) + full 8192-hyp RANSAC ({tr:.2f}s)",
+                                "sample": f"1 full pair (10k x 50k x 384, both directions: {tm:.2f}s; 8192-hyp RANSAC: {tr:.3f}s), "
+                                          f"best of 2; oracle/c restatement (AVX2 + OpenMP)",
                                 "recall_ok": bool(rte < 1.0 and rre < 5.0)}
     print(json.dumps(line), flush=True)
     if world > 1:
