@@ -216,6 +216,7 @@ def main():
     ms_dev, launches, res = timed(dev_pairs, args.steps, args.warmup)
     match_ms, match_launches = ctx.group_time_ms(0)
     ransac_ms, ransac_launches = ctx.group_time_ms(1)
+    pruned_ms, pruned_launches = ctx.group_time_ms(4)
     ctx.enable_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _, res_e2e = timed(pin_pairs, max(2, args.steps // 2), 2, host=True)
@@ -235,7 +236,9 @@ def main():
     total_pairs = world * P * args.steps
     value = total_pairs / (ms_dev / 1e3)
     e2e_val = world * P * e2e_steps / (ms_e2e / 1e3)
-    # roofline of the dominant kernel: both search directions = 2 launches per pair, 2*N*M*D flop each
+    # roofline of the dominant kernel: the full scan->map search, 2*N*M*D flop per launch.  The map->scan direction of the
+    # mutual check only needs idx10[j] at the map rows j that gated queries point at, so register() searches those
+    # (<= N) rows only (`pruned_*` below; identical correspondences, tests/test_gpu_parity.py::test_pruned_mutual_*).
     flop_per_launch = 2.0 * N_SCAN * N_MAP * DIM
     alg_bytes_per_launch = 4.0 * DIM * (N_SCAN + N_MAP)
     # warm-up launches are included in the event total, so divide by the launches actually recorded
@@ -246,12 +249,15 @@ def main():
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-    roofline = {"bound": "tensor", "kernel": "descriptor N x M match (one search direction per launch)",
+    roofline = {"bound": "tensor", "kernel": "match_tc2_kernel: descriptor N x M candidate search, scan -> map (full)",
                 "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
                 "peak_source": f"{peaks['source']} bf16 burst", "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
                 "algorithmic_bytes": alg_bytes_per_launch, "avg_launch_ms": avg_ms,
                 "launches_timed": match_launches, "algorithmic_gbs": alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9,
-                "share_of_step": (match_ms / max(match_launches, 1)) * 2 * P / (ms_dev / args.steps),
+                "share_of_step": avg_ms * (match_launches / ((args.steps + args.warmup) * P)) * P / (ms_dev / args.steps),
+                "full_search_launches_per_pair": match_launches / ((args.steps + args.warmup) * P),
+                "pruned_reverse_search_avg_ms": pruned_ms / max(pruned_launches, 1),
+                "pruned_reverse_search_launches_per_pair": pruned_launches / ((args.steps + args.warmup) * P),
                 "ransac_score_avg_ms": ransac_ms / max(ransac_launches, 1)}
     nbytes = lambda t: int(sum(x.nbytes for x in t))
     h2d = sum(nbytes(pp) for pp in pin_pairs)

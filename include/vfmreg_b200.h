@@ -65,7 +65,8 @@ VFMREG_API int vfmreg_sync(vfmreg_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 VFMREG_API int64_t vfmreg_kernel_launches(const vfmreg_ctx* ctx);
 /* device time in ms of the most recent launch of the named kernel group, measured with CUDA events on the
- * context's stream when profiling is enabled: group 0 = match GEMM, 1 = ransac score, 2 = project/gather, 3 = vit gemm */
+ * context's stream when profiling is enabled: group 0 = match GEMM (full searches), 1 = ransac score, 2 = project/gather, 3 = vit gemm,
+ * 4 = match GEMM launches of the pruned reverse search of the mutual check (row count on the device) */
 VFMREG_API int vfmreg_enable_timing(vfmreg_ctx* ctx, int on);
 VFMREG_API int vfmreg_group_time_ms(vfmreg_ctx* ctx, int group, float* ms_total, int* launches);
 

@@ -298,3 +298,25 @@ def test_full_size_ransac_properties(vfm):
     assert r2.n_inliers >= 0.95 * len(inl)
     rte, rre = synth.pose_errors(r2.T, s["T_gt"])
     assert rte < 0.2 and rre < 0.5
+
+
+@pytest.mark.parametrize("m,n,d,min_cos", [(50_000, 10_000, 384, 0.8), (50_000, 10_000, 384, None), (3000, 3000, 384, 0.8),
+                                           (5000, 200, 64, 0.5), (900, 100, 768, None), (4000, 1000, 128, 0.999),
+                                           (300, 1, 32, None)])
+def test_pruned_mutual_equals_full_search(vfm, m, n, d, min_cos):
+    """register() answers the mutual check from a reverse search restricted to the map rows that gated queries point at
+    (row count on the device); the correspondence list must equal gate + full reverse search, at BASELINE configs[1]
+    size and at the edges (no gate, no survivor, fewer rows than one tile, a single query)."""
+    s = synth.make_pair(70 + n % 50, m, n, d)
+    dev = [torch.from_numpy(s[k]).cuda() for k in ("scan_xyz", "map_xyz", "scan_feat", "map_feat")]
+    if n > 50:
+        dev[2][5] = 0                 # zero-norm query
+        dev[3][11] = dev[3][3]        # duplicated map row: tie -> lowest index
+    r = vfm.register(*dev, min_cos=min_cos, mutual=True, ransac_iters=256, inlier_thresh=1.0, seed=3)
+    full = vfm.match_nn(dev[2], dev[3], mutual=True)
+    want = vfm.filter_correspondences(full, min_cos=min_cos, mutual=True)
+    got = r.corr if isinstance(r.corr, np.ndarray) else r.corr.cpu().numpy()
+    want = want if isinstance(want, np.ndarray) else want.cpu().numpy()
+    assert np.array_equal(got, want)
+    if min_cos == 0.8 and n >= 3000:
+        assert len(got) > 0.2 * n

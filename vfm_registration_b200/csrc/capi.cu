@@ -1,6 +1,7 @@
 // extern "C" surface of libvfmreg_b200.so (see include/vfmreg_b200.h).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -32,22 +33,30 @@ int arena_reserve(vfmreg_ctx* ctx, size_t bytes) {
   return VFMREG_OK;
 }
 
+// fold the oldest `n` pending intervals of a group into its total (waits for them if they have not completed yet)
+static void group_fold(vfmreg_ctx* ctx, int group, int n) {
+  const int R = vfmreg_ctx::EV_RING;
+  for (; n > 0 && ctx->group_pending[group] > 0; --n) {
+    const int slot = ((ctx->ev_head[group] - ctx->group_pending[group]) % R + R) % R;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev1[group][slot]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ctx->ev0[group][slot], ctx->ev1[group][slot]) == cudaSuccess)
+      ctx->group_ms[group] += ms;
+    ctx->group_pending[group] -= 1;
+  }
+}
+
 void group_begin(vfmreg_ctx* ctx, int group) {
   if (!ctx->timing) return;
-  if (ctx->group_pending[group]) {  // fold the previous interval in before reusing the events
-    float ms = 0.f;
-    if (cudaEventSynchronize(ctx->ev1[group]) == cudaSuccess &&
-        cudaEventElapsedTime(&ms, ctx->ev0[group], ctx->ev1[group]) == cudaSuccess)
-      ctx->group_ms[group] += ms;
-    ctx->group_pending[group] = 0;
-  }
-  cudaEventRecord(ctx->ev0[group], ctx->stream);
+  if (ctx->group_pending[group] == vfmreg_ctx::EV_RING) group_fold(ctx, group, 1);  // ring full: reuse the oldest slot
+  cudaEventRecord(ctx->ev0[group][ctx->ev_head[group]], ctx->stream);
 }
 
 void group_end(vfmreg_ctx* ctx, int group, int n_launches) {
   if (!ctx->timing) return;
-  cudaEventRecord(ctx->ev1[group], ctx->stream);
-  ctx->group_pending[group] = 1;
+  cudaEventRecord(ctx->ev1[group][ctx->ev_head[group]], ctx->stream);
+  ctx->ev_head[group] = (ctx->ev_head[group] + 1) % vfmreg_ctx::EV_RING;
+  ctx->group_pending[group] += 1;
   ctx->group_launches[group] += n_launches;
 }
 
@@ -87,8 +96,24 @@ static size_t match_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int d, uint32
   return s;
 }
 
+// VFMREG_FULL_MUTUAL=1 keeps the full reverse search inside register() (A/B comparison; results are identical)
+static bool g_full_mutual = [] { const char* e = getenv("VFMREG_FULL_MUTUAL"); return e && e[0] == '1'; }();
+
+// The reverse search of the mutual check can be restricted to the map rows that some gated query points at when the
+// tensor-core path runs and the query side is the smaller one (the pruned search is (<= n) x n instead of m x n).
+static bool prune_mutual(int64_t n, int64_t m, uint32_t flags) {
+  return use_tc(flags) && (flags & VFMREG_MUTUAL) && n <= m && !g_full_mutual;
+}
+
+static size_t pruned_scratch(vfmreg_ctx* ctx, int64_t n, int d, uint32_t flags) {
+  const int dp = padded_dim(d, flags);
+  return arena_bytes((size_t)n * 2, 4) + arena_bytes(1, 4) + arena_bytes((size_t)n * dp, 4) + arena_bytes((size_t)n * dp, 2) +
+         arena_bytes(n, 1) + arena_bytes(n, 4) * 2 + match_tc_scratch(ctx, n, n, true);
+}
+
 static int match_nn_impl(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64_t m, int32_t d, uint32_t flags,
-                         int32_t* idx01, float* sim01, float* sec01, int32_t* idx10, float* sim10, float* sec10) {
+                         int32_t* idx01, float* sim01, float* sec01, int32_t* idx10, float* sim10, float* sec10,
+                         const vfmreg_register_params* prune = nullptr, int32_t* corr = nullptr, int32_t* count = nullptr) {
   const bool tc = use_tc(flags);
   const int dp = padded_dim(d, flags);
   float* an = arena_take<float>(ctx, (size_t)n * dp);
@@ -108,6 +133,28 @@ static int match_nn_impl(vfmreg_ctx* ctx, const float* a, int64_t n, const float
   const int norm = (flags & VFMREG_NORMALIZE) != 0;
   VFM_TRY(normalize_rows(ctx, a, n, d, dp, norm, an, ah, nza));
   VFM_TRY(normalize_rows(ctx, b, m, d, dp, norm, bn, bh, nzb));
+  if (prune) {
+    // register(): forward search, gate (cosine / ratio) -> candidate list (i, j) in query order, reverse search over the
+    // listed map rows only, then keep the candidates whose map row points back at them
+    int32_t* cand = arena_take<int32_t>(ctx, (size_t)n * 2);
+    int32_t* cand_count = arena_take<int32_t>(ctx, 1);
+    float* sel32 = arena_take<float>(ctx, (size_t)n * dp);
+    uint16_t* sel16 = arena_take<uint16_t>(ctx, (size_t)n * dp);
+    uint8_t* selnz = arena_take<uint8_t>(ctx, n);
+    int32_t* back = arena_take<int32_t>(ctx, n);
+    float* selsim = arena_take<float>(ctx, n);
+    if (!cand || !cand_count || !sel32 || !sel16 || !selnz || !back || !selsim) {
+      set_error("register: scratch arena too small");
+      return VFMREG_ERR_ALLOC;
+    }
+    VFM_TRY(match_tc(ctx, an, ah, nza, n, bn, bh, m, dp, idx01, sim01, sec01));
+    VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, nullptr, n, prune->min_cos, prune->ratio, 0, cand, cand_count));
+    VFM_TRY(gather_rows(ctx, cand, cand_count, n, 1, dp, bn, bh, nzb, sel32, sel16, selnz, sim01, selsim));
+    // <b_j, a_i> has the same canonical value as <a_i, b_j> = sim01[i]: a lower bound of row j's best that starts the
+    // candidate recording near the answer
+    VFM_TRY(match_tc(ctx, sel32, sel16, selnz, n, an, ah, n, dp, back, nullptr, nullptr, cand_count, selsim));
+    return filter_mutual_list(ctx, cand, cand_count, back, n, corr, count);
+  }
   if (flags & VFMREG_MUTUAL) VFM_CHECK_ARG(idx10, "match_nn: VFMREG_MUTUAL needs idx10");
   if (tc) {
     VFM_TRY(match_tc(ctx, an, ah, nza, n, bn, bh, m, dp, idx01, sim01, sec01));
@@ -161,8 +208,10 @@ int vfmreg_create(int device, vfmreg_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   for (int g = 0; g < NUM_GROUPS; ++g) {
-    cudaEventCreate(&ctx->ev0[g]);
-    cudaEventCreate(&ctx->ev1[g]);
+    for (int r = 0; r < vfmreg_ctx::EV_RING; ++r) {
+      cudaEventCreate(&ctx->ev0[g][r]);
+      cudaEventCreate(&ctx->ev1[g][r]);
+    }
   }
   *out = ctx;
   return VFMREG_OK;
@@ -184,8 +233,10 @@ void vfmreg_destroy(vfmreg_ctx* ctx) {
     }
   }
   for (int g = 0; g < NUM_GROUPS; ++g) {
-    cudaEventDestroy(ctx->ev0[g]);
-    cudaEventDestroy(ctx->ev1[g]);
+    for (int r = 0; r < vfmreg_ctx::EV_RING; ++r) {
+      cudaEventDestroy(ctx->ev0[g][r]);
+      cudaEventDestroy(ctx->ev1[g][r]);
+    }
   }
   delete ctx;
 }
@@ -216,19 +267,14 @@ int vfmreg_enable_timing(vfmreg_ctx* ctx, int on) {
     ctx->group_ms[g] = 0.f;
     ctx->group_launches[g] = 0;
     ctx->group_pending[g] = 0;
+    ctx->ev_head[g] = 0;
   }
   return VFMREG_OK;
 }
 
 int vfmreg_group_time_ms(vfmreg_ctx* ctx, int group, float* ms_total, int* launches) {
   VFM_CHECK_ARG(ctx && group >= 0 && group < NUM_GROUPS, "bad group");
-  if (ctx->group_pending[group]) {
-    float ms = 0.f;
-    VFM_CUDA(cudaEventSynchronize(ctx->ev1[group]));
-    VFM_CUDA(cudaEventElapsedTime(&ms, ctx->ev0[group], ctx->ev1[group]));
-    ctx->group_ms[group] += ms;
-    ctx->group_pending[group] = 0;
-  }
+  group_fold(ctx, group, ctx->group_pending[group]);
   if (ms_total) *ms_total = ctx->group_ms[group];
   if (launches) *launches = ctx->group_launches[group];
   return VFMREG_OK;
@@ -275,7 +321,8 @@ struct RegOut {
 static size_t register_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p) {
   const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
   (void)mutual;
-  return match_scratch(ctx, n, m, d, p->flags) + ransac_scratch((int32_t)n, p->n_hyp) + arena_bytes(n, 4) * 3 + arena_bytes(m, 4) +
+  return match_scratch(ctx, n, m, d, p->flags) + (prune_mutual(n, m, p->flags) ? pruned_scratch(ctx, n, d, p->flags) : 0) +
+         ransac_scratch((int32_t)n, p->n_hyp) + arena_bytes(n, 4) * 3 + arena_bytes(m, 4) +
          arena_bytes((size_t)n * 2, 4) + arena_bytes(n, 1) + arena_bytes(16, 8) + arena_bytes(8, 8) + 4096;
 }
 
@@ -288,15 +335,21 @@ static int register_enqueue(vfmreg_ctx* ctx, const float* src_xyz, const float* 
   int32_t* idx01 = arena_take<int32_t>(ctx, n);
   float* sim01 = arena_take<float>(ctx, n);
   float* sec01 = arena_take<float>(ctx, n);
-  int32_t* idx10 = mutual ? arena_take<int32_t>(ctx, m) : nullptr;
-  if (!idx01 || !sim01 || !sec01 || (mutual && !idx10)) {
+  const bool pruned = prune_mutual(n, m, p->flags);
+  int32_t* idx10 = (mutual && !pruned) ? arena_take<int32_t>(ctx, m) : nullptr;
+  if (!idx01 || !sim01 || !sec01 || (mutual && !pruned && !idx10)) {
     set_error("register: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
   int32_t* count = reinterpret_cast<int32_t*>(out.stats + 4);
-  VFM_TRY(match_nn_impl(ctx, src_feats, n, tgt_feats, m, d, p->flags, idx01, sim01, use_ratio ? sec01 : nullptr, idx10,
-                        nullptr, nullptr));
-  VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, idx10, n, p->min_cos, p->ratio, mutual, out.corr, count));
+  if (pruned) {
+    VFM_TRY(match_nn_impl(ctx, src_feats, n, tgt_feats, m, d, p->flags, idx01, sim01, use_ratio ? sec01 : nullptr, nullptr,
+                          nullptr, nullptr, p, out.corr, count));
+  } else {
+    VFM_TRY(match_nn_impl(ctx, src_feats, n, tgt_feats, m, d, p->flags, idx01, sim01, use_ratio ? sec01 : nullptr, idx10,
+                          nullptr, nullptr));
+    VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, idx10, n, p->min_cos, p->ratio, mutual, out.corr, count));
+  }
   return ransac_solve(ctx, src_xyz, tgt_xyz, 0, out.corr, count, (int32_t)n, sample_idx, p->n_hyp, p->seed, p->inlier_thresh,
                       p->refit, out.T, nullptr, nullptr, out.mask, out.stats);
 }

@@ -34,7 +34,8 @@ void set_error(const char* fmt, ...);
     if (rc__ != VFMREG_OK) return rc__; \
   } while (0)
 
-enum { GROUP_MATCH = 0, GROUP_RANSAC = 1, GROUP_PROJECT = 2, GROUP_VIT = 3, NUM_GROUPS = 4 };
+// GROUP_MATCH_PRUNED: the candidate-search launches whose row count lives on the device (pruned reverse search)
+enum { GROUP_MATCH = 0, GROUP_RANSAC = 1, GROUP_PROJECT = 2, GROUP_VIT = 3, GROUP_MATCH_PRUNED = 4, NUM_GROUPS = 5 };
 
 // Bump allocator over one cudaMalloc'd slab.  Scratch is carved per API call and reused by the next call on the
 // same stream (stream order makes that safe); growing the slab synchronises the stream first.
@@ -54,10 +55,13 @@ struct vfmreg_ctx {
   int64_t launches = 0;
   // optional per-group device timing (CUDA events on the context's stream)
   int timing = 0;
-  cudaEvent_t ev0[vfm::NUM_GROUPS] = {}, ev1[vfm::NUM_GROUPS] = {};
+  // a ring of event pairs per group, so that timing a launch never makes the host wait for the previous one
+  static constexpr int EV_RING = 64;
+  cudaEvent_t ev0[vfm::NUM_GROUPS][EV_RING] = {}, ev1[vfm::NUM_GROUPS][EV_RING] = {};
+  int ev_head[vfm::NUM_GROUPS] = {};   // next ring slot to record into
   float group_ms[vfm::NUM_GROUPS] = {};
   int group_launches[vfm::NUM_GROUPS] = {};
-  int group_pending[vfm::NUM_GROUPS] = {};
+  int group_pending[vfm::NUM_GROUPS] = {};   // recorded intervals not yet folded into group_ms (<= EV_RING)
   // pinned staging for small results
   void* pinned = nullptr;
   size_t pinned_cap = 0;
@@ -109,11 +113,19 @@ int match_simt(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64
 size_t match_simt_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m);
 // match_tc.cu: tcgen05 fp16 candidate search + exact fp32 re-rank; same results as match_simt (renormalised inputs only)
 int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
-             const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec);
-size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m);
+             const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev = nullptr,
+             const float* seed = nullptr);
+size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic = false);
+// gather the fp32 / fp16 rows and non-zero flags of b listed in column `col` of the (count, 2) list `pairs`
+int gather_rows(vfmreg_ctx* ctx, const int32_t* pairs, const int32_t* count, int64_t max_rows, int col, int dp, const float* b32,
+                const void* b16, const uint8_t* nzb, float* o32, void* o16, uint8_t* onz, const float* sim = nullptr,
+                float* osim = nullptr);   // osim[k] = sim[pairs[2k]] (the forward score of the listed pair)
 // filter.cu
 int filter_corr(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const float* sec01, const int32_t* idx10,
                 int64_t n, float min_cos, float ratio, int mutual, int32_t* corr, int32_t* count);
+// second half of the pruned mutual check: keep cand[k] = (i, j) iff back[k] == i (back = nearest query of map row j)
+int filter_mutual_list(vfmreg_ctx* ctx, const int32_t* cand, const int32_t* cand_count, const int32_t* back, int64_t max_rows,
+                       int32_t* corr, int32_t* count);
 // ransac.cu
 size_t ransac_scratch(int32_t max_corr, int32_t n_hyp);
 int ransac_solve(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int xyz_f64, const int32_t* corr,

@@ -60,4 +60,90 @@ int filter_corr(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const
   return launch_check(ctx, "filter_corr");
 }
 
+// ---- pruned mutual check -------------------------------------------------------------------------------------------
+// idx10[j] is only ever read at j = idx01[i] of the queries that passed the gate, so the reverse search runs over those
+// map rows only (a compacted copy) instead of all m; the answer per row is unchanged because rows are independent.
+
+// one warp per listed row: 128-bit copies of the fp32 row, the fp16 row and the non-zero flag
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int32_t* __restrict__ pairs, const int32_t* __restrict__ count,
+                                                          int max_rows, int col, int dp, const float* __restrict__ b32,
+                                                          const uint16_t* __restrict__ b16, const uint8_t* __restrict__ nzb,
+                                                          float* __restrict__ o32, uint16_t* __restrict__ o16,
+                                                          uint8_t* __restrict__ onz, const float* __restrict__ sim,
+                                                          float* __restrict__ osim) {
+  const int rows = min(*count, max_rows);
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < rows; k += warps) {
+    const int j = pairs[2 * k + col];
+    const uint4* s32 = reinterpret_cast<const uint4*>(b32 + (size_t)j * dp);
+    uint4* d32 = reinterpret_cast<uint4*>(o32 + (size_t)k * dp);
+    for (int q = lane; q < dp / 4; q += 32) d32[q] = __ldg(s32 + q);
+    const uint4* s16 = reinterpret_cast<const uint4*>(b16 + (size_t)j * dp);
+    uint4* d16 = reinterpret_cast<uint4*>(o16 + (size_t)k * dp);
+    for (int q = lane; q < dp / 8; q += 32) d16[q] = __ldg(s16 + q);
+    if (lane == 0) {
+      onz[k] = nzb[j];
+      if (osim) osim[k] = sim[pairs[2 * k]];
+    }
+  }
+}
+
+int gather_rows(vfmreg_ctx* ctx, const int32_t* pairs, const int32_t* count, int64_t max_rows, int col, int dp, const float* b32,
+                const void* b16, const uint8_t* nzb, float* o32, void* o16, uint8_t* onz, const float* sim, float* osim) {
+  VFM_CHECK_ARG(dp % 8 == 0, "gather_rows: padded dim %d not a multiple of 8", dp);
+  const int blocks = (int)((max_rows + 7) / 8 < ctx->sm_count * 8 ? (max_rows + 7) / 8 : ctx->sm_count * 8);
+  gather_rows_kernel<<<blocks > 0 ? blocks : 1, 256, 0, ctx->stream>>>(pairs, count, (int)max_rows, col, dp, b32,
+                                                                      static_cast<const uint16_t*>(b16), nzb, o32,
+                                                                      static_cast<uint16_t*>(o16), onz, sim, osim);
+  return launch_check(ctx, "gather_rows");
+}
+
+__global__ void __launch_bounds__(1024) filter_mutual_list_kernel(const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_count,
+                                                                 const int32_t* __restrict__ back, int max_rows,
+                                                                 int32_t* __restrict__ corr, int32_t* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int n = min(*cand_count, max_rows);
+  if (t == 0) base_s = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    const int k = start + t;
+    int i = -1, j = -1;
+    bool keep = false;
+    if (k < n) {
+      i = cand[2 * k];
+      j = cand[2 * k + 1];
+      keep = back[k] == i;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[w] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll 1
+    for (int q = 0; q < 32; ++q) {
+      const int v = warp_tot[q];
+      if (q < w) off += v;
+      tot += v;
+    }
+    const int base = base_s;
+    if (keep) {
+      const int pos = base + off + __popc(bal & ((1u << lane) - 1u));
+      corr[2 * pos] = i;
+      corr[2 * pos + 1] = j;
+    }
+    __syncthreads();
+    if (t == 0) base_s = base + tot;
+    __syncthreads();
+  }
+  if (t == 0) *count = base_s;
+}
+
+int filter_mutual_list(vfmreg_ctx* ctx, const int32_t* cand, const int32_t* cand_count, const int32_t* back, int64_t max_rows,
+                       int32_t* corr, int32_t* count) {
+  filter_mutual_list_kernel<<<1, 1024, 0, ctx->stream>>>(cand, cand_count, back, (int)max_rows, corr, count);
+  return launch_check(ctx, "filter_mutual_list");
+}
+
 }  // namespace vfm

@@ -75,19 +75,26 @@ struct TcParams {
   long long* dbg;        // optional per-CTA cycle counters (tuning aid): [cta][8]
   int experiment;        // tuning aid: 1 = producer stops issuing TMA after the first ring fill (timing only, garbage results)
   int top1;              // 1: only the best match is needed (runner-up value not requested): threshold = best - margin
+  const int* n_dev;      // optional: the number of query rows actually present (<= n), produced earlier on the stream
+  const float* seed;     // optional (top1 only): per query row a known lower bound of its exact best score (the pruned
+                         // reverse search knows <b_j, a_i> = sim01[i]); recording starts at seed - margin instead of -inf
 };
 
-__device__ __forceinline__ void flush_slot(const TcParams& P, int rb, int tid, int half, float* ring_v, int* ring_i, int cnt,
-                                           bool ovf, float best, float second) {
+// number of query rows of this launch: the host-side bound, or the device-side count when the caller's row list was
+// compacted on the GPU (the pruned reverse search of the mutual check)
+__device__ __forceinline__ int tc_rows(const TcParams& P) { return P.n_dev ? min(__ldg(P.n_dev), P.n) : P.n; }
+
+__device__ __forceinline__ void flush_slot(const TcParams& P, int n_rows, long long total_tiles, int rb, int tid, int half,
+                                           float* ring_v, int* ring_i, int cnt, bool ovf, float best, float second) {
   const int etid = half * 128 + tid;
   const int row = rb * TBM + tid;
-  if (row >= P.n) return;
+  if (row >= n_rows) return;
   // first CTA whose span [total*c/grid, total*(c+1)/grid) contains this row block's first tile
   const long long t0 = (long long)rb * P.col_tiles;
-  const long long g = gridDim.x;
-  long long c0 = (t0 * g) / P.total_tiles;
-  while ((P.total_tiles * (c0 + 1)) / g <= t0) ++c0;
-  while (c0 > 0 && (P.total_tiles * c0) / g > t0) --c0;
+  const long long g = min((long long)gridDim.x, total_tiles);   // CTAs that own a (non-empty) span
+  long long c0 = (t0 * g) / total_tiles;
+  while ((total_tiles * (c0 + 1)) / g <= t0) ++c0;
+  while (c0 > 0 && (total_tiles * c0) / g > t0) --c0;
   const int slot = (int)(blockIdx.x - c0) * HALVES + half;
   const long long o = ((long long)row * P.slots + slot);
   P.cand_n[o] = cnt | (ovf ? (1 << 30) : 0);
@@ -231,8 +238,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 16 * STAGES + 16 * NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long t_begin = (P.total_tiles * blockIdx.x) / gridDim.x;
-  const long long t_end = (P.total_tiles * (blockIdx.x + 1)) / gridDim.x;
+  const int n_rows = tc_rows(P);
+  const long long total_tiles = (long long)((n_rows + TBM - 1) / TBM) * P.col_tiles;
+  // a device-side row count can leave fewer tiles than CTAs: the first `g_eff` CTAs then own exactly one tile each, the
+  // others none, so that spans are never empty in the middle of a row block (the slot arithmetic relies on it)
+  const long long g_eff = min((long long)gridDim.x, total_tiles);
+  const bool has_work = (long long)blockIdx.x < g_eff;
+  const long long t_begin = has_work ? (total_tiles * blockIdx.x) / g_eff : 0;
+  const long long t_end = has_work ? (total_tiles * (blockIdx.x + 1)) / g_eff : 0;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -336,12 +349,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int rb = (int)(t / P.col_tiles), ct = (int)(t % P.col_tiles);
       if (rb != cur_rb) {
-        if (cur_rb >= 0) flush_slot(P, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second);
+        if (cur_rb >= 0) flush_slot(P, n_rows, total_tiles, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second);
         cur_rb = rb;
         const int row = rb * TBM + tid;
-        active = (row < P.n) && (P.nz[row] != 0);
+        active = (row < n_rows) && (P.nz[row] != 0);
         best = second = -INFINITY;
-        thr = active ? -INFINITY : INFINITY;
+        thr = active ? ((P.seed && P.top1) ? __ldg(P.seed + row) - MARGIN : -INFINITY) : INFINITY;
         cnt = 0;
         ovf = false;
       }
@@ -362,7 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       P.dbg[blockIdx.x * 8 + 4] = clock64() - e_start;
       P.dbg[blockIdx.x * 8 + 5] = w_tfull;
     }
-    if (cur_rb >= 0) flush_slot(P, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second);
+    if (cur_rb >= 0) flush_slot(P, n_rows, total_tiles, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second);
   }
   tc_fence_before();
   __syncthreads();
@@ -392,13 +405,13 @@ constexpr uint32_t S2_RING_I = S2_RING_V + EPI_THREADS * CAP * 4;
 constexpr uint32_t S2_BARS = S2_RING_I + EPI_THREADS * CAP * 4;
 constexpr uint32_t S2_TOTAL = S2_BARS + 256 + 1024;
 
-__device__ __forceinline__ void flush_slot2(const TcParams& P, int rb, int tid, int half, float* ring_v, int* ring_i, int cnt,
-                                            bool ovf, float best, float second, long long total_units, int units_per_rp) {
+__device__ __forceinline__ void flush_slot2(const TcParams& P, int n_rows, int rb, int tid, int half, float* ring_v, int* ring_i,
+                                            int cnt, bool ovf, float best, float second, long long total_units, int units_per_rp) {
   const int etid = half * 128 + tid;
   const int row = rb * TBM + tid;
-  if (row >= P.n) return;
+  if (row >= n_rows) return;
   const long long t0 = (long long)(rb >> 1) * units_per_rp;   // first unit of this row-block pair
-  const long long g = gridDim.x >> 1;                        // clusters
+  const long long g = min((long long)(gridDim.x >> 1), total_units);   // clusters that own a (non-empty) span
   long long c0 = (t0 * g) / total_units;
   while ((total_units * (c0 + 1)) / g <= t0) ++c0;
   while (c0 > 0 && (total_units * c0) / g > t0) --c0;
@@ -429,9 +442,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_cta_rank();
   const long long clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
-  const int row_pairs = (P.n + 2 * TBM - 1) / (2 * TBM);
+  const int n_rows = tc_rows(P);
+  const int row_pairs = (n_rows + 2 * TBM - 1) / (2 * TBM);
   const long long total_units = (long long)row_pairs * P.col_tiles;
-  const long long u_begin = (total_units * cid) / clusters, u_end = (total_units * (cid + 1)) / clusters;
+  // fewer units than clusters (device-side row count): the first `c_eff` clusters own one unit each, the others none
+  const long long c_eff = min(clusters, total_units);
+  const long long u_begin = cid < c_eff ? (total_units * cid) / c_eff : 0;
+  const long long u_end = cid < c_eff ? (total_units * (cid + 1)) / c_eff : 0;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -540,12 +557,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const int rp = (int)(u / P.col_tiles), ct = (int)(u % P.col_tiles);
       const int rb = 2 * rp + (int)rank;
       if (rb != cur_rb) {
-        if (cur_rb >= 0) flush_slot2(P, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second, total_units, P.col_tiles);
+        if (cur_rb >= 0) flush_slot2(P, n_rows, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second, total_units, P.col_tiles);
         cur_rb = rb;
         const int row = rb * TBM + tid;
-        active = (row < P.n) && (P.nz[row] != 0);
+        active = (row < n_rows) && (P.nz[row] != 0);
         best = second = -INFINITY;
-        thr = active ? -INFINITY : INFINITY;
+        thr = active ? ((P.seed && P.top1) ? __ldg(P.seed + row) - MARGIN : -INFINITY) : INFINITY;
         cnt = 0;
         ovf = false;
       }
@@ -558,7 +575,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
-    if (cur_rb >= 0) flush_slot2(P, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second, total_units, P.col_tiles);
+    if (cur_rb >= 0) flush_slot2(P, n_rows, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second, total_units, P.col_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -569,16 +586,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// canonical fp32 inner product: fmaf chain over k ascending (dp % 4 == 0, rows 16-byte aligned)
+// canonical fp32 inner product: fmaf chain over k ascending (dp % 32 == 0 here, rows 16-byte aligned).  The chain is
+// sequential by definition; the loads are not: 8 float4 of each row are requested before the 32 dependent fmaf run.
 __device__ __forceinline__ float canon_dot(const float* __restrict__ x, const float* __restrict__ y, int dp) {
   float acc = 0.0f;
-  for (int k = 0; k < dp; k += 4) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(x + k));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(y + k));
-    acc = fmaf(a.x, b.x, acc);
-    acc = fmaf(a.y, b.y, acc);
-    acc = fmaf(a.z, b.z, acc);
-    acc = fmaf(a.w, b.w, acc);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+#pragma unroll 1
+  for (int k = 0; k < dp / 4; k += 8) {
+    float4 a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a[u] = __ldg(x4 + k + u);
+      b[u] = __ldg(y4 + k + u);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc = fmaf(a[u].x, b[u].x, acc);
+      acc = fmaf(a[u].y, b[u].y, acc);
+      acc = fmaf(a[u].z, b[u].z, acc);
+      acc = fmaf(a[u].w, b[u].w, acc);
+    }
   }
   return acc;
 }
@@ -587,10 +615,12 @@ __device__ __forceinline__ float canon_dot(const float* __restrict__ x, const fl
 // top-2 (second largest of all slot bests / runner-ups, minus the margin), marks the candidates below it -inf and appends
 // the survivors (typically 1-3 per row) to a compact work list (one atomic per warp).
 __global__ void __launch_bounds__(128)
-    rerank_select_kernel(int n, int slots, int top1, const uint8_t* __restrict__ nz, float* __restrict__ cand_v, const int* __restrict__ cand_n,
-                         const float2* __restrict__ slot_top2, int* __restrict__ work, int* __restrict__ work_count) {
+    rerank_select_kernel(int n, const int* __restrict__ n_dev, int slots, int top1, const uint8_t* __restrict__ nz, float* __restrict__ cand_v,
+                         const int* __restrict__ cand_n, const float2* __restrict__ slot_top2, int* __restrict__ work,
+                         int* __restrict__ work_count) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  if (n_dev) n = min(n, __ldg(n_dev));
   int keep[CAP];
   int n_keep = 0;
   if (g < (long long)n * slots) {
@@ -651,10 +681,12 @@ __global__ void __launch_bounds__(128)
 // Re-rank, step 2: one thread per query row picks the exact top-2 (lowest index on ties); rows whose list overflowed are
 // queued for exact_rows_kernel.
 __global__ void __launch_bounds__(128)
-    rerank_pick_kernel(int n, int m, int slots, const uint8_t* __restrict__ nz, const float* __restrict__ cand_v,
-                       const int* __restrict__ cand_i, const int* __restrict__ cand_n, int32_t* __restrict__ idx,
-                       float* __restrict__ best, float* __restrict__ sec, int* __restrict__ redo_list, int* __restrict__ redo_count) {
+    rerank_pick_kernel(int n, const int* __restrict__ n_dev, int m, int slots, const uint8_t* __restrict__ nz,
+                       const float* __restrict__ cand_v, const int* __restrict__ cand_i, const int* __restrict__ cand_n,
+                       int32_t* __restrict__ idx, float* __restrict__ best, float* __restrict__ sec, int* __restrict__ redo_list,
+                       int* __restrict__ redo_count) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, __ldg(n_dev));
   if (row >= n) return;
   if (!nz[row]) {  // all-zero query: every canonical inner product is exactly +0 -> lowest index wins
     idx[row] = 0;
@@ -785,7 +817,10 @@ struct TcPlan {
 // VFMREG_MATCH_V1=1 in the environment keeps the single-CTA streaming kernel (A/B comparison while tuning)
 static bool g_force_v1 = [] { const char* e = getenv("VFMREG_MATCH_V1"); return e && e[0] == '1'; }();
 
-static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, int dp) {
+// `dynamic`: n is only an upper bound, the kernels read the row count from device memory.  The grid is sized for n; the
+// slot bound must then hold for every smaller total: spans of at least one unit cut a row block's col_tiles consecutive
+// units into at most col_tiles + 1 pieces (and spans of at most one unit into at most col_tiles).
+static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, int dp, bool dynamic = false) {
   TcPlan p;
   p.row_blocks = ceil_div(n, TBM);
   p.col_tiles = ceil_div(m, TBN);
@@ -796,7 +831,7 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, int dp) {
     const int clusters = (int)((p.total < ctx->sm_count / 2) ? p.total : ctx->sm_count / 2);
     p.grid = 2 * clusters;
     const long long min_span = p.total / clusters;
-    p.slots = (int)((p.col_tiles + min_span - 1) / min_span) + 1;
+    p.slots = dynamic ? p.col_tiles + 1 : (int)((p.col_tiles + min_span - 1) / min_span) + 1;
     if (p.slots > clusters) p.slots = clusters;
     p.slots *= HALVES;   // column groups per span
     return p;
@@ -805,7 +840,7 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, int dp) {
   p.grid = (int)((p.total < ctx->sm_count) ? p.total : ctx->sm_count);
   // a row block of col_tiles consecutive tiles is cut by at most ceil(col_tiles / floor(total/grid)) + 1 spans
   const long long min_span = p.total / p.grid;
-  p.slots = (int)((p.col_tiles + min_span - 1) / min_span) + 1;
+  p.slots = dynamic ? p.col_tiles + 1 : (int)((p.col_tiles + min_span - 1) / min_span) + 1;
   if (p.slots > p.grid) p.slots = p.grid;
   p.slots *= HALVES;   // column groups per span
   return p;
@@ -813,20 +848,21 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, int dp) {
 
 void match_tc_force_v1(bool on) { g_force_v1 = on; }
 
-size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m) {
-  TcPlan p = tc_plan(ctx, n, m, 64);
-  const TcPlan p1 = tc_plan(ctx, n, m, 1 << 20);
+size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic) {
+  TcPlan p = tc_plan(ctx, n, m, 64, dynamic);
+  const TcPlan p1 = tc_plan(ctx, n, m, 1 << 20, dynamic);
   if (p1.slots > p.slots) p.slots = p1.slots;
   return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
          arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + arena_bytes((size_t)n * p.slots * CAP + 1, 4) + 1024;
 }
 
 // a32/b32: renormalised fp32 rows (n x dp), a16/b16: their fp16 copies, nz_a: non-zero flags of the query rows.
+// n_dev (optional, device): the number of query rows actually present; n is then the capacity of a16 / a32 / nz_a / idx.
 int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
-             const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec) {
+             const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev, const float* seed) {
   VFM_CHECK_ARG(dp % TBK == 0, "match_tc: padded dim %d not a multiple of %d", dp, TBK);
   VFM_CHECK_ARG(n > 0 && m > 0 && n < (1LL << 30) && m < (1LL << 30), "match_tc: bad sizes");
-  const TcPlan plan = tc_plan(ctx, n, m, dp);
+  const TcPlan plan = tc_plan(ctx, n, m, dp, n_dev != nullptr);
   float* cand_v = arena_take<float>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_i = arena_take<int>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_n = arena_take<int>(ctx, (size_t)n * plan.slots);
@@ -860,6 +896,8 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   P.experiment = experiment;
   static const bool force_top1 = [] { const char* e = getenv("VFMREG_TC_TOP1"); return e && e[0] == '1'; }();  // tuning aid
   P.top1 = (sec == nullptr || force_top1) ? 1 : 0;
+  P.n_dev = n_dev;
+  P.seed = seed;
   static const bool want_dbg = [] { const char* e = getenv("VFMREG_TC_DEBUG"); return e && e[0] == '1'; }();
   static long long* dbg_dev = nullptr;
   if (want_dbg) {
@@ -873,7 +911,8 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
     VFM_CUDA(cudaFuncSetAttribute(match_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_TOTAL));
     attr_set = true;
   }
-  group_begin(ctx, GROUP_MATCH);
+  const int grp = n_dev ? GROUP_MATCH_PRUNED : GROUP_MATCH;
+  group_begin(ctx, grp);
   if (plan.paired) {
     match_tc2_kernel<<<plan.grid, TC_THREADS, S2_TOTAL, ctx->stream>>>(map_a, map_b, P);
     VFM_TRY(launch_check(ctx, "match_tc2_kernel"));
@@ -881,13 +920,13 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
     match_tc_kernel<<<plan.grid, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(map_a, map_b, P);
     VFM_TRY(launch_check(ctx, "match_tc_kernel"));
   }
-  group_end(ctx, GROUP_MATCH, 1);
+  group_end(ctx, grp, 1);
   const long long entries = (long long)n * plan.slots;
-  rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, plan.slots, P.top1, nz_a, cand_v, cand_n, slot_top2, work + 1, work);
+  rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, n_dev, plan.slots, P.top1, nz_a, cand_v, cand_n, slot_top2, work + 1, work);
   VFM_TRY(launch_check(ctx, "rerank_select_kernel"));
   rerank_dot_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work + 1, work);
   VFM_TRY(launch_check(ctx, "rerank_dot_kernel"));
-  rerank_pick_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(n, (int)m, plan.slots, nz_a, cand_v, cand_i, cand_n, idx, best, sec,
+  rerank_pick_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>((int)n, n_dev, (int)m, plan.slots, nz_a, cand_v, cand_i, cand_n, idx, best, sec,
                                                                redo + 1, redo);
   VFM_TRY(launch_check(ctx, "rerank_pick_kernel"));
   exact_rows_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(a32, b32, (int)m, dp, redo + 1, redo, idx, best, sec);
