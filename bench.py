@@ -57,7 +57,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -137,7 +137,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-step", type=int, default=4)
+    ap.add_argument("--pairs-per-step", type=int, default=8)
+    ap.add_argument("--lanes", type=int, default=0, help="compute lanes of register_batch (0 = library default)")
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -164,6 +165,8 @@ def main():
     import vfm_registration_b200 as v
     from vfm_registration_b200 import synth
     ctx = v.get_context(local_rank)
+    if args.lanes:
+        ctx.set_lanes(args.lanes)
     P = args.pairs_per_step
     peaks = load_peaks()
 
@@ -218,9 +221,17 @@ def main():
     ransac_ms, ransac_launches = ctx.group_time_ms(1)
     pruned_ms, pruned_launches = ctx.group_time_ms(4)
     ctx.enable_timing(False)
-    clocks = sampler.stop() if rank == 0 else None
+    # the same kernel timed with nothing beside it (one lane), for the record: inside the timed region above it shares
+    # the SMs with the small kernels of the neighbouring pairs
+    ctx.set_lanes(1)
+    ctx.enable_timing(True)
+    timed(dev_pairs, 2, 1)
+    alone_ms, alone_launches = ctx.group_time_ms(0)
+    ctx.enable_timing(False)
+    ctx.set_lanes(args.lanes or 3)
     ms_e2e, _, res_e2e = timed(pin_pairs, max(2, args.steps // 2), 2, host=True)
     e2e_steps = max(2, args.steps // 2)
+    clocks = sampler.stop() if rank == 0 else None   # sampled over the device-resident and the host-buffer timed regions
 
     # parity guard inside the bench: device path and host path give the same transforms
     for a, b in zip(res, res_e2e):
@@ -249,10 +260,14 @@ def main():
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-    roofline = {"bound": "tensor", "kernel": "match_tc2_kernel: descriptor N x M candidate search, scan -> map (full)",
+    roofline = {"bound": "tensor", "kernel": "match_tc3_kernel: descriptor N x M candidate search, scan -> map (full), timed while sharing the SMs with the other lanes",
                 "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
                 "peak_source": f"{peaks['source']} bf16 burst", "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
                 "algorithmic_bytes": alg_bytes_per_launch, "avg_launch_ms": avg_ms,
+                "alone": {"avg_launch_ms": alone_ms / max(alone_launches, 1),
+                          "achieved": flop_per_launch / (alone_ms / max(alone_launches, 1) * 1e-3) / 1e12,
+                          "frac": flop_per_launch / (alone_ms / max(alone_launches, 1) * 1e-3) / 1e12 / peaks["tf"],
+                          "note": "same kernel, one lane: nothing else resident on the SMs"},
                 "launches_timed": match_launches, "algorithmic_gbs": alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9,
                 "share_of_step": avg_ms * (match_launches / ((args.steps + args.warmup) * P)) * P / (ms_dev / args.steps),
                 "full_search_launches_per_pair": match_launches / ((args.steps + args.warmup) * P),
@@ -266,7 +281,8 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 match / f64 solve", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "parallelism": f"pairs sharded over {world} rank(s)",
-                       "l2": f"{P} distinct pairs x 92 MB cycled per step (> 126 MB L2)", "algo": args.algo},
+                       "l2": f"{P} distinct pairs x 92 MB cycled per step (> 126 MB L2)", "algo": args.algo,
+                       "lanes": args.lanes or 3},
             "hyps_per_sec": value * N_HYP, "recall_at_1m_5deg": recall,
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

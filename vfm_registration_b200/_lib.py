@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvfmreg_b200.so")
+# VFMREG_LIB: load another build of the same library (kernel tuning experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("VFMREG_LIB") or os.path.join(HERE, "libvfmreg_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOGPU, ERR_ALLOC = 0, 1, 2, 3, 4
 NORMALIZE, MUTUAL = 0x1, 0x2
@@ -48,6 +49,7 @@ _SIGS = {
     "vfmreg_last_error": (C.c_char_p, []),
     "vfmreg_device_count": (C.c_int, []),
     "vfmreg_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "vfmreg_set_lanes": (C.c_int, [_P, C.c_int]),
     "vfmreg_destroy": (None, [_P]),
     "vfmreg_set_stream": (C.c_int, [_P, _P]),
     "vfmreg_sync": (C.c_int, [_P]),

@@ -65,6 +65,10 @@ class Context:
     def enable_timing(self, on: bool = True):
         _lib.check(self.lib.vfmreg_enable_timing(self.handle, int(on)))
 
+    def set_lanes(self, lanes: int):
+        """Number of CUDA streams ``register_batch`` spreads consecutive (device-resident) pairs over (1..4, default 3)."""
+        _lib.check(self.lib.vfmreg_set_lanes(self.handle, int(lanes)), "vfmreg_set_lanes")
+
     def group_time_ms(self, group: int):
         ms, n = C.c_float(), C.c_int()
         _lib.check(self.lib.vfmreg_group_time_ms(self.handle, group, C.byref(ms), C.byref(n)))

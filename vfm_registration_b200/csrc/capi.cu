@@ -207,6 +207,10 @@ int vfmreg_create(int device, vfmreg_ctx** out) {
   vfmreg_ctx* ctx = new vfmreg_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("VFMREG_LANES")) {   // tuning aid; vfmreg_set_lanes is the API
+    const int l = atoi(e);
+    if (l >= 1 && l <= vfmreg_ctx::MAX_LANES) ctx->lanes = l;
+  }
   for (int g = 0; g < NUM_GROUPS; ++g) {
     for (int r = 0; r < vfmreg_ctx::EV_RING; ++r) {
       cudaEventCreate(&ctx->ev0[g][r]);
@@ -232,6 +236,13 @@ void vfmreg_destroy(vfmreg_ctx* ctx) {
       cudaEventDestroy(ctx->ev_consumed[i]);
     }
   }
+  for (int l = 1; l < vfmreg_ctx::MAX_LANES; ++l) {
+    if (!ctx->lane_stream[l]) continue;
+    cudaStreamSynchronize(ctx->lane_stream[l]);
+    cudaStreamDestroy(ctx->lane_stream[l]);
+    cudaEventDestroy(ctx->ev_join[l]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (int g = 0; g < NUM_GROUPS; ++g) {
     for (int r = 0; r < vfmreg_ctx::EV_RING; ++r) {
       cudaEventDestroy(ctx->ev0[g][r]);
@@ -259,6 +270,13 @@ int vfmreg_sync(vfmreg_ctx* ctx) {
 }
 
 int64_t vfmreg_kernel_launches(const vfmreg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vfmreg_set_lanes(vfmreg_ctx* ctx, int lanes) {
+  VFM_CHECK_ARG(ctx, "null context");
+  VFM_CHECK_ARG(lanes >= 1 && lanes <= vfmreg_ctx::MAX_LANES, "set_lanes: %d not in [1, %d]", lanes, vfmreg_ctx::MAX_LANES);
+  ctx->lanes = lanes;
+  return VFMREG_OK;
+}
 
 int vfmreg_enable_timing(vfmreg_ctx* ctx, int on) {
   VFM_CHECK_ARG(ctx, "null context");
@@ -394,6 +412,24 @@ static int register_impl(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt
   fill_result(result, pin, p->inlier_thresh);
   return VFMREG_OK;
 }
+
+static int ensure_lanes(vfmreg_ctx* ctx, int lanes) {
+  if (!ctx->ev_fork) VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  for (int l = 1; l < lanes; ++l) {
+    if (ctx->lane_stream[l]) continue;
+    VFM_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+    VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming));
+  }
+  return VFMREG_OK;
+}
+
+// Restores the context's stream when a batch entry point leaves (also on an error return in the middle of a batch).
+struct StreamGuard {
+  vfmreg_ctx* ctx;
+  cudaStream_t saved;
+  explicit StreamGuard(vfmreg_ctx* c) : ctx(c), saved(c->stream) {}
+  ~StreamGuard() { ctx->stream = saved; }
+};
 
 static int check_register_args(vfmreg_ctx* ctx, const void* a, const void* b, const void* c, const void* e, int64_t n,
                                int64_t m, int32_t d, const vfmreg_register_params* p, vfmreg_register_result* r) {
@@ -570,29 +606,52 @@ int vfmreg_register_batch(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* 
     n_max = n[i] > n_max ? n[i] : n_max;
   }
   VFM_CUDA(cudaSetDevice(ctx->device));
-  // scratch arena: [per-pair (T, stats) slots | fallback corr/mask | per-pair scratch (reused in stream order)]
+  // scratch arena: [per-pair (T, stats) slots | per lane: fallback corr/mask + per-pair scratch (reused in stream order)]
+  const int lanes = ctx->lanes < n_pairs ? ctx->lanes : n_pairs;
   const size_t slots_bytes = (size_t)n_pairs * 256;
   const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
+  const size_t lane_bytes = out_bytes + scratch + 4096;
   arena_reset(ctx);
-  VFM_TRY(arena_reserve(ctx, slots_bytes + out_bytes + scratch + 4096));
+  VFM_TRY(arena_reserve(ctx, slots_bytes + lanes * lane_bytes + 4096));
   VFM_TRY(ensure_pinned(ctx, slots_bytes));
   char* slots = arena_take<char>(ctx, slots_bytes);
-  int32_t* corr_fb = arena_take<int32_t>(ctx, (size_t)n_max * 2);
-  uint8_t* mask_fb = arena_take<uint8_t>(ctx, n_max);
-  if (!slots || !corr_fb || !mask_fb) {
+  if (!slots) {
     set_error("register_batch: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
   const size_t mark = ctx->arena.off;
+  StreamGuard guard(ctx);
+  cudaStream_t lane_streams[vfmreg_ctx::MAX_LANES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
+  if (lanes > 1) {
+    VFM_TRY(ensure_lanes(ctx, lanes));
+    VFM_CUDA(cudaEventRecord(ctx->ev_fork, guard.saved));          // inputs are ready in the caller's stream order
+    for (int l = 1; l < lanes; ++l) {
+      lane_streams[l] = ctx->lane_stream[l];
+      VFM_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
+    }
+  }
   for (int i = 0; i < n_pairs; ++i) {
+    const int lane = i % lanes;
+    ctx->stream = lane_streams[lane];
+    ctx->arena.off = mark + (size_t)lane * lane_bytes;   // every pair of a lane reuses the lane's region (stream order)
+    int32_t* corr_fb = arena_take<int32_t>(ctx, (size_t)n_max * 2);
+    uint8_t* mask_fb = arena_take<uint8_t>(ctx, n_max);
+    if (!corr_fb || !mask_fb) {
+      set_error("register_batch: scratch arena too small");
+      return VFMREG_ERR_ALLOC;
+    }
     RegOut out;
     out.corr = (corr_out && corr_out[i]) ? corr_out[i] : corr_fb;
     out.mask = (mask_out && mask_out[i]) ? mask_out[i] : mask_fb;
     out.T = (double*)(slots + (size_t)i * 256);
     out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
-    ctx->arena.off = mark;   // every pair reuses the same scratch region (stream order)
     VFM_TRY(register_enqueue(ctx, src_xyz[i], tgt_xyz[i], src_feats[i], tgt_feats[i], n[i], m[i], d, params,
                              sample_idx ? sample_idx[i] : nullptr, out));
+  }
+  ctx->stream = guard.saved;
+  for (int l = 1; l < lanes; ++l) {
+    VFM_CUDA(cudaEventRecord(ctx->ev_join[l], ctx->lane_stream[l]));
+    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
   }
   VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, slots_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   VFM_CUDA(cudaStreamSynchronize(ctx->stream));

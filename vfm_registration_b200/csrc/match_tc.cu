@@ -105,6 +105,22 @@ __device__ __forceinline__ void flush_slot(const TcParams& P, int n_rows, long l
   }
 }
 
+#ifdef VFM_SCAN_STATS
+// tuning aid (-DVFM_SCAN_STATS): warp-level counts of [0] chunks scanned, [1] chunks where some lane cleared its threshold,
+// [2] lane-chunks with several qualifying columns, [3] lane-chunks with at least one
+__device__ unsigned long long g_scan_stats[4];
+#define SCAN_STAT(i, pred)                                                                 \
+  do {                                                                                     \
+    const unsigned b__ = __ballot_sync(0xffffffffu, (pred));                               \
+    if ((threadIdx.x & 31) == 0 && b__) atomicAdd(&g_scan_stats[i], (i) == 3 ? (unsigned long long)__popc(b__) : 1ull); \
+  } while (0)
+// lane-level variant, safe inside divergent code
+#define SCAN_STAT_LANE(i, pred) do { if (pred) atomicAdd(&g_scan_stats[i], 1ull); } while (0)
+#else
+#define SCAN_STAT(i, pred) do { } while (0)
+#define SCAN_STAT_LANE(i, pred) do { } while (0)
+#endif
+
 // Record one candidate (approximate score v of column `col`) in the thread's list and raise the recording threshold.
 template <bool TOP1>
 __device__ __forceinline__ void push_candidate(float v, int col, int tid, float* ring_v, int* ring_i, float& best, float& second,
@@ -139,60 +155,79 @@ __device__ __forceinline__ void push_candidate(float v, int col, int tid, float*
   thr = (TOP1 ? best : second) - MARGIN;
 }
 
-__device__ __forceinline__ float tc_ld1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  return __uint_as_float(r);
+// r[i] for a lane-dependent i without local memory: a 5-level select tree (31 SEL)
+__device__ __forceinline__ float pick32(const uint32_t* r, int i) {
+  uint32_t a[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = (i & 16) ? r[16 + k] : r[k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = (i & 8) ? a[8 + k] : a[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = (i & 4) ? a[4 + k] : a[k];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) a[k] = (i & 2) ? a[2 + k] : a[k];
+  return __uint_as_float((i & 1) ? a[1] : a[0]);
 }
 
-// One 32-column chunk of a query row (r[i] = approximate score of column col_base + c0 + i; the chunk sits at TMEM
-// address `t_chunk`).  Fast path: a 3-input max tree and one compare, registers only.  When the maximum clears the
-// recording threshold the lane locates it and counts how many values clear the threshold, still in registers; the usual
-// case (exactly one) is a single push.  The rare chunk with several qualifying values is re-read from TMEM one column at
-// a time by the whole warp (tcgen05.ld is warp-collective), which keeps the kernel small enough for the instruction cache
-// and needs no shared-memory staging.  `tid` is the thread's index among the epilogue threads.
+// One 32-column chunk of a query row (r[i] = approximate score of column col_base + c0 + i), registers only.
+// Fast path: four group maxima (group q = columns i % 4 == q), their maximum and one compare against the recording
+// threshold.  When the maximum clears the threshold, only the groups whose maximum clears it are searched for the
+// qualifying columns (a bit mask); the usual case -- exactly one -- is a single push of (mx, position).  Several
+// qualifying columns are pushed in ascending column order through a select tree.  `tid` is the thread's index among
+// the epilogue threads.
 template <bool TOP1>
-__device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid, int col_base, int tid, uint32_t t_chunk,
-                                           float* ring_v, int* ring_i, float& best, float& second, float& thr, int& cnt, bool& ovf) {
+__device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid, int col_base, int tid, float* ring_v, int* ring_i,
+                                           float& best, float& second, float& thr, int& cnt, bool& ovf) {
   if (c0 >= valid) return;  // warp-uniform
   const bool partial = c0 + 32 > valid;  // warp-uniform: columns >= valid hold zeros (TMA out-of-bounds fill)
-  float m0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), m1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
-  float m2 = fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), m3 = fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7]));
+  float g[4];
 #pragma unroll
-  for (int i = 8; i < 32; i += 4) {
-    m0 = fmaxf(m0, __uint_as_float(r[i]));
-    m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
-    m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
-    m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+  for (int q = 0; q < 4; ++q) {
+    float m = fmaxf(__uint_as_float(r[q]), __uint_as_float(r[q + 4]));
+#pragma unroll
+    for (int j = 2; j < 8; ++j) m = fmaxf(m, __uint_as_float(r[4 * j + q]));
+    g[q] = m;
   }
-  const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  bool multi = false;
+  const float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+  SCAN_STAT(0, true);
   if (thr == -INFINITY && !partial) {
     // Nothing recorded yet in this span: seed the threshold from this chunk.  TOP1: its maximum.  Otherwise a lower bound
-    // of its second largest value: the smaller of two disjoint group maxima (m0/m2 cover i % 4 in {0, 2}, m1/m3 the rest).
-    const float seed = TOP1 ? mx : fminf(fmaxf(m0, m2), fmaxf(m1, m3));
+    // of its second largest value: the smaller of two disjoint group maxima.
+    const float seed = TOP1 ? mx : fminf(fmaxf(g[0], g[2]), fmaxf(g[1], g[3]));
     thr = seed - MARGIN;   // strictly below `seed`, so the values that define it are still recorded below
   }
+  SCAN_STAT(1, mx > thr);
+#if defined(VFM_SCAN_EXP) && VFM_SCAN_EXP == 1
+  if (mx > thr) { best = mx; thr = mx - MARGIN; }   // timing experiment: branch + threshold update only
+  return;
+#endif
   if (mx > thr) {
-    int n_above = 0, imax = 0;
+    uint32_t mask = 0;
 #pragma unroll
-    for (int i = 31; i >= 0; --i) {
-      const float v = __uint_as_float(r[i]);
-      n_above += (v > thr) ? 1 : 0;
-      imax = (v == mx) ? i : imax;
+    for (int q = 0; q < 4; ++q) {
+      if (g[q] > thr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mask |= (__uint_as_float(r[4 * j + q]) > thr) ? (1u << (4 * j + q)) : 0u;
+      }
     }
-    if (n_above == 1 && !partial)
-      push_candidate<TOP1>(mx, col_base + c0 + imax, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
-    else
-      multi = true;
-  }
-  if (__any_sync(0xffffffffu, multi)) {  // warp-uniform slow path
-    const int lim = min(32, valid - c0);
+    if (partial) mask &= (1u << (valid - c0)) - 1u;
+#if defined(VFM_SCAN_EXP) && VFM_SCAN_EXP == 2
+    best = mx; thr = mx - MARGIN; cnt = (cnt + __popc(mask)) & 7;   // timing experiment: mask, no recording
+    return;
+#endif
+    SCAN_STAT_LANE(2, (mask & (mask - 1)) != 0);
+    SCAN_STAT_LANE(3, mask != 0);
+    if (!partial && (mask & (mask - 1)) == 0) {
+      // exactly one qualifying column: it is the chunk maximum (mask != 0 because mx > thr and every column is valid)
+      push_candidate<TOP1>(mx, col_base + c0 + __ffs(mask) - 1, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
+    } else {
 #pragma unroll 1
-    for (int i = 0; i < lim; ++i) {
-      const float v = tc_ld1(t_chunk + i);
-      if (multi && v > thr) push_candidate<TOP1>(v, col_base + c0 + i, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
+      while (mask) {
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float v = pick32(r, i);
+        if (v > thr) push_candidate<TOP1>(v, col_base + c0 + i, tid, ring_v, ring_i, best, second, thr, cnt, ovf);
+      }
     }
   }
 }
@@ -209,15 +244,62 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_addr, int col_base, int
   for (int c = 0; c < COLS_PER_WARP / 32; c += 2) {
     tc_wait_ld();
     tc_ld32(t_addr + (c + 1) * 32, rbuf);  // in flight while chunk c is scanned
-    scan_chunk<TOP1>(ra, c * 32, valid, col_base, etid, t_addr + c * 32, ring_v, ring_i, best, second, thr, cnt, ovf);
+    scan_chunk<TOP1>(ra, c * 32, valid, col_base, etid, ring_v, ring_i, best, second, thr, cnt, ovf);
     tc_wait_ld();
     if (c + 2 < COLS_PER_WARP / 32) tc_ld32(t_addr + (c + 2) * 32, ra);
-    scan_chunk<TOP1>(rbuf, (c + 1) * 32, valid, col_base, etid, t_addr + (c + 1) * 32, ring_v, ring_i, best, second, thr, cnt, ovf);
+    scan_chunk<TOP1>(rbuf, (c + 1) * 32, valid, col_base, etid, ring_v, ring_i, best, second, thr, cnt, ovf);
   }
 }
 
+// timing experiment (garbage results): the fast path of the scan only (double-buffered loads + max tree), no recording
+__device__ __forceinline__ void epilogue_max_only(uint32_t t_addr, float& best) {
+  uint32_t ra[32], rbuf[32];
+  tc_ld32(t_addr, ra);
+#pragma unroll 1
+  for (int c = 0; c < COLS_PER_WARP / 32; c += 2) {
+    tc_wait_ld();
+    tc_ld32(t_addr + (c + 1) * 32, rbuf);
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      m0 = fmaxf(m0, __uint_as_float(ra[i]));
+      m1 = fmaxf(m1, __uint_as_float(ra[i + 1]));
+      m2 = fmaxf(m2, __uint_as_float(ra[i + 2]));
+      m3 = fmaxf(m3, __uint_as_float(ra[i + 3]));
+    }
+    best = fmaxf(best, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+    tc_wait_ld();
+    if (c + 2 < COLS_PER_WARP / 32) tc_ld32(t_addr + (c + 2) * 32, ra);
+    m0 = m1 = m2 = m3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      m0 = fmaxf(m0, __uint_as_float(rbuf[i]));
+      m1 = fmaxf(m1, __uint_as_float(rbuf[i + 1]));
+      m2 = fmaxf(m2, __uint_as_float(rbuf[i + 2]));
+      m3 = fmaxf(m3, __uint_as_float(rbuf[i + 3]));
+    }
+    best = fmaxf(best, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+  }
+}
+
+// timing experiments (garbage results): drain the accumulator without scanning it
+__device__ __forceinline__ void epilogue_loads_only(uint32_t t_addr, float& best) {
+  uint32_t ra[32];
+  uint32_t x = 0;
+#pragma unroll 1
+  for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+    tc_ld32(t_addr + c * 32, ra);
+    tc_wait_ld();
+    x ^= ra[0] ^ ra[31];
+  }
+  if (x == 0x12345678u) best = 0.f;
+}
+
 __device__ __forceinline__ void epilogue_tile(bool top1, uint32_t t_addr, int col_base, int m, int etid, float* ring_v, int* ring_i,
-                                              float& best, float& second, float& thr, int& cnt, bool& ovf) {
+                                              float& best, float& second, float& thr, int& cnt, bool& ovf, int experiment = 0) {
+  if (experiment == 2) { epilogue_loads_only(t_addr, best); return; }
+  if (experiment == 3) return;
+  if (experiment == 4) { epilogue_max_only(t_addr, best); return; }
   if (top1)
     epilogue_half<true>(t_addr, col_base, m, etid, ring_v, ring_i, best, second, thr, cnt, ovf);
   else
@@ -586,6 +668,219 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Version 3: CTA-pair MMA (tcgen05.mma.cta_group::2).  One instruction issued by the leader CTA computes a 256 x 256 x 16
+// block on the tensor cores of both SMs of the pair: each CTA holds its own 128 query rows (A) and HALF of the 256-column
+// database tile (B) in its own shared memory, and receives the 128 x 256 accumulator rows of its query block in its own
+// TMEM.  Against version 2 (two independent M128 N256 MMAs fed by multicast) the shared-memory operand traffic per MMA
+// drops from 12 KB to 8 KB per SM -- the measured limiter of versions 1/2 (profiles/r1_kernel_bench.txt) -- and every
+// database byte still crosses L2 -> SM once per pair without multicast.
+//   RESIDENT (dp <= 384): the query block stays in shared memory for the whole row of column tiles; only B is streamed.
+//   otherwise (dp up to 1024): A and B chunks are streamed together.
+// Barriers: `full` / `afull` / `tempty` live in the leader (both CTAs' TMA loads credit the leader's barriers through
+// .cta_group::2 loads; the peer's epilogue warps arrive remotely); `empty` / `aempty` / `tfull` exist in both CTAs and are
+// signalled by multicast tcgen05.commit.
+constexpr int STAGES3 = 6;
+constexpr uint32_t S3_A = 0;                                   // RESIDENT: dp/64 chunks; streaming: STAGES3 chunks
+constexpr uint32_t S3_B = A_MAX_KB * A_STAGE_BYTES;            // STAGES3 x (128 database rows x 64 k) = 16 KB each
+constexpr uint32_t S3_RING_V = S3_B + STAGES3 * B_HALF_BYTES;
+constexpr uint32_t S3_RING_I = S3_RING_V + EPI_THREADS * CAP * 4;
+constexpr uint32_t S3_BARS = S3_RING_I + EPI_THREADS * CAP * 4;
+constexpr uint32_t S3_TOTAL = S3_BARS + 256 + 1024;
+constexpr uint32_t IDESC3 = umma_idesc_f16(2 * TBM, TBN, 0);
+static_assert(TBN == 256 && NBUF == 2, "version 3 is written for 256-column tiles");
+static_assert(STAGES3 <= A_MAX_KB, "streamed A chunks reuse the resident region");
+
+template <bool RESIDENT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    match_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sA = base + S3_A, sB = base + S3_B;
+  float* ring_v = reinterpret_cast<float*>(smem + S3_RING_V);
+  int* ring_i = reinterpret_cast<int*>(smem + S3_RING_I);
+  const uint32_t bars = base + S3_BARS;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES3, tfull0 = bars + 16 * STAGES3, tempty0 = tfull0 + 8 * NBUF;
+  const uint32_t afull = tempty0 + 8 * NBUF, aempty = afull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S3_BARS + 16 * STAGES3 + 16 * NBUF + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_cta_rank();
+  const long long clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int n_rows = tc_rows(P);
+  const int row_pairs = (n_rows + 2 * TBM - 1) / (2 * TBM);
+  const long long total_units = (long long)row_pairs * P.col_tiles;
+  const long long c_eff = min(clusters, total_units);
+  const long long u_begin = cid < c_eff ? (total_units * cid) / c_eff : 0;
+  const long long u_end = cid < c_eff ? (total_units * (cid + 1)) / c_eff : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < STAGES3; ++s) {
+      mbar_init(full0 + 8 * s, 1);    // leader: one arrive.expect_tx per phase, bytes from both CTAs' loads
+      mbar_init(empty0 + 8 * s, 1);   // both CTAs: multicast commit from the leader's MMA warp
+    }
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);                // both CTAs: multicast commit
+      mbar_init(tempty0 + 8 * b, 2 * EPI_WARPS);   // leader: epilogue warps of both CTAs
+    }
+    mbar_init(afull, 1);
+    mbar_init(aempty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit / 2-SM load
+  if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: each CTA loads its own query rows and its half of the database tile =====
+    uint32_t stage = 0, phase = 0, aphase = 0;
+    int cur_rp = -1;
+    const uint32_t afull_leader = mapa_cluster(afull, 0);
+    long long w_empty = 0;
+    const long long p_start = clock64();
+    for (long long u = u_begin; u < u_end; ++u) {
+      const int rp = (int)(u / P.col_tiles), ct = (int)(u % P.col_tiles);
+      if (RESIDENT && rp != cur_rp) {
+        cur_rp = rp;
+        mbar_wait(aempty, aphase ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(afull, 2u * (uint32_t)P.kb * A_STAGE_BYTES);
+          for (int kb = 0; kb < P.kb; ++kb)
+            tma_load_2d_2sm(sA + kb * A_STAGE_BYTES, &map_a, afull_leader, kb * TBK, (2 * rp + (int)rank) * TBM);
+        }
+        __syncwarp();
+        aphase ^= 1;
+      }
+#pragma unroll 1
+      for (int kb = 0; kb < P.kb; ++kb) {
+        const long long c0 = clock64();
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        w_empty += clock64() - c0;
+        if (elect_one()) {
+          const uint32_t full_leader = mapa_cluster(full0 + 8 * stage, 0);
+          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, RESIDENT ? 2u * B_HALF_BYTES : 2u * (B_HALF_BYTES + A_STAGE_BYTES));
+          if (!RESIDENT) tma_load_2d_2sm(sA + stage * A_STAGE_BYTES, &map_a, full_leader, kb * TBK, (2 * rp + (int)rank) * TBM);
+          tma_load_2d_2sm(sB + stage * B_HALF_BYTES, &map_b, full_leader, kb * TBK, ct * TBN + (int)rank * (TBN / 2));
+        }
+        __syncwarp();
+        if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (P.dbg && lane == 0) {
+      P.dbg[blockIdx.x * 8 + 6] = w_empty;
+      P.dbg[blockIdx.x * 8 + 7] = clock64() - p_start;
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA only =====
+    if (rank == 0) {
+      uint32_t stage = 0, phase = 0, aphase = 0;
+      long long it = 0;
+      int cur_rp = -1;
+      const uint64_t da0 = umma_desc_k_sw128(sA), db0 = umma_desc_k_sw128(sB);
+      long long w_tempty = 0, w_full = 0;
+      const long long t_start = clock64();
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int rp = (int)(u / P.col_tiles);
+        const uint32_t buf = (uint32_t)(it % NBUF);
+        long long c0 = clock64();
+        mbar_wait(tempty0 + 8 * buf, (uint32_t)((it / NBUF) & 1) ^ 1);
+        w_tempty += clock64() - c0;
+        if (RESIDENT && rp != cur_rp) {
+          cur_rp = rp;
+          mbar_wait(afull, aphase);
+          aphase ^= 1;
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * TBN;
+        const bool last_of_rp = (u + 1 == u_end) || ((int)((u + 1) / P.col_tiles) != rp);
+#pragma unroll 1
+        for (int kb = 0; kb < P.kb; ++kb) {
+          c0 = clock64();
+          mbar_wait(full0 + 8 * stage, phase);
+          w_full += clock64() - c0;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = da0 + (uint64_t)((RESIDENT ? kb : (int)stage) * (A_STAGE_BYTES >> 4));
+            const uint64_t db = db0 + (uint64_t)(stage * (B_HALF_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < TBK / UMMA_K; ++k)
+              tc_mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC3, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_2sm(empty0 + 8 * stage, (uint16_t)3);   // stage free in both CTAs once these MMAs have read it
+            if (kb == P.kb - 1) {
+              tc_commit_2sm(tfull0 + 8 * buf, (uint16_t)3);   // accumulator halves complete -> both epilogues
+              if (RESIDENT && last_of_rp) tc_commit_2sm(aempty, (uint16_t)3);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (P.dbg && lane == 0) {
+        P.dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
+        P.dbg[blockIdx.x * 8 + 1] = w_tempty;
+        P.dbg[blockIdx.x * 8 + 2] = w_full;
+        P.dbg[blockIdx.x * 8 + 3] = it;
+      }
+    }
+  } else {
+    // ===== epilogue (as in versions 1/2): this CTA's 128 rows x 256 columns =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int tid = q * 32 + lane;
+    const int etid = half * 128 + tid;
+    int cur_rb = -1;
+    float best = -INFINITY, second = -INFINITY, thr = -INFINITY;
+    int cnt = 0;
+    bool ovf = false, active = false;
+    long long it = 0;
+    long long w_tfull = 0;
+    const long long e_start = clock64();
+    for (long long u = u_begin; u < u_end; ++u, ++it) {
+      const int rp = (int)(u / P.col_tiles), ct = (int)(u % P.col_tiles);
+      const int rb = 2 * rp + (int)rank;
+      if (rb != cur_rb) {
+        if (cur_rb >= 0) flush_slot2(P, n_rows, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second, total_units, P.col_tiles);
+        cur_rb = rb;
+        const int row = rb * TBM + tid;
+        active = (row < n_rows) && (P.nz[row] != 0);
+        best = second = -INFINITY;
+        thr = active ? ((P.seed && P.top1) ? __ldg(P.seed + row) - MARGIN : -INFINITY) : INFINITY;
+        cnt = 0;
+        ovf = false;
+      }
+      const uint32_t buf = (uint32_t)(it % NBUF);
+      const long long c0 = clock64();
+      mbar_wait(tfull0 + 8 * buf, (uint32_t)((it / NBUF) & 1));
+      w_tfull += clock64() - c0;
+      tc_fence_after();
+      epilogue_tile(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * COLS_PER_WARP, ct * TBN + half * COLS_PER_WARP,
+                    P.m, etid, ring_v, ring_i, best, second, thr, cnt, ovf, P.experiment);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(tempty0 + 8 * buf, 0));
+    }
+    if (P.dbg && warp == 2 && lane == 0) {
+      P.dbg[blockIdx.x * 8 + 4] = clock64() - e_start;
+      P.dbg[blockIdx.x * 8 + 5] = w_tfull;
+    }
+    if (cur_rb >= 0) flush_slot2(P, n_rows, cur_rb, tid, half, ring_v, ring_i, cnt, ovf, best, second, total_units, P.col_tiles);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs are done with the pair's TMEM and with each other's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512u);
+  }
+}
+
 // canonical fp32 inner product: fmaf chain over k ascending (dp % 32 == 0 here, rows 16-byte aligned).  The chain is
 // sequential by definition; the loads are not: 8 float4 of each row are requested before the 32 dependent fmaf run.
 __device__ __forceinline__ float canon_dot(const float* __restrict__ x, const float* __restrict__ y, int dp) {
@@ -811,11 +1106,14 @@ static int make_map_f16(CUtensorMap* map, const void* ptr, int64_t rows, int dp,
 struct TcPlan {
   int row_blocks, col_tiles, grid, slots;
   long long total;
-  bool paired;   // version 2: CTA pairs, resident query block, multicast database tiles
+  bool paired;   // CTA pairs: version 3 (cta_group::2 MMA) or version 2 (resident query block + multicast database tiles)
+  int version;   // 1, 2 or 3
 };
 
-// VFMREG_MATCH_V1=1 in the environment keeps the single-CTA streaming kernel (A/B comparison while tuning)
+// VFMREG_MATCH_V1=1 in the environment keeps the single-CTA streaming kernel, VFMREG_MATCH_V2=1 the multicast CTA-pair
+// kernel (A/B comparison while tuning)
 static bool g_force_v1 = [] { const char* e = getenv("VFMREG_MATCH_V1"); return e && e[0] == '1'; }();
+static bool g_force_v2 = [] { const char* e = getenv("VFMREG_MATCH_V2"); return e && e[0] == '1'; }();
 
 // `dynamic`: n is only an upper bound, the kernels read the row count from device memory.  The grid is sized for n; the
 // slot bound must then hold for every smaller total: spans of at least one unit cut a row block's col_tiles consecutive
@@ -824,7 +1122,9 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, int dp, bool dynami
   TcPlan p;
   p.row_blocks = ceil_div(n, TBM);
   p.col_tiles = ceil_div(m, TBN);
-  p.paired = !g_force_v1 && dp <= A_MAX_KB * TBK && p.row_blocks >= 2;
+  p.version = g_force_v1 ? 1 : ((g_force_v2 && dp <= A_MAX_KB * TBK) ? 2 : (g_force_v2 ? 1 : 3));
+  if (p.row_blocks < 2) p.version = 1;
+  p.paired = p.version != 1;
   if (p.paired) {
     const int row_pairs = ceil_div(n, 2 * TBM);
     p.total = (long long)row_pairs * p.col_tiles;          // units of (row-block pair, column tile)
@@ -909,11 +1209,19 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   if (!attr_set) {
     VFM_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
     VFM_CUDA(cudaFuncSetAttribute(match_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_TOTAL));
+    VFM_CUDA(cudaFuncSetAttribute(match_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_TOTAL));
+    VFM_CUDA(cudaFuncSetAttribute(match_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_TOTAL));
     attr_set = true;
   }
   const int grp = n_dev ? GROUP_MATCH_PRUNED : GROUP_MATCH;
   group_begin(ctx, grp);
-  if (plan.paired) {
+  if (plan.version == 3) {
+    if (dp <= A_MAX_KB * TBK)
+      match_tc3_kernel<true><<<plan.grid, TC_THREADS, S3_TOTAL, ctx->stream>>>(map_a, map_b, P);
+    else
+      match_tc3_kernel<false><<<plan.grid, TC_THREADS, S3_TOTAL, ctx->stream>>>(map_a, map_b, P);
+    VFM_TRY(launch_check(ctx, "match_tc3_kernel"));
+  } else if (plan.version == 2) {
     match_tc2_kernel<<<plan.grid, TC_THREADS, S2_TOTAL, ctx->stream>>>(map_a, map_b, P);
     VFM_TRY(launch_check(ctx, "match_tc2_kernel"));
   } else {
@@ -936,8 +1244,9 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpy(host, dbg_dev, sizeof(host), cudaMemcpyDeviceToHost);
     double acc[8] = {0};
+    const int mma_ctas = plan.version == 3 ? plan.grid / 2 : plan.grid;   // version 3: only leaders run the MMA loop
     for (int c = 0; c < plan.grid; ++c)
-      for (int k = 0; k < 8; ++k) acc[k] += (double)host[c * 8 + k] / plan.grid;
+      for (int k = 0; k < 8; ++k) acc[k] += (double)host[c * 8 + k] / (k < 4 ? mma_ctas : plan.grid);
     if (host[1200]) {
       const long long t0 = host[1200];
       for (int i = 0; i < 16; ++i) {
@@ -947,8 +1256,17 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
         fprintf(stderr, "\n");
       }
     }
-    fprintf(stderr, "[tc dbg] grid=%d tiles/cta=%.1f | mma warp: total %.0f cyc, wait tempty %.0f, wait full %.0f | epi warp: total %.0f, wait tfull %.0f\n",
-            plan.grid, acc[3], acc[0], acc[1], acc[2], acc[4], acc[5]);
+#ifdef VFM_SCAN_STATS
+    {
+      unsigned long long st[4], zero[4] = {0, 0, 0, 0};
+      cudaMemcpyFromSymbol(st, g_scan_stats, sizeof(st));
+      cudaMemcpyToSymbol(g_scan_stats, zero, sizeof(zero));
+      fprintf(stderr, "[tc dbg] scan stats: warp-chunks %llu, with a lane above threshold %llu (%.1f%%), lane-chunks with several hits %llu (%.2f%%), lane-chunks with a hit %llu\n",
+              st[0], st[1], 100.0 * st[1] / (st[0] ? st[0] : 1), st[2], 100.0 * st[2] / (st[0] ? st[0] : 1), st[3]);
+    }
+#endif
+    fprintf(stderr, "[tc dbg] v%d grid=%d tiles/cta=%.1f | mma warp: total %.0f cyc, wait tempty %.0f, wait full %.0f | epi warp: total %.0f, wait tfull %.0f | producer: total %.0f, wait empty %.0f\n",
+            plan.version, plan.grid, acc[3], acc[0], acc[1], acc[2], acc[4], acc[5], acc[7], acc[6]);
   }
   return VFMREG_OK;
 }
