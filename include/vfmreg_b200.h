@@ -230,6 +230,56 @@ VFMREG_API int vfmreg_vit_set_graphs(vfmreg_vit* vit, int32_t on);
 /* images: device uint8 (b, img_h, img_w, 3) RGB; tokens: device float32 (b, grid_h, grid_w, width) */
 VFMREG_API int vfmreg_vit_forward(vfmreg_vit* vit, const uint8_t* images, int32_t b, int32_t img_h, int32_t img_w, float* tokens);
 
+/* ---------------------------------------------------------------------------------------------
+ * SURVEY 8f row 2 -- voxel down-sampling and the voxel hash map (the step BEFORE the path).
+ *
+ * vfmreg_voxel_downsample replaces kiss_icp::VoxelDownsample (core/Preprocessing.cpp:50-137; pybind
+ * `_voxel_down_sample`, pybind/kiss_icp_pybind.cpp, python voxelization.voxel_down_sample): keeps the first point
+ * (lowest index) of every voxel, voxel = (p / voxel_size).cast<int>() computed in double.
+ *   points: device, n rows of `cols` elements of `elem_size` bytes (4 = float32, 8 = float64), xyz in columns 0..2
+ *   keep_idx[n] (device): indices of the kept rows in ascending order; *count (device) = how many.
+ *   The reference returns the rows in tsl::robin_map iteration order (unspecified); here they are in input order.
+ * vfmreg_gather_rows copies the listed rows (row_bytes % 4 == 0): out[k] = rows[idx[k]], k < *count.
+ * Error: VFMREG_ERR_ARG if a coordinate is not finite or |p / voxel_size| >= 2^20.
+ * ------------------------------------------------------------------------------------------- */
+VFMREG_API int vfmreg_voxel_downsample(vfmreg_ctx* ctx, const void* points, int64_t n, int32_t cols, int32_t elem_size,
+                                       double voxel_size, int32_t* keep_idx, int32_t* count);
+VFMREG_API int vfmreg_gather_rows(vfmreg_ctx* ctx, const void* rows, int32_t row_bytes, const int32_t* idx, const int32_t* count,
+                                  int64_t max_rows, void* out);
+
+/* VoxelHashMap (core/VoxelHashMap.hpp:40-75, VoxelHashMap.cpp:735-771 AddPoints, VoxelBlock::AddPoint): every voxel
+ * keeps the first max_points_per_voxel points in insertion order.  build() replaces the content with the points of one
+ * array (n x 3 float64, device); incremental add_points is done by the host wrapper, which rebuilds from
+ * [kept points, new points] -- the same result as the reference's cumulative insertion.
+ * points(): kept points grouped by voxel (ascending source index inside a voxel) + their index in the build array
+ * (the reference's Pointcloud() order is the hash map's iteration order, i.e. unspecified).
+ * nearest(): VoxelHashMap::GetCorrespondences' GetClosestNeighbor (VoxelHashMap.cpp:79-136): closest kept point among
+ * the 27 voxels around the query, first minimum in (i, j, k, insertion) order; nn_idx = -1 unless its distance is
+ * < max_dist; nn_d2 (may be NULL) = squared distance of the closest point (-1 if the 27 voxels are empty). */
+typedef struct vfmreg_voxel_map vfmreg_voxel_map;
+VFMREG_API int vfmreg_voxel_map_create(vfmreg_ctx* ctx, double voxel_size, int32_t max_points_per_voxel, vfmreg_voxel_map** map);
+VFMREG_API void vfmreg_voxel_map_destroy(vfmreg_voxel_map* map);
+VFMREG_API int vfmreg_voxel_map_build(vfmreg_ctx* ctx, vfmreg_voxel_map* map, const double* xyz, int64_t n);
+VFMREG_API int64_t vfmreg_voxel_map_size(const vfmreg_voxel_map* map);
+VFMREG_API int vfmreg_voxel_map_points(vfmreg_ctx* ctx, const vfmreg_voxel_map* map, double* xyz_out, int32_t* src_idx_out);
+VFMREG_API int vfmreg_voxel_map_nearest(vfmreg_ctx* ctx, const vfmreg_voxel_map* map, const double* query, int64_t n,
+                                        double max_dist, int32_t* nn_idx, double* nn_d2);
+
+/* ---------------------------------------------------------------------------------------------
+ * SURVEY 8f row 1 -- ICP refinement (the step AFTER the path).
+ * Replaces kiss_icp::RegisterFrame (core/Registration.cpp:145-195; pybind `_register_frame`, python
+ * registration.register_frame, called at registration_node.py:337-341): point-to-point Gauss-Newton with the
+ * Geman-McClure weight kernel^2 / (kernel + r^2)^2 over the 27-voxel nearest neighbours, SE(3) exponential update,
+ * stops when |dx| < 1e-4, when no correspondence is left, or after max_iterations (reference: 1000).
+ *   frame: device (n x 3) float64; T0 / T_out: HOST row-major 4x4; returns T_icp * T0.
+ *   iterations / correspondences (HOST, may be NULL): solves executed, correspondences of the last one.
+ * An empty map returns T0 (Registration.cpp:150).  Sums are reduced in a fixed order (the reference's
+ * tbb::parallel_reduce order is not), float64 throughout.
+ * ------------------------------------------------------------------------------------------- */
+VFMREG_API int vfmreg_register_frame(vfmreg_ctx* ctx, const vfmreg_voxel_map* map, const double* frame, int64_t n, const double* T0,
+                                     double max_correspondence_distance, double kernel, int32_t max_iterations, double* T_out,
+                                     int32_t* iterations, int32_t* correspondences);
+
 #ifdef __cplusplus
 }
 #endif

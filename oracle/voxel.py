@@ -1,0 +1,138 @@
+"""ORACLE (test infrastructure only -- never imported by the product): CPU restatement of the voxel operations either
+side of the hot path, all citations relative to /root/reference/src/kiss-icp/cpp/kiss_icp/core.
+
+  voxel_down_sample      Preprocessing.cpp:50-137   first point per voxel, voxel = (p / voxel_size).cast<int>()
+  VoxelHashMapOracle     VoxelHashMap.cpp:735-771   AddPoints + VoxelBlock::AddPoint (VoxelHashMap.hpp:45-52): first
+                                                    max_points_per_voxel points per voxel, insertion order
+    .closest_neighbor    VoxelHashMap.cpp:79-136    27 voxels in (i, j, k) ascending order, strict '<'
+    .get_correspondences VoxelHashMap.cpp:137-166   keep iff (closest - point).norm() < max distance
+  register_frame         Registration.cpp:96-195    BuildLinearSystem + ldlt solve + SE3::exp, |dx| < 1e-4, <= 1000 iterations
+
+PARITY UNPINNED: the reference's C++ (Eigen, Sophus, TBB, tsl::robin_map -- none of them on this machine, its CMake
+downloads them) cannot be built offline and ships no golden vectors, so this restatement is checked against properties
+(brute-force nearest neighbours, known SE(3) recovery, scipy's matrix exponential) instead of reference outputs.
+Orders that the reference leaves to tsl::robin_map / tbb::parallel_reduce are fixed here: outputs by input index, sums in
+index order."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def voxel_index(xyz: np.ndarray, voxel_size: float) -> np.ndarray:
+    """(p / voxel_size).cast<int>(): float64 division, truncation toward zero (Preprocessing.cpp:58)."""
+    return np.trunc(np.asarray(xyz, dtype=np.float64)[:, :3] / float(voxel_size)).astype(np.int64)
+
+
+def voxel_down_sample(points: np.ndarray, voxel_size: float, return_index: bool = False):
+    """Rows of the first point of every voxel, in input order (the reference: same set, robin_map order)."""
+    points = np.asarray(points)
+    seen, keep = set(), []
+    for i, v in enumerate(map(tuple, voxel_index(points, voxel_size))):
+        if v not in seen:          # `if (grid.contains(voxel)) continue;`
+            seen.add(v)
+            keep.append(i)
+    keep = np.asarray(keep, dtype=np.int64)
+    return (points[keep], keep) if return_index else points[keep]
+
+
+class VoxelHashMapOracle:
+    def __init__(self, voxel_size: float, max_points_per_voxel: int = 20):
+        self.voxel_size, self.max_points = float(voxel_size), int(max_points_per_voxel)
+        self.map = {}      # voxel -> list of (xyz float64[3], insertion id)
+        self._next = 0
+
+    def add_points(self, xyz: np.ndarray) -> None:
+        xyz = np.asarray(xyz, dtype=np.float64)[:, :3]
+        for p, v in zip(xyz, map(tuple, voxel_index(xyz, self.voxel_size))):
+            block = self.map.setdefault(v, [])
+            if len(block) < self.max_points:   # VoxelBlock::AddPoint
+                block.append((p.copy(), self._next))
+            self._next += 1
+
+    def point_cloud(self):
+        """(xyz, insertion id) of the kept points sorted by insertion id."""
+        items = sorted((pid, p) for block in self.map.values() for p, pid in block)
+        if not items:
+            return np.zeros((0, 3)), np.zeros(0, dtype=np.int64)
+        return np.stack([p for _, p in items]), np.asarray([i for i, _ in items], dtype=np.int64)
+
+    def closest_neighbor(self, point: np.ndarray):
+        kx, ky, kz = (int(c) for c in np.trunc(point / self.voxel_size))   # static_cast<int>
+        best, best_d2 = None, np.finfo(np.float64).max
+        for i in range(kx - 1, kx + 2):
+            for j in range(ky - 1, ky + 2):
+                for k in range(kz - 1, kz + 2):
+                    for p, _ in self.map.get((i, j, k), ()):
+                        d = p - point
+                        d2 = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]
+                        if d2 < best_d2:
+                            best, best_d2 = p, d2
+        return best, best_d2
+
+    def get_correspondences(self, points: np.ndarray, max_dist: float):
+        src, tgt = [], []
+        for p in np.asarray(points, dtype=np.float64):
+            q, d2 = self.closest_neighbor(p)
+            if q is not None and np.sqrt(d2) < max_dist:
+                src.append(p)
+                tgt.append(q)
+        if not src:
+            return np.zeros((0, 3)), np.zeros((0, 3))
+        return np.stack(src), np.stack(tgt)
+
+
+def hat(w):
+    return np.array([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]])
+
+
+def se3_exp(dx: np.ndarray) -> np.ndarray:
+    """Sophus::SE3d::exp: dx = (upsilon, omega); R = exp(hat(omega)), t = V upsilon."""
+    u, w = dx[:3], dx[3:]
+    th2 = float(w @ w)
+    th = np.sqrt(th2)
+    if th < 1e-5:
+        A, B, Cc = 1.0 - th2 / 6.0, 0.5 - th2 / 24.0, 1.0 / 6.0 - th2 / 120.0
+    else:
+        A, B, Cc = np.sin(th) / th, (1.0 - np.cos(th)) / th2, (th - np.sin(th)) / (th2 * th)
+    W = hat(w)
+    T = np.eye(4)
+    T[:3, :3] = np.eye(3) + A * W + B * (W @ W)
+    T[:3, 3] = (np.eye(3) + B * W + Cc * (W @ W)) @ u
+    return T
+
+
+def build_linear_system(src: np.ndarray, tgt: np.ndarray, kernel: float):
+    """BuildLinearSystem (Registration.cpp:96-140): J = [I | -hat(s)], r = s - t, w = kernel^2 / (kernel + |r|^2)^2."""
+    JTJ, JTr = np.zeros((6, 6)), np.zeros(6)
+    for s, t in zip(src, tgt):
+        r = s - t
+        J = np.hstack([np.eye(3), -hat(s)])
+        w = kernel * kernel / (kernel + float(r @ r)) ** 2
+        JTJ += J.T @ (w * J)
+        JTr += J.T @ (w * r)
+    return JTJ, JTr
+
+
+def register_frame(frame: np.ndarray, vmap: VoxelHashMapOracle, initial_guess: np.ndarray, max_dist: float, kernel: float,
+                   max_iterations: int = 1000, return_info: bool = False):
+    T0 = np.asarray(initial_guess, dtype=np.float64)
+    if not vmap.map:
+        return (T0.copy(), {"iterations": 0, "correspondences": 0}) if return_info else T0.copy()
+    source = np.asarray(frame, dtype=np.float64) @ T0[:3, :3].T + T0[:3, 3]
+    T_icp = np.eye(4)
+    iters, ncorr = 0, 0
+    for _ in range(max_iterations):
+        src, tgt = vmap.get_correspondences(source, max_dist)
+        ncorr = len(src)
+        if ncorr == 0:
+            break
+        JTJ, JTr = build_linear_system(src, tgt, kernel)
+        dx = np.linalg.solve(JTJ, -JTr)
+        est = se3_exp(dx)
+        source = source @ est[:3, :3].T + est[:3, 3]
+        T_icp = est @ T_icp
+        iters += 1
+        if np.linalg.norm(dx) < 1e-4:
+            break
+    T = T_icp @ T0
+    return (T, {"iterations": iters, "correspondences": ncorr}) if return_info else T

@@ -1,0 +1,153 @@
+"""GPU parity of the voxel operations and the ICP refinement against oracle/voxel.py, called
+through the C ABI.  Index sets and nearest neighbours are bit-exact; the ICP pose is float64 Gauss-Newton with a different
+(fixed) summation order than the oracle's, tolerance 1e-9 on the 4x4 written in the test."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import voxel as ov  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def vfm():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import vfm_registration_b200 as v
+    v.get_context(0)
+    return v
+
+
+def _cloud(seed, n, span=30.0, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(-span, span, (n, 3)) * np.array([1.0, 1.0, 0.15])).astype(dtype)
+
+
+@pytest.mark.parametrize("n,cols,dtype,vs", [(20000, 3, np.float64, 1.0), (50000, 3, np.float32, 0.5), (3000, 387, np.float32, 1.0),
+                                             (1, 3, np.float64, 1.0), (5000, 4, np.float64, 5.0), (1500, 35, np.float64, 0.25)])
+def test_voxel_down_sample_vs_oracle(vfm, n, cols, dtype, vs):
+    rng = np.random.default_rng(n + cols)
+    pts = np.concatenate([_cloud(n, n, dtype=dtype), rng.standard_normal((n, cols - 3)).astype(dtype)], axis=1)
+    if n > 10:
+        pts[7, :3] = pts[2, :3]                     # duplicate point: the lower index wins
+        pts[11, :3] = [-0.3 * vs, 0.2 * vs, 0.0]    # both sides of zero share voxel 0 (truncation toward zero)
+        pts[12, :3] = [0.3 * vs, -0.2 * vs, 0.0]
+    got, gi = vfm.voxel_down_sample(pts, vs, return_index=True)
+    want, wi = ov.voxel_down_sample(pts, vs, return_index=True)
+    assert np.array_equal(gi, wi) and got.dtype == pts.dtype and np.array_equal(got, want)
+    if n > 10:
+        assert 12 not in gi and 7 not in gi
+    dev = vfm.voxel_down_sample(torch.from_numpy(pts).cuda(), vs)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
+
+
+def test_voxel_down_sample_errors(vfm):
+    with pytest.raises(ValueError, match="Invalid shape"):
+        vfm.voxel_down_sample(np.zeros((10, 2)), 1.0)
+    bad = np.zeros((4, 3))
+    bad[2, 0] = np.inf
+    with pytest.raises(vfm.VfmRegError):
+        vfm.voxel_down_sample(bad, 1.0)
+    with pytest.raises(vfm.VfmRegError):
+        vfm.voxel_down_sample(np.full((4, 3), 3e7), 1.0)   # |index| >= 2^20
+    assert vfm.voxel_down_sample(np.zeros((0, 3)), 1.0).shape == (0, 3)
+
+
+@pytest.mark.parametrize("n,vs,cap", [(30000, 1.0, 20), (8000, 2.0, 3), (500, 0.1, 20), (4000, 1.0, 1)])
+def test_voxel_map_build_and_nearest_vs_oracle(vfm, n, vs, cap):
+    pts = _cloud(10 + cap, n, span=12.0)
+    m = vfm.VoxelMap(vs, cap)
+    m.build(pts)
+    o = ov.VoxelHashMapOracle(vs, cap)
+    o.add_points(pts)
+    oxyz, oid = o.point_cloud()
+    xyz, idx = m.points()
+    assert len(m) == len(oid) and np.array_equal(idx.cpu().numpy(), oid) and np.array_equal(xyz.cpu().numpy(), oxyz)
+    rng = np.random.default_rng(1)
+    q = pts[rng.integers(0, n, 400)] + rng.normal(0, 0.3 * vs, (400, 3))
+    q[0] = [1e3, 1e3, 1e3]          # nothing around it
+    q[1] = pts[5]                   # exact hit
+    tgt, valid, d2 = m.nearest(q, 0.8 * vs)
+    tgt, valid, d2 = tgt.cpu().numpy(), valid.cpu().numpy(), d2.cpu().numpy()
+    for k in range(len(q)):
+        p, od2 = o.closest_neighbor(q[k])
+        if p is None:
+            assert not valid[k] and d2[k] == -1.0
+            continue
+        assert d2[k] == od2 and valid[k] == (np.sqrt(od2) < 0.8 * vs)
+        if valid[k]:
+            assert np.array_equal(tgt[k], p)
+    m.close()
+
+
+@pytest.mark.parametrize("seed,n_scan,noise", [(1, 3000, 0.0), (2, 6000, 0.02), (3, 800, 0.05)])
+def test_register_frame_vs_oracle(vfm, seed, n_scan, noise):
+    rng = np.random.default_rng(seed)
+    map_pts = _cloud(seed, 12000, span=25.0)
+    ang = np.deg2rad(rng.uniform(-4, 4))
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    T[:3, 3] = rng.normal(0, 0.3, 3) * [1, 1, 0.2]
+    scan = (map_pts[rng.choice(len(map_pts), n_scan, replace=False)] - T[:3, 3]) @ T[:3, :3] + rng.normal(0, noise, (n_scan, 3))
+    guess = np.eye(4)
+    guess[:3, 3] = [0.05, -0.05, 0.0]
+    m = vfm.VoxelMap(1.0, 20)
+    m.build(map_pts)
+    o = ov.VoxelHashMapOracle(1.0, 20)
+    o.add_points(map_pts)
+    got, gi = vfm.register_frame(scan, m, guess, 3.0, 2.0 / 3.0, return_info=True)
+    want, wi = ov.register_frame(scan, o, guess, 3.0, 2.0 / 3.0, return_info=True)
+    assert gi["iterations"] == wi["iterations"] and gi["correspondences"] == wi["correspondences"]
+    assert np.abs(got - want).max() < 1e-9          # float64, different summation order
+    assert np.abs(got - T).max() < (1e-6 if noise == 0 else 0.02)
+    one, info = vfm.register_frame(scan, m, guess, 3.0, 2.0 / 3.0, max_iterations=1, return_info=True)
+    assert info["iterations"] == 1 and np.abs(one - ov.register_frame(scan, o, guess, 3.0, 2.0 / 3.0, max_iterations=1)).max() < 1e-12
+    # empty map -> the initial guess; no correspondence -> loop exits with the pose so far
+    e = vfm.VoxelMap(1.0, 20)
+    assert np.array_equal(vfm.register_frame(scan, e, guess, 3.0, 0.5), guess)
+    far = scan + 1e4
+    assert np.array_equal(vfm.register_frame(far, m, np.eye(4), 3.0, 0.5), np.eye(4))
+    with pytest.raises(ValueError, match="Invalid shape"):
+        vfm.register_frame(np.zeros((5, 4)), m, guess, 3.0, 0.5)
+
+
+def test_compat_ransac_registration_with_icp_vs_oracle_chain(vfm):
+    """The reference's ransac_registration(method='vfm', run_icp=True) call surface (registration_node.py:273-357) through
+    the shim, against the same chain assembled from the oracles: voxel thinning / down-sampling, top-1 cosine gate, RANSAC,
+    Newton orthogonalisation, ICP."""
+    from oracle import cref, match
+    from vfm_registration_b200 import compat, metrics, synth
+    s = synth.make_pair(21, 6000, 3000, 64)
+    vmap_arr = np.c_[s["map_xyz"], s["map_feat"]].astype(np.float32)
+    scan_arr = np.c_[s["scan_xyz"], s["scan_feat"]].astype(np.float32)
+    vmap_arr = np.concatenate([vmap_arr, np.repeat(vmap_arr[:3], 30, axis=0)], axis=0)   # > 20 points in three voxels
+    node = compat.RegistrationNode(ransac_iters=4096, max_correspondence_distance=1.0, seed=5)
+    ransac_pose, icp_pose = node.ransac_registration(vmap_arr, scan_arr, "vfm", run_icp=True)
+    # oracle chain
+    om = ov.VoxelHashMapOracle(1.0, 20)
+    om.add_points(vmap_arr[:, :3])
+    kept_xyz, kept_id = om.point_cloud()
+    assert len(kept_id) == 6000 + 3 * 19
+    voxel_scan = ov.voxel_down_sample(ov.voxel_down_sample(scan_arr, 0.5), 1.0)
+    q = ov.voxel_down_sample(voxel_scan, 5.0)
+    mm = cref.match_nn(q[:, 3:], vmap_arr[kept_id, 3:])
+    corr = match.filter_correspondences(mm["idx01"], mm["sim01"], min_cos=0.8)
+    assert len(corr) >= 75
+    c = cref.ransac(np.ascontiguousarray(q[:, :3]), kept_xyz.astype(np.float32), corr, None, 1.0, seed=5, n_hyp=4096)
+    want_ransac = c["T"].copy()
+    want_ransac[:3, :3] = metrics.orthogonalize_rotation(want_ransac[:3, :3])
+    assert np.array_equal(ransac_pose, want_ransac)
+    want_icp = ov.register_frame(voxel_scan[:, :3].astype(np.float64), om, want_ransac, 6.0, 2.0 / 3.0)
+    assert np.abs(icp_pose - want_icp).max() < 1e-9
+    e_r, e_i = synth.pose_errors(ransac_pose, s["T_gt"]), synth.pose_errors(icp_pose, s["T_gt"])
+    assert e_r[0] < 0.05 and e_i[0] < 0.05 and e_i[1] < 0.1   # both within the 2 cm point noise of the planted pose
+    # the shim's map object: cumulative add_points == one add_points, (N, 3) and (N, 3 + D) stores are separate
+    a, b = compat.VoxelHashMap(1.0, 100.0, 20), compat.VoxelHashMap(1.0, 100.0, 20)
+    a.add_points(vmap_arr[:, :3])
+    b.add_points(vmap_arr[:2000, :3])
+    b.add_points(vmap_arr[2000:, :3])
+    assert np.array_equal(a.point_cloud(), b.point_cloud()) and np.array_equal(a.point_cloud(), kept_xyz) and a.empty_n()
+    src, tgt = a.get_correspondences(s["scan_xyz"], 0.5)
+    osrc, otgt = om.get_correspondences(s["scan_xyz"].astype(np.float64), 0.5)
+    assert np.array_equal(src, osrc) and np.array_equal(tgt, otgt) and len(src) > 500

@@ -76,6 +76,16 @@ _SIGS = {
     "vfmreg_vit_grid": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vfmreg_vit_set_graphs": (C.c_int, [_P, C.c_int32]),
     "vfmreg_vit_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "vfmreg_voxel_downsample": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_double, _P, _P]),
+    "vfmreg_gather_rows": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int64, _P]),
+    "vfmreg_voxel_map_create": (C.c_int, [_P, C.c_double, C.c_int32, C.POINTER(_P)]),
+    "vfmreg_voxel_map_destroy": (None, [_P]),
+    "vfmreg_voxel_map_build": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "vfmreg_voxel_map_size": (C.c_int64, [_P]),
+    "vfmreg_voxel_map_points": (C.c_int, [_P, _P, _P, _P]),
+    "vfmreg_voxel_map_nearest": (C.c_int, [_P, _P, _P, C.c_int64, C.c_double, _P, _P]),
+    "vfmreg_register_frame": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

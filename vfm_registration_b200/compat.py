@@ -1,15 +1,19 @@
-"""Compatibility shim: the reference's own entry points for the hot path, same names / array layouts / error behaviour,
-running on libvfmreg_b200.so.  A user of src/vfm-reg can import these instead of the kiss_icp / Open3D ones.
+"""Compatibility shim: the reference's own entry points for the hot path and for the steps either side of it, same names /
+array layouts / error behaviour, running on libvfmreg_b200.so.  A user of src/vfm-reg can import these instead of the
+kiss_icp / Open3D ones.
 
-  VoxelHashMap.get_vfm_correspondences   kiss_icp/mapping.py:120-131 -> pybind :128 -> VoxelHashMap.cpp:461-626
-  RegistrationNode.ransac_registration   src/vfm-reg/src/registration_node.py:273-357 (method='vfm')
+  voxel_down_sample                      kiss_icp/voxelization.py:27-40 -> Preprocessing.cpp:50-137
+  VoxelHashMap.add_points / point_cloud / get_correspondences / get_vfm_correspondences
+                                         kiss_icp/mapping.py:38-131 -> VoxelHashMap.cpp:76-168, 461-626, 735-771
+  register_frame                         kiss_icp/registration.py:27-71 -> Registration.cpp:145-195 (point-to-point, (N, 3) frames)
+  RegistrationNode.ransac_registration   src/vfm-reg/src/registration_node.py:273-357 (method='vfm', run_icp)
   RegistrationNode.compute_vfm_correspondences / compute_errors / compute_success_rate   :396-425, :997-1025
 
 Points and descriptors travel as ONE (N, 3 + D) array, as in the reference (registration_node.py:579).
 
-Not reproduced here ("next" rows): the voxel down-sampling steps around the matcher
-(registration_node.py:399-403,414 -- callers pass clouds at the density they want matched), first-come voxel thinning in
-``add_points`` (VoxelHashMap.cpp:746-757) and the ICP refinement (``run_icp=True`` raises NotImplementedError)."""
+Where the reference's result depends on tsl::robin_map iteration order (the ORDER of down-sampled rows and of
+``point_cloud()``), rows come back in input order here; the sets of points are the same.  The descriptor-carrying ICP
+variant (Registration.cpp:197-382) and the baseline descriptors are not part of this build."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -18,31 +22,87 @@ import numpy as np
 import torch
 
 from . import api, metrics
+from . import voxel as _voxel
+
+voxel_down_sample = _voxel.voxel_down_sample
+
+
+def register_frame(points, voxel_map: "VoxelHashMap", initial_guess, max_correspondance_distance: float, kernel: float):
+    """kiss_icp.registration.register_frame for (N, 3) frames."""
+    points = np.asarray(points)
+    if points.ndim != 2 or points.shape[1] != 3:
+        raise ValueError("Invalid shape")
+    core = voxel_map._map3 if len(voxel_map._map3) else voxel_map._mapn   # GetCorrespondences: map_ first, else map_n_
+    return _voxel.register_frame(points, core, np.asarray(initial_guess, dtype=np.float64), max_correspondance_distance, kernel)
 
 
 class VoxelHashMap:
-    """Holds the map cloud with its descriptors on the device, like the reference object holds it in C++."""
+    """The reference object's two point stores: ``map_`` for (N, 3) clouds and ``map_n_`` for descriptor-carrying clouds,
+    each keeping the first ``max_points_per_voxel`` points per voxel; both live on the device."""
 
     def __init__(self, voxel_size: float = 1.0, max_distance: float = 100.0, max_points_per_voxel: int = 20, device=None):
         self.voxel_size, self.max_distance, self.max_points_per_voxel = voxel_size, max_distance, max_points_per_voxel
         self._ctx = api.get_context(device)
-        self._xyz = np.zeros((0, 3), dtype=np.float64)
-        self._feat: Optional[torch.Tensor] = None
+        self._map3 = _voxel.VoxelMap(voxel_size, max_points_per_voxel, device=self._ctx.device)
+        self._mapn = _voxel.VoxelMap(voxel_size, max_points_per_voxel, device=self._ctx.device)
+        self._xyz3 = np.zeros((0, 3), dtype=np.float64)   # kept points of map_, insertion order
+        self._xyzn = np.zeros((0, 3), dtype=np.float64)   # kept points of map_n_
+        self._feat: Optional[torch.Tensor] = None          # their descriptors (device, float32)
+
+    def clear(self) -> None:
+        self.__init__(self.voxel_size, self.max_distance, self.max_points_per_voxel, self._ctx.device)
 
     def add_points(self, points: np.ndarray) -> None:
         points = np.asarray(points)
         if points.ndim != 2 or points.shape[1] < 3:
             raise ValueError("Invalid shape")  # mapping.py:84-85
-        self._xyz = np.concatenate([self._xyz, points[:, :3].astype(np.float64)], axis=0)
-        if points.shape[1] > 3:
-            f = torch.from_numpy(np.ascontiguousarray(points[:, 3:], dtype=np.float32)).to(f"cuda:{self._ctx.device}")
-            self._feat = f if self._feat is None else torch.cat([self._feat, f], dim=0)
+        if points.shape[0] == 0:
+            return
+        new_xyz = points[:, :3].astype(np.float64)
+        if points.shape[1] == 3:
+            # cumulative insertion == thinning of [kept so far, new points]: a kept point stays kept, order is preserved
+            allx = np.concatenate([self._xyz3, new_xyz], axis=0)
+            self._map3.build(allx)
+            xyz, idx = self._map3.points()
+            self._xyz3 = xyz.cpu().numpy()
+            return
+        k_old = self._xyzn.shape[0]
+        allx = np.concatenate([self._xyzn, new_xyz], axis=0)
+        self._mapn.build(allx)
+        xyz, idx = self._mapn.points()
+        self._xyzn = xyz.cpu().numpy()
+        f_new = torch.from_numpy(np.ascontiguousarray(points[:, 3:], dtype=np.float32)).to(f"cuda:{self._ctx.device}")
+        if self._feat is not None and self._feat.shape[1] != f_new.shape[1]:
+            raise ValueError("Invalid shape")
+        f_all = f_new if self._feat is None else torch.cat([self._feat, f_new], dim=0)
+        assert f_all.shape[0] == k_old + points.shape[0]
+        self._feat = f_all[idx.long()]
 
     def empty(self) -> bool:
-        return self._xyz.shape[0] == 0
+        return self._xyz3.shape[0] == 0
+
+    def empty_n(self) -> bool:
+        return self._xyzn.shape[0] == 0
 
     def point_cloud(self) -> np.ndarray:
-        return self._xyz.copy()
+        return self._xyz3.copy()
+
+    def point_cloud_n(self) -> np.ndarray:
+        if self._feat is None:
+            return np.zeros((0, 3))
+        return np.c_[self._xyzn, self._feat.cpu().numpy().astype(np.float64)]
+
+    def get_correspondences(self, points: np.ndarray, max_correspondance_distance: float) -> Tuple[np.ndarray, np.ndarray]:
+        """(source, target) of the points whose closest map point (27-voxel search) is nearer than the distance."""
+        points = np.asarray(points)
+        if points.ndim != 2 or points.shape[1] < 3:
+            raise ValueError("Invalid shape")
+        core = self._map3 if len(self._map3) else self._mapn
+        if points.shape[0] == 0 or len(core) == 0:
+            return np.zeros((0, 3)), np.zeros((0, 3))
+        tgt, valid, _ = core.nearest(points[:, :3], max_correspondance_distance)
+        valid = valid.cpu().numpy()
+        return points[valid, :3].astype(np.float64), tgt.cpu().numpy()[valid]
 
     def get_vfm_correspondences(self, points: np.ndarray, max_correspondance_distance: float) -> Tuple[np.ndarray, np.ndarray]:
         """(src_xyz[K,3] f64, tgt_xyz[K,3] f64) of the queries whose top-1 cosine is >= the threshold, in query order.
@@ -50,41 +110,86 @@ class VoxelHashMap:
         points = np.asarray(points)
         if points.ndim != 2 or self._feat is None or points.shape[1] != 3 + self._feat.shape[1]:
             raise ValueError("Invalid shape")
-        if points.shape[0] == 0 or self.empty():
+        if points.shape[0] == 0 or self.empty_n():
             return np.zeros((0, 3)), np.zeros((0, 3))  # the reference has UB here (VoxelHashMap.cpp:464)
         m = api.match_nn(points[:, 3:], self._feat, normalize=True, device=self._ctx.device)
         corr = api.filter_correspondences(m, min_cos=float(max_correspondance_distance), device=self._ctx.device).cpu().numpy()
-        return points[corr[:, 0], :3].astype(np.float64), self._xyz[corr[:, 1]]
+        return points[corr[:, 0], :3].astype(np.float64), self._xyzn[corr[:, 1]]
 
 
 class RegistrationNode:
     """The two hot methods of the reference's experiment driver plus its error bookkeeping."""
 
     def __init__(self, ransac_iters: int = 50000, max_correspondence_distance: float = 10000.0, min_cosine: float = 0.8,
-                 seed: int = 42, device=None):
+                 seed: int = 42, device=None, *, voxel_size: float = 1.0, max_points_per_voxel: int = 20, max_range: float = 100.0,
+                 initial_threshold: float = 2.0, preprocess: bool = True):
+        """``voxel_size`` / ``max_points_per_voxel`` / ``max_range`` / ``initial_threshold`` are the KISS-ICP config values the
+        reference reads (config.mapping.voxel_size = max_range / 100, 20, 100 m, config.adaptive_threshold.initial_threshold
+        = 2).  ``preprocess=False`` skips the voxel steps: the clouds are matched at the density they are given."""
         self.ransac_iters, self.max_dist, self.min_cosine, self.seed, self.device = (ransac_iters, max_correspondence_distance,
                                                                                    min_cosine, seed, device)
+        self.voxel_size, self.max_points_per_voxel, self.max_range = voxel_size, max_points_per_voxel, max_range
+        self.initial_threshold, self.preprocess = initial_threshold, preprocess
         self.rot_errors, self.trans_errors = {}, {}
 
+    def _voxel_scan(self, raw_scan: np.ndarray) -> np.ndarray:
+        # "double-downsampling from KISS-ICP" (registration_node.py:287-288, 399-400)
+        return voxel_down_sample(voxel_down_sample(raw_scan, self.voxel_size * 0.5), self.voxel_size * 1.0)
+
+    def _new_map(self) -> VoxelHashMap:
+        return VoxelHashMap(self.voxel_size, self.max_range, self.max_points_per_voxel, device=self.device)
+
     def compute_vfm_correspondences(self, voxel_map: np.ndarray, raw_scan: np.ndarray, initial_pose=np.eye(4)):
-        vmap = VoxelHashMap(device=self.device)
+        """registration_node.py:396-425: thin the map (<= 20 points per voxel), down-sample the scan (0.5 v, 1 v, then 5 m;
+        1 m if that leaves fewer than 75 matches), top-1 cosine >= 0.8."""
+        vmap = self._new_map()
         vmap.add_points(voxel_map)
-        return vmap.get_vfm_correspondences(metrics.transform_pcl(raw_scan, initial_pose), self.min_cosine)
+        if not self.preprocess:
+            return vmap.get_vfm_correspondences(metrics.transform_pcl(raw_scan, initial_pose), self.min_cosine)
+        pcl = metrics.transform_pcl(self._voxel_scan(raw_scan), initial_pose)
+        corr = vmap.get_vfm_correspondences(voxel_down_sample(pcl, 5.0), self.min_cosine)
+        if corr[0].shape[0] < 75:
+            corr = vmap.get_vfm_correspondences(voxel_down_sample(pcl, 1.0), self.min_cosine)
+        return corr
 
     def ransac_registration(self, voxel_map: np.ndarray, raw_scan: np.ndarray, method: str, run_icp: bool = False):
+        """registration_node.py:273-357 for method='vfm': correspondences -> RANSAC (-> ICP refinement).  The reference
+        recovers correspondence indices in the voxelised clouds with KD-trees (:289-309); here the voxel operations
+        return indices, so the correspondences are first-class and that step disappears."""
         if method != "vfm":
             if method in ("fpfh", "dip", "gedi", "fcgf", "gcl", "spinnet"):
                 raise NotImplementedError(f"baseline descriptor '{method}' is outside the VFM hot path")
             raise ValueError(f"Invalid method: {method}")  # registration_node.py:284-285
-        if run_icp:
-            raise NotImplementedError("ICP refinement (register_frame) is a 'next' row, SURVEY.md section 8f")
         voxel_map, raw_scan = np.asarray(voxel_map), np.asarray(raw_scan)
         if voxel_map.ndim != 2 or raw_scan.ndim != 2 or voxel_map.shape[1] != raw_scan.shape[1] or raw_scan.shape[1] <= 3:
             raise ValueError("Invalid shape")
-        r = api.register(raw_scan[:, :3], voxel_map[:, :3], raw_scan[:, 3:], voxel_map[:, 3:], normalize=True,
-                         min_cos=self.min_cosine, ransac_iters=self.ransac_iters, inlier_thresh=self.max_dist, seed=self.seed,
-                         device=self.device)
-        return r.T, None
+        kw = dict(normalize=True, min_cos=self.min_cosine, ransac_iters=self.ransac_iters, inlier_thresh=self.max_dist,
+                  seed=self.seed, device=self.device)
+        if not self.preprocess:
+            r = api.register(raw_scan[:, :3], voxel_map[:, :3], raw_scan[:, 3:], voxel_map[:, 3:], **kw)
+            scan_xyz, vmap = raw_scan[:, :3], None
+        else:
+            vmap = self._new_map()
+            vmap.add_points(voxel_map)                     # descriptor map, thinned
+            feat_map = vmap._feat
+            voxel_scan = self._voxel_scan(raw_scan)        # (n, 3 + D); its xyz is the reference's `voxel_scan`
+            scan_xyz = voxel_scan[:, :3]
+            r = None
+            for leaf in (5.0, 1.0):                        # "Voxelized too sparse, retrying with a larger voxel size"
+                q = voxel_down_sample(voxel_scan, leaf)
+                r = api.register(q[:, :3], vmap._xyzn.astype(np.float32), q[:, 3:], feat_map, **kw)
+                if len(r.corr) >= 75:
+                    break
+        ransac_pose = r.T
+        if not run_icp:
+            return ransac_pose, None
+        ransac_pose = ransac_pose.copy()
+        ransac_pose[:3, :3] = metrics.orthogonalize_rotation(ransac_pose[:3, :3])   # registration_node.py:331-336
+        icp_map = self._new_map()
+        icp_map.add_points(np.ascontiguousarray(voxel_map[:, :3]))                   # :290-291
+        sigma = self.initial_threshold
+        pose = register_frame(scan_xyz, icp_map, ransac_pose, 3 * sigma, sigma / 3)  # :337-341
+        return ransac_pose, pose
 
     def compute_errors(self, pose, gt_pose, method: str):
         t, r = metrics.compute_errors(np.asarray(pose), np.asarray(gt_pose))
