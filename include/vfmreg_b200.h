@@ -280,6 +280,18 @@ VFMREG_API int vfmreg_register_frame(vfmreg_ctx* ctx, const vfmreg_voxel_map* ma
                                      double max_correspondence_distance, double kernel, int32_t max_iterations, double* T_out,
                                      int32_t* iterations, int32_t* correspondences);
 
+/* The descriptor-carrying overload of RegisterFrame ("VFM-ICP", core/Registration.cpp:197-382; reached through
+ * register_frame with (N, 3 + D) frames, kiss_icp/registration.py:41-62).  vfm_src / vfm_tgt (device, k x 3 float64) are the
+ * descriptor correspondences the reference computes first (VoxelDownsample(source, 5.0) -> GetVFMCorrespondences(.., 0.8);
+ * source points BEFORE the initial guess is applied, map points).  Loop 1: Gauss-Newton on that fixed list, pruned after
+ * every update to |d - median| < 1.5 * 1.4826 * MAD, until the mean distance moves by < 0.01 m.  Loop 2: the vanilla ICP of
+ * vfmreg_register_frame with the remaining iteration budget.  vfm_iterations / iterations / vfm_kept (HOST, may be NULL):
+ * iterations of loop 1, of loop 2, correspondences left after the pruning. */
+VFMREG_API int vfmreg_register_frame_vfm(vfmreg_ctx* ctx, const vfmreg_voxel_map* map, const double* frame, int64_t n,
+                                         const double* vfm_src, const double* vfm_tgt, int64_t k, const double* T0,
+                                         double max_correspondence_distance, double kernel, int32_t max_iterations, double* T_out,
+                                         int32_t* vfm_iterations, int32_t* iterations, int32_t* vfm_kept);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,3 +136,54 @@ def register_frame(frame: np.ndarray, vmap: VoxelHashMapOracle, initial_guess: n
             break
     T = T_icp @ T0
     return (T, {"iterations": iters, "correspondences": ncorr}) if return_info else T
+
+
+def _median_nth(values: np.ndarray) -> float:
+    """std::nth_element median with the even-size average of the two middle order statistics (Registration.cpp:283-293)."""
+    s = np.sort(np.asarray(values, dtype=np.float64))
+    n = len(s) // 2
+    return float(s[n]) if len(s) & 1 else float((s[n] + s[n - 1]) / 2)
+
+
+def vfm_icp_first_loop(src_raw: np.ndarray, tgt: np.ndarray, initial_guess: np.ndarray, kernel: float, max_iterations: int = 1000):
+    """Registration.cpp:236-329: Gauss-Newton on the fixed descriptor correspondences with MAD pruning.  Returns
+    (T_icp @ initial_guess, j, surviving (src, tgt))."""
+    T0 = np.asarray(initial_guess, dtype=np.float64)
+    src = np.asarray(src_raw, dtype=np.float64).reshape(-1, 3) @ T0[:3, :3].T + T0[:3, 3]
+    tgt = np.asarray(tgt, dtype=np.float64).reshape(-1, 3)
+    T_icp = np.eye(4)
+    prev = np.linalg.norm(src - tgt, axis=1).mean() if len(src) else np.nan
+    j = 0
+    while j < max_iterations:
+        if len(src) == 0:
+            break
+        JTJ, JTr = build_linear_system(src, tgt, kernel)
+        est = se3_exp(np.linalg.solve(JTJ, -JTr))
+        src = src @ est[:3, :3].T + est[:3, 3]
+        T_icp = est @ T_icp
+        d = np.linalg.norm(src - tgt, axis=1)
+        mean = d.mean()
+        median = _median_nth(d)
+        mad = _median_nth(np.abs(d - median)) * 1.4826
+        keep = np.abs(d - median) < 1.5 * mad
+        src, tgt = src[keep], tgt[keep]
+        if abs(prev - mean) < 0.01:   # EUCL_DIST_THRESHOLD_: break does not advance j
+            break
+        prev = mean
+        j += 1
+    return T_icp @ T0, j, (src, tgt)
+
+
+def register_frame_vfm(frame_xyz: np.ndarray, vmap: VoxelHashMapOracle, vfm_src_raw: np.ndarray, vfm_tgt: np.ndarray,
+                       initial_guess: np.ndarray, max_dist: float, kernel: float, max_iterations: int = 1000, return_info: bool = False):
+    """RegisterFrame(VectorNd...) (Registration.cpp:197-382) given the descriptor correspondences it starts from."""
+    T0 = np.asarray(initial_guess, dtype=np.float64)
+    if not vmap.map:
+        return (T0.copy(), {"vfm_iterations": 0, "iterations": 0, "vfm_kept": 0}) if return_info else T0.copy()
+    T1, j, (s, _) = vfm_icp_first_loop(vfm_src_raw, vfm_tgt, T0, kernel, max_iterations)
+    info = {"vfm_iterations": j, "vfm_kept": len(s), "iterations": 0}
+    T = T1
+    if max_iterations - j > 0 and len(frame_xyz):
+        T, i2 = register_frame(frame_xyz, vmap, T1, max_dist, kernel, max_iterations - j, return_info=True)
+        info["iterations"] = i2["iterations"]
+    return (T, info) if return_info else T

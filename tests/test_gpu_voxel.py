@@ -148,6 +148,72 @@ def test_compat_ransac_registration_with_icp_vs_oracle_chain(vfm):
     b.add_points(vmap_arr[:2000, :3])
     b.add_points(vmap_arr[2000:, :3])
     assert np.array_equal(a.point_cloud(), b.point_cloud()) and np.array_equal(a.point_cloud(), kept_xyz) and a.empty_n()
-    src, tgt = a.get_correspondences(s["scan_xyz"], 0.5)
-    osrc, otgt = om.get_correspondences(s["scan_xyz"].astype(np.float64), 0.5)
+    posed = s["scan_xyz"].astype(np.float64) @ s["T_gt"][:3, :3].T + s["T_gt"][:3, 3]
+    src, tgt = a.get_correspondences(posed, 0.5)
+    osrc, otgt = om.get_correspondences(posed, 0.5)
     assert np.array_equal(src, osrc) and np.array_equal(tgt, otgt) and len(src) > 500
+
+
+@pytest.mark.parametrize("k,outliers", [(400, 40), (37, 0), (1500, 300), (6, 0), (0, 0)])
+def test_register_frame_vfm_vs_oracle(vfm, k, outliers):
+    """VFM-ICP (Registration.cpp:197-382) given its descriptor correspondences: pruning loop + vanilla loop vs the oracle;
+    the surviving count and both iteration counts are equal, the pose agrees to 1e-9 (float64, fixed summation order).
+    (Fewer than 3 correspondences make J^T W J singular: the reference's ldlt, NumPy's solve and this LDL^T then return
+    different arbitrary updates, so that case is not a parity case.)"""
+    rng = np.random.default_rng(100 + k)
+    map_pts = _cloud(40 + k, 9000, span=20.0)
+    ang = np.deg2rad(4.0)
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    T[:3, 3] = [0.8, -0.4, 0.05]
+    sel = rng.choice(len(map_pts), 2500, replace=False)
+    frame = (map_pts[sel] - T[:3, 3]) @ T[:3, :3] + rng.normal(0, 0.01, (2500, 3))
+    vs, vt = frame[:k].copy(), map_pts[sel[:k]].copy()
+    vs[:outliers] += rng.normal(0, 4.0, (outliers, 3))
+    m = vfm.VoxelMap(1.0, 20)
+    m.build(map_pts)
+    o = ov.VoxelHashMapOracle(1.0, 20)
+    o.add_points(map_pts)
+    guess = np.eye(4)
+    guess[:3, 3] = [0.1, 0.1, 0.0]
+    got, gi = vfm.register_frame_vfm(frame, m, vs, vt, guess, 6.0, 2.0 / 3.0, return_info=True)
+    want, wi = ov.register_frame_vfm(frame, o, vs, vt, guess, 6.0, 2.0 / 3.0, return_info=True)
+    assert gi == wi, (gi, wi)
+    assert np.abs(got - want).max() < 1e-9
+    if k >= 37:
+        assert np.abs(got - T).max() < 0.02
+    T1, j, _ = ov.vfm_icp_first_loop(vs, vt, guess, 2.0 / 3.0, 3)
+    only1, i1 = vfm.register_frame_vfm(frame[:0], m, vs, vt, guess, 6.0, 2.0 / 3.0, max_iterations=3, return_info=True)
+    assert i1["vfm_iterations"] == j and np.abs(only1 - T1).max() < 1e-10
+
+
+def test_compat_register_frame_with_descriptors(vfm):
+    """register_frame on (N, 3 + D) frames = VFM-ICP through the shim (kiss_icp/registration.py:41-62)."""
+    from oracle import match
+    from vfm_registration_b200 import compat, synth
+    s = synth.make_pair(31, 8000, 4000, 32, inlier_frac=0.6)
+    vmap_arr = np.c_[s["map_xyz"], s["map_feat"]].astype(np.float32)
+    scan_arr = np.c_[s["scan_xyz"], s["scan_feat"]].astype(np.float32)
+    guess = s["T_gt"].copy()
+    guess[:3, 3] += [0.4, -0.3, 0.05]
+    vm = compat.VoxelHashMap(1.0, 100.0, 20)
+    vm.add_points(vmap_arr)
+    pose = compat.register_frame(scan_arr, vm, guess, 6.0, 2.0 / 3.0)
+    # oracle chain
+    src_t = scan_arr[:, :3].astype(np.float64) @ guess[:3, :3].T + guess[:3, 3]
+    posed = np.c_[src_t, scan_arr[:, 3:]].astype(np.float32)
+    vox, idx = ov.voxel_down_sample(posed, 5.0, return_index=True)
+    assert len(vox) >= 100
+    om = ov.VoxelHashMapOracle(1.0, 20)
+    om.add_points(vmap_arr[:, :3])
+    kept_xyz, kept_id = om.point_cloud()
+    osrc, otgt = match.get_vfm_correspondences(vox, vmap_arr[kept_id], 0.8)
+    assert len(osrc) > 50
+    mm = match.match_nn(vox[:, 3:], vmap_arr[kept_id, 3:])
+    corr = match.filter_correspondences(mm["idx01"], mm["sim01"], min_cos=0.8)
+    want = ov.register_frame_vfm(scan_arr[:, :3].astype(np.float64), om, scan_arr[idx[corr[:, 0]], :3].astype(np.float64),
+                                 kept_xyz[corr[:, 1]], guess, 6.0, 2.0 / 3.0)
+    assert np.abs(pose - want).max() < 1e-8
+    rte, rre = synth.pose_errors(pose, s["T_gt"])
+    assert rte < 0.05 and rre < 0.1
+    assert np.array_equal(compat.register_frame(scan_arr, compat.VoxelHashMap(1.0, 100.0, 20), guess, 6.0, 0.5), guess)

@@ -84,3 +84,19 @@ def test_register_frame_recovers_planted_pose(seed):
     est, info = ov.register_frame(scan, m, np.eye(4), 3.0, 2.0 / 3.0, return_info=True)
     assert info["iterations"] < 60 and np.abs(est - T).max() < 1e-6
     assert np.array_equal(ov.register_frame(scan, ov.VoxelHashMapOracle(1.0), T, 3.0, 0.5), T)   # empty map -> initial guess
+
+
+def test_vfm_icp_first_loop_prunes_outliers_and_converges():
+    rng = np.random.default_rng(9)
+    tgt = _cloud(9, 400)
+    ang = np.deg2rad(5.0)
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    T[:3, 3] = [1.0, -0.5, 0.1]
+    src = (tgt - T[:3, 3]) @ T[:3, :3]
+    src[:40] += rng.normal(0, 5.0, (40, 3))          # wrong descriptor matches
+    assert ov._median_nth([3.0, 1.0, 2.0]) == 2.0 and ov._median_nth([4.0, 1.0, 3.0, 2.0]) == 2.5
+    est, j, (s, t) = ov.vfm_icp_first_loop(src, tgt, np.eye(4), 2.0 / 3.0)
+    assert 1 <= j < 50 and len(s) <= 365 and np.abs(est - T).max() < 0.05
+    e0, j0, (s0, _) = ov.vfm_icp_first_loop(np.zeros((0, 3)), np.zeros((0, 3)), T, 0.5)
+    assert j0 == 0 and len(s0) == 0 and np.array_equal(e0, T)

@@ -132,12 +132,43 @@ def bench_extract(n=10000):
         print(f"extract_features {model}: 6 images + {n} points: {ms:.3f} ms device-resident, {ms_h:.3f} ms from/to host", flush=True)
 
 
+def bench_voxel():
+    """voxel down-sampling, voxel-map build, 27-voxel nearest neighbour, ICP (NCLT-like sizes)."""
+    rng = np.random.default_rng(0)
+    for n, cols in ((100_000, 3), (1_000_000, 3), (50_000, 387)):
+        pts = torch.from_numpy(np.c_[rng.uniform(-50, 50, (n, 2)), rng.uniform(-2, 8, n), rng.standard_normal((n, cols - 3))]
+                               .astype(np.float32)).cuda()
+        for vs in (0.5, 1.0):
+            ms = time_fn(lambda: v.voxel_down_sample(pts, vs), iters=5)
+            kept = v.voxel_down_sample(pts, vs).shape[0]
+            print(f"voxel_down_sample N={n} cols={cols} voxel={vs}: {ms:.3f} ms ({kept} kept, {n / ms / 1e3:.0f} M points/s, "
+                  f"{(12 * n + 2 * 4 * cols * kept) / ms / 1e6:.0f} GB/s algorithmic)", flush=True)
+    map_pts = np.c_[rng.uniform(-50, 50, (200_000, 2)), rng.uniform(-2, 8, 200_000)]
+    m = v.VoxelMap(1.0, 20)
+    ms = time_fn(lambda: m.build(map_pts), iters=5)
+    print(f"VoxelMap.build 200000 points: {ms:.3f} ms incl. the host->device copy ({len(m)} kept)", flush=True)
+    scan = map_pts[rng.choice(200_000, 20_000, replace=False)] + rng.normal(0, 0.02, (20_000, 3))
+    ang = np.deg2rad(2.0)
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    T[:3, 3] = [0.3, -0.2, 0.02]
+    scan_t = torch.from_numpy((scan - T[:3, 3]) @ T[:3, :3]).cuda()
+    ms = time_fn(lambda: m.nearest(scan_t, 3.0), iters=5)
+    print(f"VoxelMap.nearest 20000 queries (27 voxels, <= 20 points each): {ms:.3f} ms = {20_000 / ms / 1e3:.1f} M queries/s", flush=True)
+    _, info = v.register_frame(scan_t, m, np.eye(4), 6.0, 2.0 / 3.0, return_info=True)
+    ms = time_fn(lambda: v.register_frame(scan_t, m, np.eye(4), 6.0, 2.0 / 3.0), iters=5)
+    print(f"register_frame 20000 x 200000: {ms:.3f} ms for {info['iterations']} iterations "
+          f"({ms / max(info['iterations'], 1) * 1e3:.0f} us per iteration, 2 launches each, host check every 8)", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "match"
     if what == "match":
         bench_match()
     elif what == "ransac":
         bench_ransac()
+    elif what == "voxel":
+        bench_voxel()
     elif what == "project":
         bench_project()
     elif what == "vit":

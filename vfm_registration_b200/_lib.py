@@ -86,6 +86,8 @@ _SIGS = {
     "vfmreg_voxel_map_nearest": (C.c_int, [_P, _P, _P, C.c_int64, C.c_double, _P, _P]),
     "vfmreg_register_frame": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P,
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vfmreg_register_frame_vfm": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P,
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

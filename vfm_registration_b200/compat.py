@@ -5,15 +5,15 @@ kiss_icp / Open3D ones.
   voxel_down_sample                      kiss_icp/voxelization.py:27-40 -> Preprocessing.cpp:50-137
   VoxelHashMap.add_points / point_cloud / get_correspondences / get_vfm_correspondences
                                          kiss_icp/mapping.py:38-131 -> VoxelHashMap.cpp:76-168, 461-626, 735-771
-  register_frame                         kiss_icp/registration.py:27-71 -> Registration.cpp:145-195 (point-to-point, (N, 3) frames)
+  register_frame                         kiss_icp/registration.py:27-71 -> Registration.cpp:145-195 ((N, 3) frames) and :197-382 (VFM-ICP)
   RegistrationNode.ransac_registration   src/vfm-reg/src/registration_node.py:273-357 (method='vfm', run_icp)
   RegistrationNode.compute_vfm_correspondences / compute_errors / compute_success_rate   :396-425, :997-1025
 
 Points and descriptors travel as ONE (N, 3 + D) array, as in the reference (registration_node.py:579).
 
 Where the reference's result depends on tsl::robin_map iteration order (the ORDER of down-sampled rows and of
-``point_cloud()``), rows come back in input order here; the sets of points are the same.  The descriptor-carrying ICP
-variant (Registration.cpp:197-382) and the baseline descriptors are not part of this build."""
+``point_cloud()``), rows come back in input order here; the sets of points are the same.  The baseline descriptors
+(FPFH, DIP, GeDi, FCGF, GCL, SpinNet) are not part of this build."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -28,12 +28,29 @@ voxel_down_sample = _voxel.voxel_down_sample
 
 
 def register_frame(points, voxel_map: "VoxelHashMap", initial_guess, max_correspondance_distance: float, kernel: float):
-    """kiss_icp.registration.register_frame for (N, 3) frames."""
+    """kiss_icp.registration.register_frame: (N, 3) frames run the point-to-point ICP (Registration.cpp:145-195); frames
+    that carry descriptors, (N, 3 + D), run the VFM-ICP overload (Registration.cpp:197-382): descriptor correspondences of
+    the 5 m-voxelised, initially-posed frame at cosine >= 0.8, a correspondence-driven loop with MAD pruning, then the
+    vanilla loop."""
     points = np.asarray(points)
-    if points.ndim != 2 or points.shape[1] != 3:
+    if points.ndim != 2 or points.shape[1] < 3:
         raise ValueError("Invalid shape")
-    core = voxel_map._map3 if len(voxel_map._map3) else voxel_map._mapn   # GetCorrespondences: map_ first, else map_n_
-    return _voxel.register_frame(points, core, np.asarray(initial_guess, dtype=np.float64), max_correspondance_distance, kernel)
+    T0 = np.asarray(initial_guess, dtype=np.float64)
+    if points.shape[1] == 3:
+        core = voxel_map._map3 if len(voxel_map._map3) else voxel_map._mapn   # GetCorrespondences: map_ first, else map_n_
+        return _voxel.register_frame(points, core, T0, max_correspondance_distance, kernel)
+    if voxel_map.empty_n():
+        return T0.copy()                                                     # "if (voxel_map.EmptyN()) return initial_guess"
+    source = metrics.transform_pcl(points, T0)
+    vox, idx = voxel_down_sample(source, 5.0, return_index=True)
+    if vox.shape[0] < 100:                                                   # "Voxelized too sparse. Keep input."
+        vox, idx = source, np.arange(points.shape[0])
+    m = api.match_nn(vox[:, 3:], voxel_map._feat, normalize=True, device=voxel_map._ctx.device)
+    corr = api.filter_correspondences(m, min_cos=0.8, device=voxel_map._ctx.device).cpu().numpy()
+    vfm_src = points[idx[corr[:, 0]], :3].astype(np.float64)                 # before the initial guess (applied on the device)
+    vfm_tgt = voxel_map._xyzn[corr[:, 1]]
+    core = voxel_map._map3 if len(voxel_map._map3) else voxel_map._mapn
+    return _voxel.register_frame_vfm(points[:, :3], core, vfm_src, vfm_tgt, T0, max_correspondance_distance, kernel)
 
 
 class VoxelHashMap:

@@ -280,37 +280,56 @@ struct MapView {
   double vs;
 };
 
+// One warp per query: lane l < 27 searches voxel l of the (i, j, k)-ascending enumeration (l = 9 (i - kx + 1) + 3 (j - ky + 1)
+// + (k - kz + 1)), strict '<' inside a voxel keeps the first minimum; the warp-wide arg-min prefers the lower lane on equal
+// distances, i.e. the earlier voxel -- the same winner as the reference's sequential scan.  All lanes return the result.
 __device__ __forceinline__ int nearest_in_map(const MapView& M, double x, double y, double z, double& best_d2) {
+  const int lane = threadIdx.x & 31;
   // static_cast<int>(point[k] / voxel_size_): truncation toward zero
   const int kx = __double2int_rz(x / M.vs), ky = __double2int_rz(y / M.vs), kz = __double2int_rz(z / M.vs);
   int best = -1;
-  best_d2 = 1.7976931348623157e308;   // std::numeric_limits<double>::max()
-  for (int i = kx - 1; i <= kx + 1; ++i)
-    for (int j = ky - 1; j <= ky + 1; ++j)
-      for (int k = kz - 1; k <= kz + 1; ++k) {
-        if (abs(i) >= COORD_BIAS - 2 || abs(j) >= COORD_BIAS - 2 || abs(k) >= COORD_BIAS - 2) continue;
-        const int s = table_find(M.keys, M.mask, pack_key(i, j, k));
-        if (s < 0) continue;
+  double bd = 1.7976931348623157e308;   // std::numeric_limits<double>::max()
+  if (lane < 27) {
+    const int i = kx - 1 + lane / 9, j = ky - 1 + (lane / 3) % 3, k = kz - 1 + lane % 3;
+    if (abs(i) < COORD_BIAS - 2 && abs(j) < COORD_BIAS - 2 && abs(k) < COORD_BIAS - 2) {
+      const int s = table_find(M.keys, M.mask, pack_key(i, j, k));
+      if (s >= 0) {
         const int o = M.start[s], c = M.num[s];
         for (int e = 0; e < c; ++e) {
           const double dx = M.pts[(size_t)(o + e) * 3 + 0] - x, dy = M.pts[(size_t)(o + e) * 3 + 1] - y,
                        dz = M.pts[(size_t)(o + e) * 3 + 2] - z;
           const double d2 = (dx * dx + dy * dy) + dz * dz;   // Eigen squaredNorm of a 3-vector, no contraction
-          if (d2 < best_d2) {
-            best_d2 = d2;
+          if (d2 < bd) {
+            bd = d2;
             best = o + e;
           }
         }
       }
+    }
+  }
+  int who = lane;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+    const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int ow = __shfl_xor_sync(0xffffffffu, who, off);
+    if (od < bd || (od == bd && ow < who)) {
+      bd = od;
+      best = ob;
+      who = ow;
+    }
+  }
+  best_d2 = bd;
   return best;
 }
 
 __global__ void __launch_bounds__(128) map_nearest_kernel(MapView M, const double* __restrict__ q, int n, double max_dist,
                                                          int32_t* __restrict__ nn, double* __restrict__ nn_d2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp per query
   if (i >= n) return;
   double d2;
   const int b = nearest_in_map(M, q[(size_t)i * 3], q[(size_t)i * 3 + 1], q[(size_t)i * 3 + 2], d2);
+  if ((threadIdx.x & 31) != 0) return;
   const bool ok = b >= 0 && sqrt(d2) < max_dist;   // (closest - point).norm() < max_correspondance_distance
   nn[i] = ok ? b : -1;
   if (nn_d2) nn_d2[i] = b >= 0 ? d2 : -1.0;
@@ -329,53 +348,54 @@ struct IcpState {          // device
   int32_t pad;
 };
 
-// one pass: source <- est * source (the previous iteration's update, Registration.cpp:177), nearest neighbours, per-CTA
-// partial sums of the normal equations in a fixed order (deterministic)
+// one pass: source <- est * source (the previous iteration's update, Registration.cpp:177), nearest neighbours (one warp
+// per point, points strided over a fixed grid), per-CTA partial sums of the normal equations in a fixed order
+// (deterministic for a given grid size)
 __global__ void __launch_bounds__(ICP_THREADS) icp_accumulate_kernel(MapView M, double* __restrict__ src, int n, double max_dist,
                                                                     double kernel, const IcpState* __restrict__ st,
                                                                     double* __restrict__ partial) {
   __shared__ double red[ICP_THREADS / 32][ICP_TERMS];
   if (st->done) return;
-  const int i = blockIdx.x * ICP_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int warps = (gridDim.x * ICP_THREADS) >> 5;
   double acc[ICP_TERMS];
 #pragma unroll
   for (int k = 0; k < ICP_TERMS; ++k) acc[k] = 0.0;
-  if (i < n) {
-    const double* e = st->est;
+  double e[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) e[k] = st->est[k];
+  for (int i = (blockIdx.x * ICP_THREADS + threadIdx.x) >> 5; i < n; i += warps) {
     const double px = src[(size_t)i * 3], py = src[(size_t)i * 3 + 1], pz = src[(size_t)i * 3 + 2];
     const double x = ((e[0] * px + e[1] * py) + e[2] * pz) + e[9];
     const double y = ((e[3] * px + e[4] * py) + e[5] * pz) + e[10];
     const double z = ((e[6] * px + e[7] * py) + e[8] * pz) + e[11];
-    src[(size_t)i * 3] = x;
-    src[(size_t)i * 3 + 1] = y;
-    src[(size_t)i * 3 + 2] = z;
     double d2;
     const int b = nearest_in_map(M, x, y, z, d2);
-    if (b >= 0 && sqrt(d2) < max_dist) {
-      const double rx = x - M.pts[(size_t)b * 3], ry = y - M.pts[(size_t)b * 3 + 1], rz = z - M.pts[(size_t)b * 3 + 2];
-      const double r2 = (rx * rx + ry * ry) + rz * rz;
-      const double kk = kernel + r2;
-      const double w = (kernel * kernel) / (kk * kk);   // square(kernel) / square(kernel + residual2)
-      // J = [I | -hat(s)]: columns c3 = (0, -z, y), c4 = (z, 0, -x), c5 = (-y, x, 0)
-      const double c[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, -z, y}, {z, 0, -x}, {-y, x, 0}};
-      int t = 0;
+    __syncwarp();
+    if (lane == 0) {
+      src[(size_t)i * 3] = x;
+      src[(size_t)i * 3 + 1] = y;
+      src[(size_t)i * 3 + 2] = z;
+      if (b >= 0 && sqrt(d2) < max_dist) {
+        const double rx = x - M.pts[(size_t)b * 3], ry = y - M.pts[(size_t)b * 3 + 1], rz = z - M.pts[(size_t)b * 3 + 2];
+        const double r2 = (rx * rx + ry * ry) + rz * rz;
+        const double kk = kernel + r2;
+        const double wgt = (kernel * kernel) / (kk * kk);   // square(kernel) / square(kernel + residual2)
+        // J = [I | -hat(s)]: columns c3 = (0, -z, y), c4 = (z, 0, -x), c5 = (-y, x, 0)
+        const double c[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, -z, y}, {z, 0, -x}, {-y, x, 0}};
+        int t = 0;
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
+        for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int bb = a; bb < 6; ++bb) acc[t++] = w * ((c[a][0] * c[bb][0] + c[a][1] * c[bb][1]) + c[a][2] * c[bb][2]);
+          for (int bb = a; bb < 6; ++bb) acc[t++] += wgt * ((c[a][0] * c[bb][0] + c[a][1] * c[bb][1]) + c[a][2] * c[bb][2]);
 #pragma unroll
-      for (int a = 0; a < 6; ++a) acc[21 + a] = w * ((c[a][0] * rx + c[a][1] * ry) + c[a][2] * rz);
-      acc[27] = 1.0;
+        for (int a = 0; a < 6; ++a) acc[21 + a] += wgt * ((c[a][0] * rx + c[a][1] * ry) + c[a][2] * rz);
+        acc[27] += 1.0;
+      }
     }
   }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < ICP_TERMS; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) red[w][k] = v;
-  }
+  if (lane == 0)
+    for (int k = 0; k < ICP_TERMS; ++k) red[w][k] = acc[k];
   __syncthreads();
   if (threadIdx.x < ICP_TERMS) {
     double v = 0.0;
@@ -422,20 +442,9 @@ __device__ void rt_mul(const double* a, const double* b, double* c) {
   }
 }
 
-// one thread: fixed-order sum of the partials, 6x6 solve (LDL^T without pivoting: J^T W J is symmetric positive
-// semi-definite), SE(3) exponential, pose update, termination test (Registration.cpp:172-183)
-__global__ void icp_solve_kernel(const double* __restrict__ partial, int n_blocks, IcpState* st) {
-  if (threadIdx.x != 0 || st->done) return;
-  double s[ICP_TERMS];
-  for (int k = 0; k < ICP_TERMS; ++k) s[k] = 0.0;
-  for (int b = 0; b < n_blocks; ++b)
-    for (int k = 0; k < ICP_TERMS; ++k) s[k] += partial[(size_t)b * ICP_TERMS + k];
-  st->last_corr = (int32_t)s[27];
-  if (s[27] == 0.0) {   // "No correspondences found": leave the loop, pose unchanged
-    st->done = 1;
-    for (int i = 0; i < 12; ++i) st->est[i] = (i < 9 && i % 4 == 0) ? 1.0 : 0.0;
-    return;
-  }
+// dx = -(J^T W J)^-1 J^T W r from the 27 accumulated terms (LDL^T without pivoting: J^T W J is symmetric positive
+// semi-definite), est = SE3::exp(dx); returns |dx|
+__device__ double solve_update(const double* s, double* est) {
   double Amat[6][6], rhs[6];
   int t = 0;
   for (int a = 0; a < 6; ++a)
@@ -445,7 +454,6 @@ __global__ void icp_solve_kernel(const double* __restrict__ partial, int n_block
       ++t;
     }
   for (int a = 0; a < 6; ++a) rhs[a] = -s[21 + a];
-  // LDL^T
   double L[6][6], D[6];
   for (int j = 0; j < 6; ++j) {
     double d = Amat[j][j];
@@ -468,17 +476,222 @@ __global__ void icp_solve_kernel(const double* __restrict__ partial, int n_block
     for (int k = i + 1; k < 6; ++k) v -= L[k][i] * dx[k];
     dx[i] = v;
   }
-  double est[12], Tn[12];
   se3_exp(dx, est);
+  double nrm = 0.0;
+  for (int i = 0; i < 6; ++i) nrm += dx[i] * dx[i];
+  return sqrt(nrm);
+}
+
+// one thread: fixed-order sum of the partials, solve, pose update, termination test (Registration.cpp:172-183)
+__global__ void icp_solve_kernel(const double* __restrict__ partial, int n_blocks, IcpState* st) {
+  __shared__ double s[32];
+  if (st->done) return;
+  if (threadIdx.x < ICP_TERMS) {   // lane k sums term k over the blocks, in block order
+    double v = 0.0;
+    for (int b = 0; b < n_blocks; ++b) v += partial[(size_t)b * ICP_TERMS + threadIdx.x];
+    s[threadIdx.x] = v;
+  }
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  st->last_corr = (int32_t)s[27];
+  if (s[27] == 0.0) {   // "No correspondences found": leave the loop, pose unchanged
+    st->done = 1;
+    for (int i = 0; i < 12; ++i) st->est[i] = (i < 9 && i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  double est[12], Tn[12];
+  const double nrm = solve_update(s, est);
   rt_mul(est, st->T, Tn);
   for (int i = 0; i < 12; ++i) {
     st->est[i] = est[i];
     st->T[i] = Tn[i];
   }
   st->iters += 1;
-  double nrm = 0.0;
-  for (int i = 0; i < 6; ++i) nrm += dx[i] * dx[i];
-  if (sqrt(nrm) < 1e-4) st->done = 1;   // ESTIMATION_THRESHOLD_ (the update has been applied to the pose)
+  if (nrm < 1e-4) st->done = 1;   // ESTIMATION_THRESHOLD_ (the update has been applied to the pose)
+}
+
+// ---- VFM-ICP, first loop (Registration.cpp:197-329): Gauss-Newton on a FIXED list of descriptor correspondences, pruned
+// after every update to |d - median| < 1.5 * 1.4826 * MAD, until the mean distance changes by < 0.01 m.  K is a few
+// hundred (the source is voxelised at 5 m first), so the whole loop is one CTA; medians come from a bitonic sort.
+constexpr int P1_THREADS = 1024;
+
+struct Phase1Out {
+  double T[12];     // T_icp of this loop * initial guess
+  int32_t iters;    // value of j when the loop was left
+  int32_t kept;     // correspondences left
+};
+
+__device__ void block_sum(double* vals, int n_terms, double (*red)[ICP_TERMS], double* out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = 0; k < n_terms; ++k) {
+    double v = vals[k];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) red[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_terms) {
+    double v = 0.0;
+    for (int ww = 0; ww < P1_THREADS / 32; ++ww) v += red[ww][threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+// ascending bitonic sort of buf[0 .. n2) (n2 a power of two) by the whole CTA
+__device__ void block_bitonic_sort(double* buf, int n2) {
+  for (int size = 2; size <= n2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < n2 / 2; i += P1_THREADS) {
+        const int lo = (i / stride) * 2 * stride + (i % stride), hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const double a = buf[lo], b = buf[hi];
+        if ((a > b) == up) {
+          buf[lo] = b;
+          buf[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// std::nth_element median with the even-size average (Registration.cpp:283-293)
+__device__ __forceinline__ double median_sorted(const double* sorted, int k) {
+  const int n = k / 2;
+  return (k & 1) ? sorted[n] : (sorted[n] + sorted[n - 1]) / 2;
+}
+
+__global__ void __launch_bounds__(P1_THREADS) vfm_icp_phase1_kernel(const double* __restrict__ src_in, const double* __restrict__ tgt_in, int K,
+                                                                   const double* __restrict__ T0, double kernel, int max_iters,
+                                                                   double* src, double* tgt, double* src2, double* tgt2, double* dist,
+                                                                   double* sortbuf, Phase1Out* out) {
+  __shared__ double red[P1_THREADS / 32][ICP_TERMS];
+  __shared__ double sums[ICP_TERMS];
+  __shared__ double est_s[12], T_s[12];
+  __shared__ double stat_s[4];   // mean, median, mad
+  __shared__ int wsum[32];
+  __shared__ int base_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  // Equation (9): source <- initial_guess * source
+  if (t < 12) T_s[t] = (t < 9) ? T0[(t / 3) * 4 + (t % 3)] : T0[(t - 9) * 4 + 3];
+  __syncthreads();
+  double acc1[1] = {0.0};
+  for (int k = t; k < K; k += P1_THREADS) {
+    const double px = src_in[k * 3], py = src_in[k * 3 + 1], pz = src_in[k * 3 + 2];
+    const double x = ((T_s[0] * px + T_s[1] * py) + T_s[2] * pz) + T_s[9];
+    const double y = ((T_s[3] * px + T_s[4] * py) + T_s[5] * pz) + T_s[10];
+    const double z = ((T_s[6] * px + T_s[7] * py) + T_s[8] * pz) + T_s[11];
+    src[k * 3] = x; src[k * 3 + 1] = y; src[k * 3 + 2] = z;
+    const double qx = tgt_in[k * 3], qy = tgt_in[k * 3 + 1], qz = tgt_in[k * 3 + 2];
+    tgt[k * 3] = qx; tgt[k * 3 + 1] = qy; tgt[k * 3 + 2] = qz;
+    const double dx = x - qx, dy = y - qy, dz = z - qz;
+    acc1[0] += sqrt((dx * dx + dy * dy) + dz * dz);
+  }
+  block_sum(acc1, 1, red, sums);
+  double prev = sums[0] / (double)K;   // NaN for K == 0, never used then
+  int j = 0;
+  for (; j < max_iters; ++j) {
+    if (K == 0) break;   // "No correspondences found"
+    double acc[ICP_TERMS];
+#pragma unroll
+    for (int i = 0; i < ICP_TERMS; ++i) acc[i] = 0.0;
+    for (int k = t; k < K; k += P1_THREADS) {
+      const double x = src[k * 3], y = src[k * 3 + 1], z = src[k * 3 + 2];
+      const double rx = x - tgt[k * 3], ry = y - tgt[k * 3 + 1], rz = z - tgt[k * 3 + 2];
+      const double r2 = (rx * rx + ry * ry) + rz * rz;
+      const double kk = kernel + r2;
+      const double wgt = (kernel * kernel) / (kk * kk);
+      const double c[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, -z, y}, {z, 0, -x}, {-y, x, 0}};
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) acc[q++] += wgt * ((c[a][0] * c[b][0] + c[a][1] * c[b][1]) + c[a][2] * c[b][2]);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc[21 + a] += wgt * ((c[a][0] * rx + c[a][1] * ry) + c[a][2] * rz);
+    }
+    block_sum(acc, 27, red, sums);
+    if (t == 0) {
+      double est[12], Tn[12];
+      solve_update(sums, est);
+      rt_mul(est, T_s, Tn);
+      for (int i = 0; i < 12; ++i) {
+        est_s[i] = est[i];
+        T_s[i] = Tn[i];
+      }
+    }
+    __syncthreads();
+    // TransformPoints(estimation, src_3d); distances; their mean
+    int n2 = 1;
+    while (n2 < K) n2 <<= 1;
+    acc1[0] = 0.0;
+    for (int k = t; k < n2; k += P1_THREADS) {
+      double d = INFINITY;
+      if (k < K) {
+        const double px = src[k * 3], py = src[k * 3 + 1], pz = src[k * 3 + 2];
+        const double x = ((est_s[0] * px + est_s[1] * py) + est_s[2] * pz) + est_s[9];
+        const double y = ((est_s[3] * px + est_s[4] * py) + est_s[5] * pz) + est_s[10];
+        const double z = ((est_s[6] * px + est_s[7] * py) + est_s[8] * pz) + est_s[11];
+        src[k * 3] = x; src[k * 3 + 1] = y; src[k * 3 + 2] = z;
+        const double dx = x - tgt[k * 3], dy = y - tgt[k * 3 + 1], dz = z - tgt[k * 3 + 2];
+        d = sqrt((dx * dx + dy * dy) + dz * dz);
+        dist[k] = d;
+        acc1[0] += d;
+      }
+      sortbuf[k] = d;
+    }
+    block_sum(acc1, 1, red, sums);
+    block_bitonic_sort(sortbuf, n2);
+    if (t == 0) {
+      stat_s[0] = sums[0] / (double)K;
+      stat_s[1] = median_sorted(sortbuf, K);
+    }
+    __syncthreads();
+    const double mean = stat_s[0], median = stat_s[1];
+    for (int k = t; k < n2; k += P1_THREADS) sortbuf[k] = (k < K) ? fabs(dist[k] - median) : INFINITY;
+    __syncthreads();
+    block_bitonic_sort(sortbuf, n2);
+    if (t == 0) stat_s[2] = median_sorted(sortbuf, K) * 1.4826;
+    if (t == 0) base_s = 0;
+    __syncthreads();
+    const double mad = stat_s[2];
+    // keep |d - median| < 1.5 * mad, order preserved
+    for (int start = 0; start < K; start += P1_THREADS) {
+      const int k = start + t;
+      const bool keep = (k < K) && (fabs(dist[k] - median) < 1.5 * mad);
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) wsum[w] = __popc(bal);
+      __syncthreads();
+      int off = 0, tot = 0;
+      for (int q = 0; q < 32; ++q) {
+        const int vv = wsum[q];
+        if (q < w) off += vv;
+        tot += vv;
+      }
+      const int base = base_s;
+      if (keep) {
+        const int pos = base + off + __popc(bal & ((1u << lane) - 1u));
+        for (int c = 0; c < 3; ++c) {
+          src2[pos * 3 + c] = src[k * 3 + c];
+          tgt2[pos * 3 + c] = tgt[k * 3 + c];
+        }
+      }
+      __syncthreads();
+      if (t == 0) base_s = base + tot;
+      __syncthreads();
+    }
+    K = base_s;
+    double* sw = src; src = src2; src2 = sw;
+    sw = tgt; tgt = tgt2; tgt2 = sw;
+    __syncthreads();
+    if (fabs(prev - mean) < 0.01) break;   // EUCL_DIST_THRESHOLD_ (j is not advanced by the break)
+    prev = mean;
+  }
+  if (t < 12) out->T[t] = T_s[t];
+  if (t == 0) {
+    out->iters = j;
+    out->kept = K;
+  }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -623,7 +836,7 @@ static MapView view_of(const vfmreg_voxel_map* m) {
 int voxel_map_nearest(vfmreg_ctx* ctx, const vfmreg_voxel_map* m, const double* q, int64_t n, double max_dist, int32_t* nn, double* d2) {
   VFM_CHECK_ARG(m && m->n_points > 0, "voxel_map_nearest: empty map");
   VFM_CHECK_ARG(n > 0, "voxel_map_nearest: no query points");
-  map_nearest_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(view_of(m), q, (int)n, max_dist, nn, d2);
+  map_nearest_kernel<<<ceil_div(n * 32, 128), 128, 0, ctx->stream>>>(view_of(m), q, (int)n, max_dist, nn, d2);
   return launch_check(ctx, "map_nearest_kernel");
 }
 
@@ -636,7 +849,8 @@ int icp_register_frame(vfmreg_ctx* ctx, const vfmreg_voxel_map* m, const double*
     if (corr_out) *corr_out = 0;
     return VFMREG_OK;
   }
-  const int blocks = ceil_div(n, ICP_THREADS);
+  const int64_t want_blocks = ceil_div(n * 32, ICP_THREADS);
+  const int blocks = (int)(want_blocks < ctx->sm_count * 8 ? want_blocks : ctx->sm_count * 8);
   double* src = arena_take<double>(ctx, (size_t)n * 3);
   double* partial = arena_take<double>(ctx, (size_t)blocks * ICP_TERMS);
   IcpState* st = arena_take<IcpState>(ctx, 1);
@@ -676,6 +890,54 @@ int icp_register_frame(vfmreg_ctx* ctx, const vfmreg_voxel_map* m, const double*
   if (iters_out) *iters_out = h.iters;
   if (corr_out) *corr_out = h.last_corr;
   return VFMREG_OK;
+}
+
+// VFM-ICP (Registration.cpp:197-382): the correspondence-driven loop above, then the vanilla loop with what is left of
+// the iteration budget.  vfm_src / vfm_tgt: the descriptor correspondences (raw source coordinates, map coordinates).
+int icp_register_frame_vfm(vfmreg_ctx* ctx, const vfmreg_voxel_map* m, const double* frame, int64_t n, const double* vfm_src,
+                           const double* vfm_tgt, int64_t k, const double* T0, double max_dist, double kernel, int max_iters,
+                           double* T_out, int32_t* vfm_iters, int32_t* iters_out, int32_t* vfm_kept) {
+  if (!m || m->n_points == 0) {   // "if (voxel_map.EmptyN()) return initial_guess"
+    memcpy(T_out, T0, 16 * sizeof(double));
+    if (vfm_iters) *vfm_iters = 0;
+    if (iters_out) *iters_out = 0;
+    if (vfm_kept) *vfm_kept = 0;
+    return VFMREG_OK;
+  }
+  VFM_CHECK_ARG(k >= 0 && k < (1 << 20), "register_frame_vfm: too many descriptor correspondences");
+  int k2 = 1;
+  while (k2 < k) k2 <<= 1;
+  const size_t kk = (size_t)(k > 0 ? k : 1);
+  double* bufs = arena_take<double>(ctx, kk * 3 * 4 + kk + (size_t)k2 + 16);
+  Phase1Out* out = arena_take<Phase1Out>(ctx, 1);
+  double* T0d = arena_take<double>(ctx, 16);
+  if (!bufs || !out || !T0d) {
+    set_error("register_frame_vfm: scratch arena too small");
+    return VFMREG_ERR_ALLOC;
+  }
+  VFM_CUDA(cudaMemcpyAsync(T0d, T0, 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  vfm_icp_phase1_kernel<<<1, P1_THREADS, 0, ctx->stream>>>(vfm_src, vfm_tgt, (int)k, T0d, kernel, max_iters, bufs, bufs + kk * 3,
+                                                          bufs + kk * 6, bufs + kk * 9, bufs + kk * 12, bufs + kk * 13, out);
+  VFM_TRY(launch_check(ctx, "vfm_icp_phase1_kernel"));
+  Phase1Out h;
+  VFM_CUDA(cudaMemcpyAsync(&h, out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (vfm_iters) *vfm_iters = h.iters;
+  if (vfm_kept) *vfm_kept = h.kept;
+  double T1[16] = {0};
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T1[i * 4 + j] = h.T[i * 3 + j];
+    T1[i * 4 + 3] = h.T[9 + i];
+  }
+  T1[15] = 1.0;
+  const int left = max_iters - h.iters;
+  if (left <= 0 || n == 0) {
+    memcpy(T_out, T1, sizeof(T1));
+    if (iters_out) *iters_out = 0;
+    return VFMREG_OK;
+  }
+  arena_reset(ctx);
+  return icp_register_frame(ctx, m, frame, n, T1, max_dist, kernel, left, T_out, iters_out, nullptr);
 }
 
 }  // namespace vfm
@@ -754,9 +1016,26 @@ int vfmreg_register_frame(vfmreg_ctx* ctx, const vfmreg_voxel_map* map, const do
   VFM_CHECK_ARG(max_iterations > 0, "register_frame: max_iterations must be > 0");
   VFM_CUDA(cudaSetDevice(ctx->device));
   arena_reset(ctx);
-  VFM_TRY(arena_reserve(ctx, arena_bytes((size_t)(n > 0 ? n : 1) * 3, 8) + arena_bytes((size_t)(ceil_div(n, ICP_THREADS) + 1) * ICP_TERMS, 8) + 4096));
+  VFM_TRY(arena_reserve(ctx, arena_bytes((size_t)(n > 0 ? n : 1) * 3, 8) + arena_bytes((size_t)(ctx->sm_count * 8 + 1) * ICP_TERMS, 8) + 4096));
   return icp_register_frame(ctx, map, frame, n, T0, max_correspondence_distance, kernel, max_iterations, T_out, iterations,
                             correspondences);
+}
+
+int vfmreg_register_frame_vfm(vfmreg_ctx* ctx, const vfmreg_voxel_map* map, const double* frame, int64_t n, const double* vfm_src,
+                              const double* vfm_tgt, int64_t k, const double* T0, double max_correspondence_distance, double kernel,
+                              int32_t max_iterations, double* T_out, int32_t* vfm_iterations, int32_t* iterations,
+                              int32_t* vfm_kept) {
+  VFM_CHECK_ARG(ctx && T0 && T_out && (frame || n == 0) && ((vfm_src && vfm_tgt) || k == 0), "register_frame_vfm: null pointer");
+  VFM_CHECK_ARG(max_iterations > 0, "register_frame_vfm: max_iterations must be > 0");
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  arena_reset(ctx);
+  size_t k2 = 1;
+  while ((int64_t)k2 < k) k2 <<= 1;
+  const size_t need1 = arena_bytes((size_t)(k > 0 ? k : 1) * 13 + k2 + 16, 8) + 4096;
+  const size_t need2 = arena_bytes((size_t)(n > 0 ? n : 1) * 3, 8) + arena_bytes((size_t)(ctx->sm_count * 8 + 1) * ICP_TERMS, 8) + 4096;
+  VFM_TRY(arena_reserve(ctx, need1 > need2 ? need1 : need2));
+  return icp_register_frame_vfm(ctx, map, frame, n, vfm_src, vfm_tgt, k, T0, max_correspondence_distance, kernel, max_iterations,
+                                T_out, vfm_iterations, iterations, vfm_kept);
 }
 
 }  // extern "C"

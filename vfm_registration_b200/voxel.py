@@ -146,3 +146,34 @@ def register_frame(points, voxel_map: "VoxelMap", initial_guess, max_corresponda
     if return_info:
         return T, {"iterations": int(iters.value), "correspondences": int(corr.value)}
     return T
+
+
+def register_frame_vfm(points_xyz, voxel_map: "VoxelMap", vfm_src, vfm_tgt, initial_guess, max_correspondance_distance: float,
+                       kernel: float, *, max_iterations: int = MAX_NUM_ITERATIONS, return_info: bool = False):
+    """The descriptor-carrying RegisterFrame ("VFM-ICP", Registration.cpp:197-382) given its descriptor correspondences:
+    ``vfm_src`` (K, 3) source points before the initial guess is applied, ``vfm_tgt`` (K, 3) matched map points.  Loop 1
+    refines on those (MAD pruning), loop 2 is the vanilla ICP of ``register_frame`` with the remaining iteration budget."""
+    ctx = voxel_map.ctx
+    dev = torch.device("cuda", ctx.device)
+
+    def f64(x):
+        t = torch.as_tensor(x)
+        if t.ndim != 2 or t.shape[1] != 3:
+            raise ValueError("Invalid shape")
+        return t.to(device=dev, dtype=torch.float64).contiguous()
+    pts, s, t = f64(points_xyz), f64(np.zeros((0, 3)) if vfm_src is None else vfm_src), f64(np.zeros((0, 3)) if vfm_tgt is None else vfm_tgt)
+    if s.shape != t.shape:
+        raise ValueError("Invalid shape")
+    T0 = np.ascontiguousarray(np.asarray(initial_guess, dtype=np.float64))
+    if T0.shape != (4, 4):
+        raise ValueError("Invalid shape")
+    T = np.zeros((4, 4), dtype=np.float64)
+    it1, it2, kept = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_register_frame_vfm(ctx.handle, voxel_map.handle, _ptr(pts), pts.shape[0], _ptr(s), _ptr(t), s.shape[0],
+                                                T0.ctypes.data_as(C.c_void_p), float(max_correspondance_distance), float(kernel),
+                                                int(max_iterations), T.ctypes.data_as(C.c_void_p), C.byref(it1), C.byref(it2),
+                                                C.byref(kept)), "vfmreg_register_frame_vfm")
+    if return_info:
+        return T, {"vfm_iterations": int(it1.value), "iterations": int(it2.value), "vfm_kept": int(kept.value)}
+    return T
