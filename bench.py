@@ -82,6 +82,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """One process per GPU: run on the cores NVML reports as local to that GPU, so that the pinned host buffers of the e2e leg
+    are first-touched on the GPU's NUMA node (a rank left on the far socket halves its H2D rate).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cores local to GPU {index}"
+    except Exception as e:  # pragma: no cover
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 def cpu_path(pair, n_scan_rows, threads_note=True):
     """The reference-style CPU path (oracle/c) on one pair; match restricted to the first n_scan_rows scan points for
     the scan->map direction and timed separately so it can be scaled."""
@@ -152,6 +170,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -282,7 +301,7 @@ def main():
             "dtype": "f32 match / f64 solve", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "parallelism": f"pairs sharded over {world} rank(s)",
                        "l2": f"{P} distinct pairs x 92 MB cycled per step (> 126 MB L2)", "algo": args.algo,
-                       "lanes": args.lanes or 3},
+                       "lanes": args.lanes or 3, "host_affinity": numa},
             "hyps_per_sec": value * N_HYP, "recall_at_1m_5deg": recall,
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -72,20 +72,21 @@ static int ensure_pinned(vfmreg_ctx* ctx, size_t bytes) {
 
 static inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
 
-static bool use_tc(uint32_t flags) {
+static bool use_tc(uint32_t flags, int d) {
   const uint32_t algo = flags & VFMREG_ALGO_MASK;
-  // the tcgen05 path's error bound assumes unit-norm rows; un-normalised searches stay on the exact fp32 kernel
-  return (flags & VFMREG_NORMALIZE) && algo != VFMREG_ALGO_SIMT;
+  // the tcgen05 path's error bound assumes unit-norm rows of at most 1024 dimensions; un-normalised or wider searches
+  // stay on the exact fp32 kernel
+  return (flags & VFMREG_NORMALIZE) && algo != VFMREG_ALGO_SIMT && d <= 1024;
 }
 
-static inline int padded_dim(int d, uint32_t flags) { return round_up(d, use_tc(flags) ? 64 : 16); }
+static inline int padded_dim(int d, uint32_t flags) { return round_up(d, use_tc(flags, d) ? 64 : 16); }
 
 // scratch needed by match_nn_impl beyond the caller-visible outputs
 static size_t match_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int d, uint32_t flags) {
   const int dp = padded_dim(d, flags);
   const bool mutual = (flags & VFMREG_MUTUAL) != 0;
   size_t s = arena_bytes((size_t)n * dp, 4) + arena_bytes((size_t)m * dp, 4);
-  if (use_tc(flags)) {
+  if (use_tc(flags, d)) {
     s += arena_bytes((size_t)n * dp, 2) + arena_bytes((size_t)m * dp, 2) + arena_bytes(n, 1) + arena_bytes(m, 1);
     s += match_tc_scratch(ctx, n, m);
     if (mutual) s += match_tc_scratch(ctx, m, n);
@@ -101,8 +102,8 @@ static bool g_full_mutual = [] { const char* e = getenv("VFMREG_FULL_MUTUAL"); r
 
 // The reverse search of the mutual check can be restricted to the map rows that some gated query points at when the
 // tensor-core path runs and the query side is the smaller one (the pruned search is (<= n) x n instead of m x n).
-static bool prune_mutual(int64_t n, int64_t m, uint32_t flags) {
-  return use_tc(flags) && (flags & VFMREG_MUTUAL) && n <= m && !g_full_mutual;
+static bool prune_mutual(int64_t n, int64_t m, int d, uint32_t flags) {
+  return use_tc(flags, d) && (flags & VFMREG_MUTUAL) && n <= m && !g_full_mutual;
 }
 
 static size_t pruned_scratch(vfmreg_ctx* ctx, int64_t n, int d, uint32_t flags) {
@@ -114,7 +115,7 @@ static size_t pruned_scratch(vfmreg_ctx* ctx, int64_t n, int d, uint32_t flags) 
 static int match_nn_impl(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64_t m, int32_t d, uint32_t flags,
                          int32_t* idx01, float* sim01, float* sec01, int32_t* idx10, float* sim10, float* sec10,
                          const vfmreg_register_params* prune = nullptr, int32_t* corr = nullptr, int32_t* count = nullptr) {
-  const bool tc = use_tc(flags);
+  const bool tc = use_tc(flags, d);
   const int dp = padded_dim(d, flags);
   float* an = arena_take<float>(ctx, (size_t)n * dp);
   float* bn = arena_take<float>(ctx, (size_t)m * dp);
@@ -339,7 +340,7 @@ struct RegOut {
 static size_t register_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p) {
   const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
   (void)mutual;
-  return match_scratch(ctx, n, m, d, p->flags) + (prune_mutual(n, m, p->flags) ? pruned_scratch(ctx, n, d, p->flags) : 0) +
+  return match_scratch(ctx, n, m, d, p->flags) + (prune_mutual(n, m, d, p->flags) ? pruned_scratch(ctx, n, d, p->flags) : 0) +
          ransac_scratch((int32_t)n, p->n_hyp) + arena_bytes(n, 4) * 3 + arena_bytes(m, 4) +
          arena_bytes((size_t)n * 2, 4) + arena_bytes(n, 1) + arena_bytes(16, 8) + arena_bytes(8, 8) + 4096;
 }
@@ -353,7 +354,7 @@ static int register_enqueue(vfmreg_ctx* ctx, const float* src_xyz, const float* 
   int32_t* idx01 = arena_take<int32_t>(ctx, n);
   float* sim01 = arena_take<float>(ctx, n);
   float* sec01 = arena_take<float>(ctx, n);
-  const bool pruned = prune_mutual(n, m, p->flags);
+  const bool pruned = prune_mutual(n, m, d, p->flags);
   int32_t* idx10 = (mutual && !pruned) ? arena_take<int32_t>(ctx, m) : nullptr;
   if (!idx01 || !sim01 || !sec01 || (mutual && !pruned && !idx10)) {
     set_error("register: scratch arena too small");

@@ -5,47 +5,62 @@
 
 namespace vfm {
 
+// exclusive prefix of one int per thread over a 1024-thread CTA; *total = sum
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* wsum, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += u;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int x = wsum[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += u;
+    }
+    wsum[lane] = x;
+  }
+  __syncthreads();
+  total = wsum[31];
+  return (w > 0 ? wsum[w - 1] : 0) + incl - v;
+}
+
+__device__ __forceinline__ bool corr_keep(const int32_t* __restrict__ idx01, const float* __restrict__ sim01, const float* __restrict__ sec01,
+                                          const int32_t* __restrict__ idx10, int i, float min_cos, float ratio2, int use_cos,
+                                          int use_ratio, int mutual, int& j) {
+  j = idx01[i];
+  bool keep = j >= 0;
+  if (keep && use_cos) keep = sim01[i] >= min_cos;
+  if (keep && mutual) keep = idx10[j] == i;
+  if (keep && use_ratio) keep = __fsub_rn(1.0f, sim01[i]) < __fmul_rn(ratio2, __fsub_rn(1.0f, sec01[i]));
+  return keep;
+}
+
+// Thread t owns the consecutive queries [t * per, (t + 1) * per): count, one block-wide scan, write -- two passes over
+// at most a few 10^4 queries, three barriers in total.
 __global__ void __launch_bounds__(1024) filter_corr_kernel(const int32_t* __restrict__ idx01, const float* __restrict__ sim01,
                                                           const float* __restrict__ sec01, const int32_t* __restrict__ idx10,
                                                           int n, float min_cos, float ratio2, int use_cos, int use_ratio,
                                                           int mutual, int32_t* __restrict__ corr, int32_t* __restrict__ count) {
-  __shared__ int warp_tot[32];
-  __shared__ int base_s;
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t == 0) base_s = 0;
-  __syncthreads();
-  for (int start = 0; start < n; start += 1024) {
-    const int i = start + t;
-    bool keep = false;
-    int j = -1;
-    if (i < n) {
-      j = idx01[i];
-      keep = j >= 0;
-      if (keep && use_cos) keep = sim01[i] >= min_cos;
-      if (keep && mutual) keep = idx10[j] == i;
-      if (keep && use_ratio) keep = __fsub_rn(1.0f, sim01[i]) < __fmul_rn(ratio2, __fsub_rn(1.0f, sec01[i]));
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_tot[w] = __popc(bal);
-    __syncthreads();
-    int off = 0, tot = 0;
-#pragma unroll 1
-    for (int k = 0; k < 32; ++k) {
-      const int v = warp_tot[k];
-      if (k < w) off += v;
-      tot += v;
-    }
-    const int base = base_s;
-    if (keep) {
-      const int pos = base + off + __popc(bal & ((1u << lane) - 1u));
+  __shared__ int wsum[32];
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int mine = 0, j;
+  for (int i = lo; i < hi; ++i) mine += corr_keep(idx01, sim01, sec01, idx10, i, min_cos, ratio2, use_cos, use_ratio, mutual, j) ? 1 : 0;
+  int total;
+  int pos = block_exclusive_scan_1024(mine, wsum, total);
+  for (int i = lo; i < hi; ++i)
+    if (corr_keep(idx01, sim01, sec01, idx10, i, min_cos, ratio2, use_cos, use_ratio, mutual, j)) {
       corr[2 * pos] = i;
       corr[2 * pos + 1] = j;
+      ++pos;
     }
-    __syncthreads();
-    if (t == 0) base_s = base + tot;
-    __syncthreads();
-  }
-  if (t == 0) *count = base_s;
+  if (threadIdx.x == 0) *count = total;
 }
 
 int filter_corr(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const float* sec01, const int32_t* idx10,
@@ -102,42 +117,23 @@ int gather_rows(vfmreg_ctx* ctx, const int32_t* pairs, const int32_t* count, int
 __global__ void __launch_bounds__(1024) filter_mutual_list_kernel(const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_count,
                                                                  const int32_t* __restrict__ back, int max_rows,
                                                                  int32_t* __restrict__ corr, int32_t* __restrict__ count) {
-  __shared__ int warp_tot[32];
-  __shared__ int base_s;
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  __shared__ int wsum[32];
   const int n = min(*cand_count, max_rows);
-  if (t == 0) base_s = 0;
-  __syncthreads();
-  for (int start = 0; start < n; start += 1024) {
-    const int k = start + t;
-    int i = -1, j = -1;
-    bool keep = false;
-    if (k < n) {
-      i = cand[2 * k];
-      j = cand[2 * k + 1];
-      keep = back[k] == i;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_tot[w] = __popc(bal);
-    __syncthreads();
-    int off = 0, tot = 0;
-#pragma unroll 1
-    for (int q = 0; q < 32; ++q) {
-      const int v = warp_tot[q];
-      if (q < w) off += v;
-      tot += v;
-    }
-    const int base = base_s;
-    if (keep) {
-      const int pos = base + off + __popc(bal & ((1u << lane) - 1u));
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int mine = 0;
+  for (int k = lo; k < hi; ++k) mine += (back[k] == cand[2 * k]) ? 1 : 0;
+  int total;
+  int pos = block_exclusive_scan_1024(mine, wsum, total);
+  for (int k = lo; k < hi; ++k) {
+    const int i = cand[2 * k];
+    if (back[k] == i) {
       corr[2 * pos] = i;
-      corr[2 * pos + 1] = j;
+      corr[2 * pos + 1] = cand[2 * k + 1];
+      ++pos;
     }
-    __syncthreads();
-    if (t == 0) base_s = base + tot;
-    __syncthreads();
   }
-  if (t == 0) *count = base_s;
+  if (threadIdx.x == 0) *count = total;
 }
 
 int filter_mutual_list(vfmreg_ctx* ctx, const int32_t* cand, const int32_t* cand_count, const int32_t* back, int64_t max_rows,

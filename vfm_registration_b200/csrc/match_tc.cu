@@ -912,7 +912,7 @@ __device__ __forceinline__ float canon_dot(const float* __restrict__ x, const fl
 __global__ void __launch_bounds__(128)
     rerank_select_kernel(int n, const int* __restrict__ n_dev, int slots, int top1, const uint8_t* __restrict__ nz, float* __restrict__ cand_v,
                          const int* __restrict__ cand_n, const float2* __restrict__ slot_top2, int* __restrict__ work,
-                         int* __restrict__ work_count) {
+                         int* __restrict__ work_count, uint8_t* __restrict__ row_overflow) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   if (n_dev) n = min(n, __ldg(n_dev));
@@ -931,6 +931,7 @@ __global__ void __launch_bounds__(128)
         const float2 t = slot_top2[(long long)row * slots + s];
         if (t.x > t1) { t2 = fmaxf(t1, t.y); t1 = t.x; } else { t2 = fmaxf(t2, t.x); }
       }
+      if (overflow && row_overflow) row_overflow[row] = 1;
       if (!overflow) {  // overflowed rows are redone exactly
         const float thr = (top1 ? t1 : t2) - MARGIN;
 #pragma unroll
@@ -960,17 +961,99 @@ __global__ void __launch_bounds__(128)
     if (e < n_keep) work[o + e] = (int)(g * CAP + keep[e]);
 }
 
-// Re-rank, step 1b: one thread per surviving candidate computes its canonical fp32 score (the fmaf chain over k is
-// sequential by definition; the parallelism is across candidates) and writes it over the approximate one.
+// (score, index) packed so that an unsigned 64-bit max picks the largest score and, on equal scores, the lowest index.
+// Canonical scores are never -0 (the fmaf chain starts from +0), so the bit order of the transformed float is the float order.
+__device__ __forceinline__ unsigned long long pack_best(float score, int idx) {
+  uint32_t u = __float_as_uint(score);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
+}
+__device__ __forceinline__ void unpack_best(unsigned long long key, float& score, int& idx) {
+  uint32_t u = (uint32_t)(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  score = __uint_as_float(u);
+  idx = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu));
+}
+
+// Re-rank, step 1b: L = 16 lanes per surviving candidate.  Lane l owns the l-th contiguous segment of the two rows (dp / 16
+// elements = dp / 64 float4 per row, at most PER_MAX), so every load of a candidate is in flight at once; the canonical fmaf chain over k
+// ascending is then walked lane by lane, the accumulator handed on by shuffle -- the same operation order as one thread
+// running the whole chain.  The exact score replaces the approximate one; in top-1 mode it is also folded into the
+// row's packed (score, index) maximum, which makes the per-row pick a single atomic.
+template <int PER_MAX>
 __global__ void __launch_bounds__(128)
     rerank_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int dp, int slots, float* __restrict__ cand_v,
-                      const int* __restrict__ cand_i, const int* __restrict__ work, const int* __restrict__ work_count) {
+                      const int* __restrict__ cand_i, const int* __restrict__ work, const int* __restrict__ work_count,
+                      unsigned long long* __restrict__ row_key) {
+  constexpr int L = 16;
   const int count = *work_count;
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
-    const int ent = work[w];
-    const int row = ent / (slots * CAP);
-    cand_v[ent] = canon_dot(a + (long long)row * dp, b + (long long)cand_i[ent] * dp, dp);
+  const int lane = threadIdx.x & 31, gl = lane & (L - 1), gbase = lane & ~(L - 1);
+  const int per = dp / (4 * L);   // float4 per lane and row (dp % 64 == 0, dp <= 64 PER_MAX)
+  const int groups = (gridDim.x * blockDim.x) / L;
+  const int rounds = (count + groups - 1) / groups;
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+  for (int r = 0; r < rounds; ++r, w += groups) {   // every lane walks the loop: the shuffles need the whole warp
+    const bool live = w < count;
+    int ent = 0, row = 0, col = 0;
+    float4 av[PER_MAX], bv[PER_MAX];
+    if (live) {
+      ent = work[w];
+      row = ent / (slots * CAP);
+      col = cand_i[ent];
+      const float4* a4 = reinterpret_cast<const float4*>(a + (long long)row * dp) + gl * per;
+      const float4* b4 = reinterpret_cast<const float4*>(b + (long long)col * dp) + gl * per;
+#pragma unroll
+      for (int u = 0; u < PER_MAX; ++u)
+        if (u < per) {
+          av[u] = __ldg(a4 + u);
+          bv[u] = __ldg(b4 + u);
+        }
+    }
+    float acc = 0.0f;
+#pragma unroll 1
+    for (int sl = 0; sl < L; ++sl) {
+      if (live && gl == sl) {
+#pragma unroll
+        for (int u = 0; u < PER_MAX; ++u)
+          if (u < per) {
+            acc = fmaf(av[u].x, bv[u].x, acc);
+            acc = fmaf(av[u].y, bv[u].y, acc);
+            acc = fmaf(av[u].z, bv[u].z, acc);
+            acc = fmaf(av[u].w, bv[u].w, acc);
+          }
+      }
+      acc = __shfl_sync(0xffffffffu, acc, gbase + sl);   // lane sl's running sum -> every lane of the group
+    }
+    if (live && gl == 0) {
+      cand_v[ent] = acc;
+      if (row_key) atomicMax(row_key + row, pack_best(acc, col));
+    }
   }
+}
+
+// Re-rank, step 2 in top-1 mode: unpack the row's (score, index) maximum; overflowed rows go to exact_rows_kernel.
+__global__ void __launch_bounds__(128)
+    rerank_finish_kernel(int n, const int* __restrict__ n_dev, const uint8_t* __restrict__ nz, const unsigned long long* __restrict__ row_key,
+                         const uint8_t* __restrict__ row_overflow, int32_t* __restrict__ idx, float* __restrict__ best,
+                         int* __restrict__ redo_list, int* __restrict__ redo_count) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, __ldg(n_dev));
+  if (row >= n) return;
+  if (!nz[row]) {  // all-zero query: every canonical inner product is exactly +0 -> lowest index wins
+    idx[row] = 0;
+    if (best) best[row] = 0.0f;
+    return;
+  }
+  const unsigned long long key = row_key[row];
+  if (row_overflow[row] || key == 0ULL) {
+    redo_list[atomicAdd(redo_count, 1)] = row;
+    return;
+  }
+  float sc;
+  int j;
+  unpack_best(key, sc, j);
+  idx[row] = j;
+  if (best) best[row] = sc;
 }
 
 // Re-rank, step 2: one thread per query row picks the exact top-2 (lowest index on ties); rows whose list overflowed are
@@ -1153,14 +1236,15 @@ size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic) {
   const TcPlan p1 = tc_plan(ctx, n, m, 1 << 20, dynamic);
   if (p1.slots > p.slots) p.slots = p1.slots;
   return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
-         arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + arena_bytes((size_t)n * p.slots * CAP + 1, 4) + 1024;
+         arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + arena_bytes((size_t)n * p.slots * CAP + 1, 4) +
+         arena_bytes((size_t)n, 8) + arena_bytes((size_t)n, 1) + 1024;
 }
 
 // a32/b32: renormalised fp32 rows (n x dp), a16/b16: their fp16 copies, nz_a: non-zero flags of the query rows.
 // n_dev (optional, device): the number of query rows actually present; n is then the capacity of a16 / a32 / nz_a / idx.
 int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
              const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev, const float* seed) {
-  VFM_CHECK_ARG(dp % TBK == 0, "match_tc: padded dim %d not a multiple of %d", dp, TBK);
+  VFM_CHECK_ARG(dp % TBK == 0 && dp <= 1024, "match_tc: padded dim %d must be a multiple of %d and <= 1024 (error bound)", dp, TBK);
   VFM_CHECK_ARG(n > 0 && m > 0 && n < (1LL << 30) && m < (1LL << 30), "match_tc: bad sizes");
   const TcPlan plan = tc_plan(ctx, n, m, dp, n_dev != nullptr);
   float* cand_v = arena_take<float>(ctx, (size_t)n * plan.slots * CAP);
@@ -1169,13 +1253,17 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   float2* slot_top2 = arena_take<float2>(ctx, (size_t)n * plan.slots);
   int* redo = arena_take<int>(ctx, (size_t)n + 1);  // [0] = count, [1..] = rows
   int* work = arena_take<int>(ctx, (size_t)n * plan.slots * CAP + 1);  // [0] = count, [1..] = candidate entries to re-score
-  if (!cand_v || !cand_i || !cand_n || !slot_top2 || !redo || !work) {
+  unsigned long long* row_key = arena_take<unsigned long long>(ctx, (size_t)n);   // top-1 mode: packed (score, index) maximum
+  uint8_t* row_overflow = arena_take<uint8_t>(ctx, (size_t)n);
+  if (!cand_v || !cand_i || !cand_n || !slot_top2 || !redo || !work || !row_key || !row_overflow) {
     set_error("match_tc: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
   VFM_CUDA(cudaMemsetAsync(cand_n, 0, sizeof(int) * (size_t)n * plan.slots, ctx->stream));
   VFM_CUDA(cudaMemsetAsync(redo, 0, sizeof(int), ctx->stream));
   VFM_CUDA(cudaMemsetAsync(work, 0, sizeof(int), ctx->stream));
+  VFM_CUDA(cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)n, ctx->stream));
+  VFM_CUDA(cudaMemsetAsync(row_overflow, 0, (size_t)n, ctx->stream));
   CUtensorMap map_a, map_b;
   VFM_TRY(make_map_f16(&map_a, a16, n, dp, TBM));
   VFM_TRY(make_map_f16(&map_b, b16, m, dp, plan.paired ? TBN / 2 : TBN));
@@ -1230,13 +1318,25 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   }
   group_end(ctx, grp, 1);
   const long long entries = (long long)n * plan.slots;
-  rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, n_dev, plan.slots, P.top1, nz_a, cand_v, cand_n, slot_top2, work + 1, work);
+  const bool fold_pick = (sec == nullptr);   // only the best match is requested: the pick is folded into the re-score
+  rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, n_dev, plan.slots, P.top1, nz_a, cand_v, cand_n, slot_top2,
+                                                                       work + 1, work, row_overflow);
   VFM_TRY(launch_check(ctx, "rerank_select_kernel"));
-  rerank_dot_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work + 1, work);
+  if (dp <= 512)
+    rerank_dot_kernel<8><<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work + 1, work,
+                                                                      fold_pick ? row_key : nullptr);
+  else
+    rerank_dot_kernel<16><<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work + 1, work,
+                                                                      fold_pick ? row_key : nullptr);
   VFM_TRY(launch_check(ctx, "rerank_dot_kernel"));
-  rerank_pick_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>((int)n, n_dev, (int)m, plan.slots, nz_a, cand_v, cand_i, cand_n, idx, best, sec,
-                                                               redo + 1, redo);
-  VFM_TRY(launch_check(ctx, "rerank_pick_kernel"));
+  if (fold_pick) {
+    rerank_finish_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>((int)n, n_dev, nz_a, row_key, row_overflow, idx, best, redo + 1, redo);
+    VFM_TRY(launch_check(ctx, "rerank_finish_kernel"));
+  } else {
+    rerank_pick_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>((int)n, n_dev, (int)m, plan.slots, nz_a, cand_v, cand_i, cand_n, idx, best, sec,
+                                                                 redo + 1, redo);
+    VFM_TRY(launch_check(ctx, "rerank_pick_kernel"));
+  }
   exact_rows_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(a32, b32, (int)m, dp, redo + 1, redo, idx, best, sec);
   VFM_TRY(launch_check(ctx, "exact_rows_kernel"));
   if (want_dbg) {
