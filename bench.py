@@ -179,6 +179,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its banner on stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import vfm_registration_b200 as v

@@ -21,6 +21,8 @@ struct Layer {
   float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ls1, *ln2_g, *ln2_b, *fc1_b, *fc2_b, *ls2;
   __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
   CUtensorMap m_qkv, m_proj, m_fc1, m_fc2;
+  CUtensorMap m_proj_n, m_fc2_n;   // 128-row boxes of proj / fc2 for small batches
+  bool has_narrow = false;
 };
 
 }  // namespace
@@ -166,6 +168,11 @@ int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit*
     if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_proj, l.proj_w, w, w, w, vit_gemm_tile_n(w), true);
     if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc1, l.fc1_w, md, w, w, vit_gemm_tile_n(md), true);
     if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc2, l.fc2_w, w, md, md, vit_gemm_tile_n(w), true);
+    if (rc == VFMREG_OK && w % 128 == 0) {
+      rc = make_tmap_16bit(&l.m_proj_n, l.proj_w, w, w, w, 128, true);
+      if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc2_n, l.fc2_w, w, md, md, 128, true);
+      l.has_narrow = true;
+    }
   }
   if (rc != VFMREG_OK) {
     vfmreg_vit_destroy(v);
@@ -292,12 +299,12 @@ static int vit_enqueue(vfmreg_vit* v, const uint8_t* images, int b, int img_h, i
     VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS, v->m_xn, l.m_qkv, ep));
     VFM_TRY(vit_attention(ctx, v->qkv, b, t, v->cfg.heads, w, v->ao));
     ep = GemmEpilogue{rows, w, w, 0, w, l.proj_b, l.ls1, nullptr, v->x, nullptr};
-    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_ao, l.m_proj, ep));
+    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_ao, l.m_proj, ep, l.has_narrow ? &l.m_proj_n : nullptr));
     VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, l.ln2_g, l.ln2_b, v->cfg.ln_eps, v->xn));
     ep = GemmEpilogue{rows, md, w, 0, md, l.fc1_b, nullptr, nullptr, nullptr, v->hbuf};
     VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS_GELU, v->m_xn, l.m_fc1, ep));
     ep = GemmEpilogue{rows, w, md, 0, w, l.fc2_b, l.ls2, nullptr, v->x, nullptr};
-    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_h, l.m_fc2, ep));
+    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_h, l.m_fc2, ep, l.has_narrow ? &l.m_fc2_n : nullptr));
   }
   return vit_final_norm(ctx, v->x, b, t, w, v->norm_g, v->norm_b, v->cfg.ln_eps, v->cn_g, v->cn_b, v->cfg.cn_eps, v->cfg.channel_norm,
                         tokens);

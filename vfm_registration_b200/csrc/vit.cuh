@@ -20,7 +20,9 @@ struct GemmEpilogue {
   __nv_bfloat16* out_bf16;  // bf16 output (EPI_BF16_*)
 };
 
-int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep);
+// w_narrow (optional): the same weight with a 128-row TMA box, used by the residual GEMMs when the wide tiling under-fills the GPU
+int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep,
+             const CUtensorMap* w_narrow = nullptr);
 // output-tile width the GEMM uses for an N-column weight (256 or 192; 0 = unsupported): the weight's TMA box has that many rows
 int vit_gemm_tile_n(int n);
 

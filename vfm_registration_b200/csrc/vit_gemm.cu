@@ -8,12 +8,14 @@
 //
 // Persistent kernel, one CTA per SM, static round-robin over 128 x BN output tiles (BN = 256 when N % 256 == 0, else 192:
 // every DINOv2 width is a multiple of one of them; wide N keeps the MMA off the shared-memory read limit, which a
-// 128-wide tile hits).  Warp 0 = TMA producer (128B-swizzled 64-wide K chunks, 4-stage mbarrier ring), warp 1 = TMEM
+// 128-wide tile hits).  The residual GEMMs (N = width) fall back to BN = 128 when the wide tiling would leave more than a
+// quarter of the SMs without a tile (small batches: 6 images x 257 tokens = 13 row blocks x 4 column tiles = 52 CTAs).  Warp 0 = TMA producer (128B-swizzled 64-wide K chunks, 4-stage mbarrier ring), warp 1 = TMEM
 // allocator + elected-lane tcgen05.mma issuer (kind::f16, bf16 operands, M128 N{192,256} K16), accumulators double-buffered in
 // TMEM (2 x 256 columns) so the epilogue of tile i (warps 2-5: tcgen05.ld 32x32b, one output row per thread) overlaps
 // the MMAs of tile i+1.  Bound: tensor pipe for the large layers; at BASELINE config 3 (6 images, 1542 tokens) most layers
 // are below one wave of tiles and are latency bound.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -27,6 +29,8 @@ constexpr uint32_t GB_BYTES_MAX = 256 * GBK * 2;
 constexpr uint32_t GSMEM_BARS = GSTAGES * (GA_BYTES + GB_BYTES_MAX);
 constexpr uint32_t GSMEM_TOTAL = GSMEM_BARS + 256 + 1024;
 
+// exact-erf GELU.  (An Abramowitz-Stegun erf -- reciprocal + ex2 + 6 fma -- was measured SLOWER than libm's erff here:
+// 17.98 vs 16.24 ms for ViT-L/14 B=48 on the same box; erff's polynomial fast path has no reciprocal.)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 template <int EPI, int BN>
@@ -208,9 +212,13 @@ static int launch_gemm(vfmreg_ctx* ctx, const CUtensorMap& a, const CUtensorMap&
 
 int vit_gemm_tile_n(int n) { return (n % 256 == 0) ? 256 : ((n % 192 == 0) ? 192 : 0); }
 
-int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep) {
+int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep, const CUtensorMap* w_narrow) {
   const int bn = vit_gemm_tile_n(ep.n);
   VFM_CHECK_ARG(ep.k % GBK == 0 && bn != 0 && ep.m > 0, "vit_gemm: unsupported shape m=%d n=%d k=%d", ep.m, ep.n, ep.k);
+  // tuning aid: VFMREG_VIT_NARROW=0 keeps the wide tiles (ViT-L/14, 6 images: 4.09 ms wide, 3.71 ms narrow on the same box)
+  static const bool narrow_ok = [] { const char* e = getenv("VFMREG_VIT_NARROW"); return !(e && e[0] == '0'); }();
+  if (narrow_ok && w_narrow && epi == EPI_F32_RESID && ep.n % 128 == 0 && ceil_div(ep.m, GBM) * (ep.n / bn) * 4 < ctx->sm_count * 3)
+    return launch_gemm<EPI_F32_RESID, 128>(ctx, a, *w_narrow, ep);
 #define VFM_GEMM_CASE(E)                                                   \
   case E:                                                                  \
     return bn == 256 ? launch_gemm<E, 256>(ctx, a, w, ep) : launch_gemm<E, 192>(ctx, a, w, ep);
