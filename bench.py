@@ -30,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_MAP, N_SCAN, DIM, N_HYP = 50_000, 10_000, 384, 8192
+N_MAP, N_SCAN, DIM, N_HYP = 50_000, 10_000, 384, int(os.environ.get("VFM_BENCH_HYPS", "8192"))   # env: tuning experiments only
 MIN_COS, TAU = 0.8, 1.0
 METRIC, UNIT = "scene_pairs_per_sec", "pairs/s"
 WORKLOAD = ("configs[1]: NCLT-shape pair, 50k map x 10k scan pts, 384-d feats, mutual-NN + cos>=0.8 gate, "

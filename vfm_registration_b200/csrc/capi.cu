@@ -244,6 +244,13 @@ void vfmreg_destroy(vfmreg_ctx* ctx) {
     cudaEventDestroy(ctx->ev_join[l]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->match_stream_owned[i]) {
+      cudaStreamSynchronize(ctx->match_stream_owned[i]);
+      cudaStreamDestroy(ctx->match_stream_owned[i]);
+    }
+  for (int i = 0; i < vfmreg_ctx::MATCH_EVENTS; ++i)
+    if (ctx->match_ev[i]) cudaEventDestroy(ctx->match_ev[i]);
   for (int g = 0; g < NUM_GROUPS; ++g) {
     for (int r = 0; r < vfmreg_ctx::EV_RING; ++r) {
       cudaEventDestroy(ctx->ev0[g][r]);
@@ -414,8 +421,17 @@ static int register_impl(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt
   return VFMREG_OK;
 }
 
+// VFMREG_MATCH_STREAMS=0 keeps the candidate-search kernels on their lane's stream (A/B comparison)
+static bool g_match_streams = [] { const char* e = getenv("VFMREG_MATCH_STREAMS"); return !(e && e[0] == '0'); }();
+
 static int ensure_lanes(vfmreg_ctx* ctx, int lanes) {
   if (!ctx->ev_fork) VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  if (!ctx->match_stream_owned[0]) {
+    int lo = 0, hi = 0;
+    VFM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
+    for (int i = 0; i < 2; ++i) VFM_CUDA(cudaStreamCreateWithPriority(&ctx->match_stream_owned[i], cudaStreamNonBlocking, hi));
+    for (int i = 0; i < vfmreg_ctx::MATCH_EVENTS; ++i) VFM_CUDA(cudaEventCreateWithFlags(&ctx->match_ev[i], cudaEventDisableTiming));
+  }
   for (int l = 1; l < lanes; ++l) {
     if (ctx->lane_stream[l]) continue;
     VFM_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
@@ -429,7 +445,10 @@ struct StreamGuard {
   vfmreg_ctx* ctx;
   cudaStream_t saved;
   explicit StreamGuard(vfmreg_ctx* c) : ctx(c), saved(c->stream) {}
-  ~StreamGuard() { ctx->stream = saved; }
+  ~StreamGuard() {
+    ctx->stream = saved;
+    ctx->match_stream[0] = ctx->match_stream[1] = nullptr;
+  }
 };
 
 static int check_register_args(vfmreg_ctx* ctx, const void* a, const void* b, const void* c, const void* e, int64_t n,
@@ -630,6 +649,10 @@ int vfmreg_register_batch(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* 
       lane_streams[l] = ctx->lane_stream[l];
       VFM_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
     }
+    if (g_match_streams) {
+      ctx->match_stream[0] = ctx->match_stream_owned[0];
+      ctx->match_stream[1] = ctx->match_stream_owned[1];
+    }
   }
   for (int i = 0; i < n_pairs; ++i) {
     const int lane = i % lanes;
@@ -650,6 +673,7 @@ int vfmreg_register_batch(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* 
                              sample_idx ? sample_idx[i] : nullptr, out));
   }
   ctx->stream = guard.saved;
+  ctx->match_stream[0] = ctx->match_stream[1] = nullptr;   // every search was handed back to its lane by an event
   for (int l = 1; l < lanes; ++l) {
     VFM_CUDA(cudaEventRecord(ctx->ev_join[l], ctx->lane_stream[l]));
     VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));

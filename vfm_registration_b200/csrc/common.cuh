@@ -77,6 +77,12 @@ struct vfmreg_ctx {
   int lanes = 3;                                   // vfmreg_set_lanes
   cudaStream_t lane_stream[MAX_LANES] = {};        // [0] unused: lane 0 is the caller's stream
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {};
+  // batch mode: high-priority streams for the candidate-search kernels ([0] full, [1] pruned); null outside a batch
+  static constexpr int MATCH_EVENTS = 32;
+  cudaStream_t match_stream[2] = {};
+  cudaStream_t match_stream_owned[2] = {};
+  cudaEvent_t match_ev[MATCH_EVENTS] = {};
+  int match_ev_head = 0;
 };
 
 namespace vfm {

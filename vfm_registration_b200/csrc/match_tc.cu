@@ -1302,21 +1302,43 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
     attr_set = true;
   }
   const int grp = n_dev ? GROUP_MATCH_PRUNED : GROUP_MATCH;
+  // Batch mode (vfmreg_register_batch with several lanes): the candidate-search kernels of all lanes go to one of two
+  // high-priority streams -- full searches on [0], pruned reverse searches on [1] -- so that they run back to back in pair
+  // order and are scheduled ahead of the lanes' small kernels, which fill the SMs beside them.  The lane stream hands
+  // over with an event and takes the result back with another.
+  cudaStream_t lane = ctx->stream;
+  cudaStream_t ks = ctx->match_stream[n_dev ? 1 : 0];
+  if (ks) {
+    cudaEvent_t ev = ctx->match_ev[ctx->match_ev_head];
+    ctx->match_ev_head = (ctx->match_ev_head + 1) % vfmreg_ctx::MATCH_EVENTS;
+    VFM_CUDA(cudaEventRecord(ev, lane));
+    VFM_CUDA(cudaStreamWaitEvent(ks, ev, 0));
+    ctx->stream = ks;
+  }
   group_begin(ctx, grp);
+  int rc_launch = VFMREG_OK;
   if (plan.version == 3) {
     if (dp <= A_MAX_KB * TBK)
       match_tc3_kernel<true><<<plan.grid, TC_THREADS, S3_TOTAL, ctx->stream>>>(map_a, map_b, P);
     else
       match_tc3_kernel<false><<<plan.grid, TC_THREADS, S3_TOTAL, ctx->stream>>>(map_a, map_b, P);
-    VFM_TRY(launch_check(ctx, "match_tc3_kernel"));
+    rc_launch = launch_check(ctx, "match_tc3_kernel");
   } else if (plan.version == 2) {
     match_tc2_kernel<<<plan.grid, TC_THREADS, S2_TOTAL, ctx->stream>>>(map_a, map_b, P);
-    VFM_TRY(launch_check(ctx, "match_tc2_kernel"));
+    rc_launch = launch_check(ctx, "match_tc2_kernel");
   } else {
     match_tc_kernel<<<plan.grid, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(map_a, map_b, P);
-    VFM_TRY(launch_check(ctx, "match_tc_kernel"));
+    rc_launch = launch_check(ctx, "match_tc_kernel");
   }
   group_end(ctx, grp, 1);
+  if (ks) {
+    ctx->stream = lane;
+    cudaEvent_t ev = ctx->match_ev[ctx->match_ev_head];
+    ctx->match_ev_head = (ctx->match_ev_head + 1) % vfmreg_ctx::MATCH_EVENTS;
+    VFM_CUDA(cudaEventRecord(ev, ks));
+    VFM_CUDA(cudaStreamWaitEvent(lane, ev, 0));
+  }
+  VFM_TRY(rc_launch);
   const long long entries = (long long)n * plan.slots;
   const bool fold_pick = (sec == nullptr);   // only the best match is requested: the pick is folded into the re-score
   rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, n_dev, plan.slots, P.top1, nz_a, cand_v, cand_n, slot_top2,
