@@ -641,7 +641,8 @@ int vfmreg_register_batch(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* 
   }
   const size_t mark = ctx->arena.off;
   StreamGuard guard(ctx);
-  cudaStream_t lane_streams[vfmreg_ctx::MAX_LANES] = {ctx->stream, ctx->stream, ctx->stream, ctx->stream};
+  cudaStream_t lane_streams[vfmreg_ctx::MAX_LANES];
+  for (int l = 0; l < vfmreg_ctx::MAX_LANES; ++l) lane_streams[l] = ctx->stream;
   if (lanes > 1) {
     VFM_TRY(ensure_lanes(ctx, lanes));
     VFM_CUDA(cudaEventRecord(ctx->ev_fork, guard.saved));          // inputs are ready in the caller's stream order
