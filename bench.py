@@ -9,9 +9,11 @@ mutual nearest neighbour + cosine gate 0.8, 8192 RANSAC hypotheses (tau = 1 m). 
 over a batch of P distinct synthetic pairs (P x 92 MB of inputs > the 126 MB L2, so consecutive pairs evict each
 other); weak scaling: every rank owns its own P pairs and the per-pair 4x4 transforms are all-gathered once per step.
 
-  value  = pairs/s with the inputs already resident in HBM (vfmreg_register, device pointers)
+  value  = pairs/s with the inputs already resident in HBM (register_batch on CUDA tensors -> vfmreg_register_batch:
+           consecutive pairs on `--lanes` streams, the candidate-search kernels on two high-priority streams)
   e2e    = pairs/s through the public API (register_batch) with HOST (pinned) buffers, H2D + D2H inside the timed region
-  roofline = the dominant kernel (descriptor N x M match), timed with CUDA events on the launching stream
+  roofline = the dominant kernel (descriptor N x M candidate search, scan -> map), timed with CUDA events on the stream it
+             is launched on, inside the timed region (`frac`) and once more with nothing beside it (`alone`)
   cpu_baseline = oracle/c (the reference-style CPU restatement; the reference itself cannot be built offline) on the
                  box's host cores, bounded sample.  `--impl reference` times that same CPU path as the reference arm.
 """
