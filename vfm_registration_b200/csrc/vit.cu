@@ -20,9 +20,7 @@ namespace {
 struct Layer {
   float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ls1, *ln2_g, *ln2_b, *fc1_b, *fc2_b, *ls2;
   __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
-  CUtensorMap m_qkv, m_proj, m_fc1, m_fc2;
-  CUtensorMap m_proj_n, m_fc2_n;   // 128-row boxes of proj / fc2 for small batches
-  bool has_narrow = false;
+  WeightMaps m_qkv, m_proj, m_fc1, m_fc2;
 };
 
 }  // namespace
@@ -32,7 +30,7 @@ struct vfmreg_vit {
   vfmreg_vit_config cfg;
   int kp;  // padded patch-embedding K (3 * patch^2 -> multiple of 64)
   __nv_bfloat16* pe_w = nullptr;
-  CUtensorMap m_pe;
+  WeightMaps m_pe;
   float *pe_b = nullptr, *cls = nullptr, *norm_g = nullptr, *norm_b = nullptr, *cn_g = nullptr, *cn_b = nullptr;
   std::vector<Layer> layers;
   std::map<long long, float*> pos;  // (gh << 20 | gw) -> device (1 + gh*gw, W)
@@ -143,7 +141,7 @@ int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit*
   VFM_CHECK_ARG(cfg->depth > 0 && cfg->heads > 0 && cfg->width == cfg->heads * 64, "vit_create: width must be heads * 64");
   VFM_CHECK_ARG(cfg->width % 128 == 0 && cfg->width <= 1024 && cfg->mlp_dim % 64 == 0, "vit_create: unsupported width/mlp_dim");
   VFM_CHECK_ARG(vit_gemm_tile_n(cfg->width) && vit_gemm_tile_n(3 * cfg->width) && vit_gemm_tile_n(cfg->mlp_dim),
-                "vit_create: width, 3*width and mlp_dim must be multiples of 192 or 256");
+                "vit_create: width, 3*width and mlp_dim must be multiples of 128, 192 or 256");
   VFM_CHECK_ARG(cfg->patch > 0 && cfg->patch_h > 0, "vit_create: bad patch geometry");
   VFM_CUDA(cudaSetDevice(ctx->device));
   vfmreg_vit* v = new vfmreg_vit();
@@ -161,18 +159,13 @@ int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit*
     A(&l.ln2_g, w); A(&l.ln2_b, w); A(&l.fc1_b, md); A(&l.fc2_b, w); A(&l.ls2, w);
     A(&l.qkv_w, (size_t)3 * w * w); A(&l.proj_w, (size_t)w * w); A(&l.fc1_w, (size_t)md * w); A(&l.fc2_w, (size_t)w * md);
   }
-  if (rc == VFMREG_OK) rc = make_tmap_16bit(&v->m_pe, v->pe_w, w, v->kp, v->kp, vit_gemm_tile_n(w), true);
+  if (rc == VFMREG_OK) rc = vit_weight_maps(&v->m_pe, v->pe_w, w, v->kp);
   for (Layer& l : v->layers) {
     if (rc != VFMREG_OK) break;
-    rc = make_tmap_16bit(&l.m_qkv, l.qkv_w, 3 * w, w, w, vit_gemm_tile_n(3 * w), true);
-    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_proj, l.proj_w, w, w, w, vit_gemm_tile_n(w), true);
-    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc1, l.fc1_w, md, w, w, vit_gemm_tile_n(md), true);
-    if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc2, l.fc2_w, w, md, md, vit_gemm_tile_n(w), true);
-    if (rc == VFMREG_OK && w % 128 == 0) {
-      rc = make_tmap_16bit(&l.m_proj_n, l.proj_w, w, w, w, 128, true);
-      if (rc == VFMREG_OK) rc = make_tmap_16bit(&l.m_fc2_n, l.fc2_w, w, md, md, 128, true);
-      l.has_narrow = true;
-    }
+    rc = vit_weight_maps(&l.m_qkv, l.qkv_w, 3 * w, w);
+    if (rc == VFMREG_OK) rc = vit_weight_maps(&l.m_proj, l.proj_w, w, w);
+    if (rc == VFMREG_OK) rc = vit_weight_maps(&l.m_fc1, l.fc1_w, md, w);
+    if (rc == VFMREG_OK) rc = vit_weight_maps(&l.m_fc2, l.fc2_w, w, md);
   }
   if (rc != VFMREG_OK) {
     vfmreg_vit_destroy(v);
@@ -299,12 +292,12 @@ static int vit_enqueue(vfmreg_vit* v, const uint8_t* images, int b, int img_h, i
     VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS, v->m_xn, l.m_qkv, ep));
     VFM_TRY(vit_attention(ctx, v->qkv, b, t, v->cfg.heads, w, v->ao));
     ep = GemmEpilogue{rows, w, w, 0, w, l.proj_b, l.ls1, nullptr, v->x, nullptr};
-    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_ao, l.m_proj, ep, l.has_narrow ? &l.m_proj_n : nullptr));
+    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_ao, l.m_proj, ep));
     VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, l.ln2_g, l.ln2_b, v->cfg.ln_eps, v->xn));
     ep = GemmEpilogue{rows, md, w, 0, md, l.fc1_b, nullptr, nullptr, nullptr, v->hbuf};
     VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS_GELU, v->m_xn, l.m_fc1, ep));
     ep = GemmEpilogue{rows, w, md, 0, w, l.fc2_b, l.ls2, nullptr, v->x, nullptr};
-    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_h, l.m_fc2, ep, l.has_narrow ? &l.m_fc2_n : nullptr));
+    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_h, l.m_fc2, ep));
   }
   return vit_final_norm(ctx, v->x, b, t, w, v->norm_g, v->norm_b, v->cfg.ln_eps, v->cn_g, v->cn_b, v->cfg.cn_eps, v->cfg.channel_norm,
                         tokens);

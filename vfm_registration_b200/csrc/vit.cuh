@@ -20,9 +20,14 @@ struct GemmEpilogue {
   __nv_bfloat16* out_bf16;  // bf16 output (EPI_BF16_*)
 };
 
-// w_narrow (optional): the same weight with a 128-row TMA box, used by the residual GEMMs when the wide tiling under-fills the GPU
-int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep,
-             const CUtensorMap* w_narrow = nullptr);
+// One weight matrix (N x K, K-major bf16) with a TMA box per output-tile width it can be tiled by (256 / 192 / 128 rows).
+struct WeightMaps {
+  CUtensorMap map[3];    // [0] = 256-row box, [1] = 192, [2] = 128
+  bool ok[3] = {false, false, false};
+};
+int vit_weight_maps(WeightMaps* w, const void* ptr, int n, int k);
+// picks the tile width that needs the fewest (waves x tile time) for this M on this GPU
+int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const WeightMaps& w, const GemmEpilogue& ep);
 // output-tile width the GEMM uses for an N-column weight (256 or 192; 0 = unsupported): the weight's TMA box has that many rows
 int vit_gemm_tile_n(int n);
 

@@ -8,8 +8,9 @@
 //
 // Persistent kernel, one CTA per SM, static round-robin over 128 x BN output tiles (BN = 256 when N % 256 == 0, else 192:
 // every DINOv2 width is a multiple of one of them; wide N keeps the MMA off the shared-memory read limit, which a
-// 128-wide tile hits).  The residual GEMMs (N = width) fall back to BN = 128 when the wide tiling would leave more than a
-// quarter of the SMs without a tile (small batches: 6 images x 257 tokens = 13 row blocks x 4 column tiles = 52 CTAs).  Warp 0 = TMA producer (128B-swizzled 64-wide K chunks, 4-stage mbarrier ring), warp 1 = TMEM
+// 128-wide tile hits).  Every weight carries a TMA box per width it divides into (256 / 192 / 128), and each
+// launch picks the width with the fewest waves x tile time for its M: large batches use 256, BASELINE config 3 (6 images x
+// 257 tokens = 13 row blocks) uses 192 for QKV and 128 for proj / fc1 / fc2.  Warp 0 = TMA producer (128B-swizzled 64-wide K chunks, 4-stage mbarrier ring), warp 1 = TMEM
 // allocator + elected-lane tcgen05.mma issuer (kind::f16, bf16 operands, M128 N{192,256} K16), accumulators double-buffered in
 // TMEM (2 x 256 columns) so the epilogue of tile i (warps 2-5: tcgen05.ld 32x32b, one output row per thread) overlaps
 // the MMAs of tile i+1.  Bound: tensor pipe for the large layers; at BASELINE config 3 (6 images, 1542 tokens) most layers
@@ -210,18 +211,44 @@ static int launch_gemm(vfmreg_ctx* ctx, const CUtensorMap& a, const CUtensorMap&
   return launch_check(ctx, "vit_gemm_kernel");
 }
 
-int vit_gemm_tile_n(int n) { return (n % 256 == 0) ? 256 : ((n % 192 == 0) ? 192 : 0); }
+int vit_gemm_tile_n(int n) { return (n % 256 == 0) ? 256 : ((n % 192 == 0) ? 192 : ((n % 128 == 0) ? 128 : 0)); }
 
-int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep, const CUtensorMap* w_narrow) {
-  const int bn = vit_gemm_tile_n(ep.n);
-  VFM_CHECK_ARG(ep.k % GBK == 0 && bn != 0 && ep.m > 0, "vit_gemm: unsupported shape m=%d n=%d k=%d", ep.m, ep.n, ep.k);
-  // tuning aid: VFMREG_VIT_NARROW=0 keeps the wide tiles (ViT-L/14, 6 images: 4.09 ms wide, 3.71 ms narrow on the same box)
-  static const bool narrow_ok = [] { const char* e = getenv("VFMREG_VIT_NARROW"); return !(e && e[0] == '0'); }();
-  if (narrow_ok && w_narrow && epi == EPI_F32_RESID && ep.n % 128 == 0 && ceil_div(ep.m, GBM) * (ep.n / bn) * 4 < ctx->sm_count * 3)
-    return launch_gemm<EPI_F32_RESID, 128>(ctx, a, *w_narrow, ep);
-#define VFM_GEMM_CASE(E)                                                   \
-  case E:                                                                  \
-    return bn == 256 ? launch_gemm<E, 256>(ctx, a, w, ep) : launch_gemm<E, 192>(ctx, a, w, ep);
+int vit_weight_maps(WeightMaps* w, const void* ptr, int n, int k) {
+  const int widths[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    w->ok[i] = (n % widths[i] == 0);
+    if (w->ok[i]) VFM_TRY(make_tmap_16bit(&w->map[i], ptr, n, k, k, widths[i], true));
+  }
+  return VFMREG_OK;
+}
+
+int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const WeightMaps& w, const GemmEpilogue& ep) {
+  VFM_CHECK_ARG(ep.k % GBK == 0 && ep.m > 0 && (w.ok[0] || w.ok[1] || w.ok[2]), "vit_gemm: unsupported shape m=%d n=%d k=%d", ep.m,
+                ep.n, ep.k);
+  // Tile width: the persistent CTAs take ceil(tiles / SMs) tiles each; a tile's MMA time is proportional to its width,
+  // except that 128-wide tiles run into the shared-memory operand limit (x 1.25).  Small batches (6 images = 13 row blocks)
+  // pick narrower tiles than the 256 that large batches use.  VFMREG_VIT_TILE=256|192|128 forces a width (tuning aid).
+  static const int forced = [] { const char* e = getenv("VFMREG_VIT_TILE"); return e ? atoi(e) : 0; }();
+  const int widths[3] = {256, 192, 128}, cost[3] = {256, 192, 160};
+  int best = -1;
+  long long best_cost = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (!w.ok[i]) continue;
+    const long long tiles = (long long)ceil_div(ep.m, GBM) * (ep.n / widths[i]);
+    const long long c = ((tiles + ctx->sm_count - 1) / ctx->sm_count) * cost[i];
+    if (forced == widths[i]) {
+      best = i;
+      break;
+    }
+    if (best < 0 || c < best_cost) {
+      best = i;
+      best_cost = c;
+    }
+  }
+#define VFM_GEMM_CASE(E)                                                                              \
+  case E:                                                                                             \
+    return best == 0 ? launch_gemm<E, 256>(ctx, a, w.map[0], ep)                                      \
+                     : (best == 1 ? launch_gemm<E, 192>(ctx, a, w.map[1], ep) : launch_gemm<E, 128>(ctx, a, w.map[2], ep));
   switch (epi) {
     VFM_GEMM_CASE(EPI_BF16_BIAS)
     VFM_GEMM_CASE(EPI_BF16_BIAS_GELU)
