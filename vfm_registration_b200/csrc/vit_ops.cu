@@ -3,7 +3,7 @@
 //   preprocess_kernel   ToTensor -> bilinear Resize(antialias=False, align_corners=False) -> Normalize, written straight
 //                       into the im2col patch matrix in bf16 (the resized image is never materialised); HBM-bound.
 //   layernorm kernels   one warp per token, 128-bit loads, two-pass statistics in registers; HBM-bound.
-//   attention_kernel    softmax(Q K^T / sqrt(64)) V, one CTA per (image, head): K/V of the head staged once in shared
+//   attention_kernel    softmax(Q K^T / sqrt(64)) V, one CTA per (image, head, query split): K/V of the head staged in shared
 //                       memory, 8 warps walk 16-query tiles with a flash-style online softmax over 64-key chunks, bf16
 //                       mma.sync m16n8k16 with fp32 accumulation.  (~4 % of the model's FLOPs; the GEMMs that carry
 //                       the rest run on tcgen05.)
@@ -204,8 +204,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 constexpr int ATT_WARPS = 8;
 
-// One CTA per (image, head): K and V of the head are staged in shared memory ONCE, then each of the 8 warps walks
-// 16-query tiles (tile = warp, warp + 8, ...) with a flash-style online softmax over 64-key chunks.
+// One CTA per (image, head, query split): K and V of the head are staged in shared memory once per CTA, then each of the
+// 8 warps walks the split's 16-query tiles (tile = first + warp, first + warp + 8, ...) with a flash-style online softmax
+// over 64-key chunks.  gridDim.z query splits keep small batches from leaving SMs idle (6 images x 16 heads = 96 CTAs).
 __global__ void __launch_bounds__(ATT_WARPS * 32)
     attention_kernel(const __nv_bfloat16* __restrict__ qkv, int t, int width, int tp, __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -232,7 +233,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
   const int g = lane >> 2, tq = lane & 3;
   const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   __nv_bfloat16* ob = out + (long long)img * t * width + head * ATT_DH;
-  for (int q0 = warp * 16; q0 < t; q0 += ATT_WARPS * 16) {
+  const int n_tiles = (t + 15) / 16, per_split = (n_tiles + gridDim.z - 1) / gridDim.z;
+  const int q_begin = blockIdx.z * per_split * 16, q_end = min(t, (int)(blockIdx.z + 1) * per_split * 16);
+  for (int q0 = q_begin + warp * 16; q0 < q_end; q0 += ATT_WARPS * 16) {
     __syncwarp();
     for (int i = lane; i < 16 * 8; i += 32) {
       const int r = i >> 3, ch = i & 7;
@@ -348,7 +351,12 @@ int vit_attention(vfmreg_ctx* ctx, const __nv_bfloat16* qkv, int b, int t, int h
     VFM_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  attention_kernel<<<dim3(heads, b), ATT_WARPS * 32, smem, ctx->stream>>>(qkv, t, width, tp, out);
+  // query splits: enough CTAs for two per SM, at least one round of 8 query tiles each
+  const int n_tiles = (t + 15) / 16;
+  int splits = ceil_div(2 * ctx->sm_count, heads * b);
+  const int max_splits = (n_tiles + ATT_WARPS - 1) / ATT_WARPS;
+  splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
+  attention_kernel<<<dim3(heads, b, splits), ATT_WARPS * 32, smem, ctx->stream>>>(qkv, t, width, tp, out);
   return launch_check(ctx, "attention_kernel");
 }
 
