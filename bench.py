@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-step", type=int, default=8)
+    ap.add_argument("--pairs-per-step", type=int, default=16)
     ap.add_argument("--lanes", type=int, default=0, help="compute lanes of register_batch (0 = library default)")
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
