@@ -680,7 +680,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 // Barriers: `full` / `afull` / `tempty` live in the leader (both CTAs' TMA loads credit the leader's barriers through
 // .cta_group::2 loads; the peer's epilogue warps arrive remotely); `empty` / `aempty` / `tfull` exist in both CTAs and are
 // signalled by multicast tcgen05.commit.
-constexpr int STAGES3 = 5;
+constexpr int STAGES3 = 6;
 constexpr uint32_t S3_A = 0;                                   // RESIDENT: dp/64 chunks; streaming: STAGES3 chunks
 constexpr uint32_t S3_B = A_MAX_KB * A_STAGE_BYTES;            // STAGES3 x (128 database rows x 64 k) = 16 KB each
 constexpr uint32_t S3_RING_V = S3_B + STAGES3 * B_HALF_BYTES;
@@ -744,8 +744,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     uint32_t stage = 0, phase = 0, aphase = 0;
     int cur_rp = -1;
     const uint32_t afull_leader = mapa_cluster(afull, 0);
+    const bool dbg = P.dbg != nullptr;   // pipeline counters only when asked for (VFMREG_TC_DEBUG=1)
     long long w_empty = 0;
-    const long long p_start = clock64();
+    const long long p_start = dbg ? clock64() : 0;
     for (long long u = u_begin; u < u_end; ++u) {
       const int rp = (int)(u / P.col_tiles), ct = (int)(u % P.col_tiles);
       if (RESIDENT && rp != cur_rp) {
@@ -761,9 +762,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
 #pragma unroll 1
       for (int kb = 0; kb < P.kb; ++kb) {
-        const long long c0 = clock64();
+        const long long c0 = dbg ? clock64() : 0;
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        w_empty += clock64() - c0;
+        if (dbg) w_empty += clock64() - c0;
         if (elect_one()) {
           const uint32_t full_leader = mapa_cluster(full0 + 8 * stage, 0);
           if (rank == 0) mbar_expect_tx(full0 + 8 * stage, RESIDENT ? 2u * B_HALF_BYTES : 2u * (B_HALF_BYTES + A_STAGE_BYTES));
@@ -774,7 +775,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         if (++stage == STAGES3) { stage = 0; phase ^= 1; }
       }
     }
-    if (P.dbg && lane == 0) {
+    if (dbg && lane == 0) {
       P.dbg[blockIdx.x * 8 + 6] = w_empty;
       P.dbg[blockIdx.x * 8 + 7] = clock64() - p_start;
     }
@@ -785,14 +786,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       long long it = 0;
       int cur_rp = -1;
       const uint64_t da0 = umma_desc_k_sw128(sA), db0 = umma_desc_k_sw128(sB);
+      const bool dbg = P.dbg != nullptr;
       long long w_tempty = 0, w_full = 0;
-      const long long t_start = clock64();
+      const long long t_start = dbg ? clock64() : 0;
       for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int rp = (int)(u / P.col_tiles);
         const uint32_t buf = (uint32_t)(it % NBUF);
-        long long c0 = clock64();
+        long long c0 = dbg ? clock64() : 0;
         mbar_wait(tempty0 + 8 * buf, (uint32_t)((it / NBUF) & 1) ^ 1);
-        w_tempty += clock64() - c0;
+        if (dbg) w_tempty += clock64() - c0;
         if (RESIDENT && rp != cur_rp) {
           cur_rp = rp;
           mbar_wait(afull, aphase);
@@ -803,9 +805,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         const bool last_of_rp = (u + 1 == u_end) || ((int)((u + 1) / P.col_tiles) != rp);
 #pragma unroll 1
         for (int kb = 0; kb < P.kb; ++kb) {
-          c0 = clock64();
+          if (dbg) c0 = clock64();
           mbar_wait(full0 + 8 * stage, phase);
-          w_full += clock64() - c0;
+          if (dbg) w_full += clock64() - c0;
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = da0 + (uint64_t)((RESIDENT ? kb : (int)stage) * (A_STAGE_BYTES >> 4));
@@ -823,7 +825,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (++stage == STAGES3) { stage = 0; phase ^= 1; }
         }
       }
-      if (P.dbg && lane == 0) {
+      if (dbg && lane == 0) {
         P.dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
         P.dbg[blockIdx.x * 8 + 1] = w_tempty;
         P.dbg[blockIdx.x * 8 + 2] = w_full;
@@ -840,8 +842,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     int cnt = 0;
     bool ovf = false, active = false;
     long long it = 0;
+    const bool dbg = P.dbg != nullptr;
     long long w_tfull = 0;
-    const long long e_start = clock64();
+    const long long e_start = dbg ? clock64() : 0;
     for (long long u = u_begin; u < u_end; ++u, ++it) {
       const int rp = (int)(u / P.col_tiles), ct = (int)(u % P.col_tiles);
       const int rb = 2 * rp + (int)rank;
@@ -856,9 +859,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         ovf = false;
       }
       const uint32_t buf = (uint32_t)(it % NBUF);
-      const long long c0 = clock64();
+      const long long c0 = dbg ? clock64() : 0;
       mbar_wait(tfull0 + 8 * buf, (uint32_t)((it / NBUF) & 1));
-      w_tfull += clock64() - c0;
+      if (dbg) w_tfull += clock64() - c0;
       tc_fence_after();
       epilogue_tile(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * COLS_PER_WARP, ct * TBN + half * COLS_PER_WARP,
                     P.m, etid, ring_v, ring_i, best, second, thr, cnt, ovf, P.experiment);
@@ -866,7 +869,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(tempty0 + 8 * buf, 0));
     }
-    if (P.dbg && warp == 2 && lane == 0) {
+    if (dbg && warp == 2 && lane == 0) {
       P.dbg[blockIdx.x * 8 + 4] = clock64() - e_start;
       P.dbg[blockIdx.x * 8 + 5] = w_tfull;
     }

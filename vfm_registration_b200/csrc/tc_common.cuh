@@ -121,9 +121,12 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t ct
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
   return r;
 }
-// arrive on a barrier that may live in the peer CTA (address from mapa_cluster)
+// arrive on a barrier that may live in the peer CTA (address from mapa_cluster).  Default semantics (release at CTA scope),
+// as CUTLASS' ClusterBarrier::arrive: what the barrier orders here is TMEM reads, which tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync already cover.  (`.release.cluster` compiled to MEMBAR.ALL.GPU + ERRBAR per arrive and
+// cost the epilogue warps a fifth of their time -- ncu source page, profiles/r1_kernel_bench.txt.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load into this CTA's shared memory whose completion bytes are credited to a barrier in the leader CTA
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
