@@ -1240,7 +1240,7 @@ size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic) {
   if (p1.slots > p.slots) p.slots = p1.slots;
   return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
          arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + arena_bytes((size_t)n * p.slots * CAP + 1, 4) +
-         arena_bytes((size_t)n, 8) + arena_bytes((size_t)n, 1) + 1024;
+         arena_bytes((size_t)n, 8) + arena_bytes((size_t)n, 1) + 2048;
 }
 
 // a32/b32: renormalised fp32 rows (n x dp), a16/b16: their fp16 copies, nz_a: non-zero flags of the query rows.
@@ -1252,21 +1252,23 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   const TcPlan plan = tc_plan(ctx, n, m, dp, n_dev != nullptr);
   float* cand_v = arena_take<float>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_i = arena_take<int>(ctx, (size_t)n * plan.slots * CAP);
-  int* cand_n = arena_take<int>(ctx, (size_t)n * plan.slots);
   float2* slot_top2 = arena_take<float2>(ctx, (size_t)n * plan.slots);
-  int* redo = arena_take<int>(ctx, (size_t)n + 1);  // [0] = count, [1..] = rows
-  int* work = arena_take<int>(ctx, (size_t)n * plan.slots * CAP + 1);  // [0] = count, [1..] = candidate entries to re-score
-  unsigned long long* row_key = arena_take<unsigned long long>(ctx, (size_t)n);   // top-1 mode: packed (score, index) maximum
-  uint8_t* row_overflow = arena_take<uint8_t>(ctx, (size_t)n);
-  if (!cand_v || !cand_i || !cand_n || !slot_top2 || !redo || !work || !row_key || !row_overflow) {
+  int* redo_list = arena_take<int>(ctx, (size_t)n);                             // rows for exact_rows_kernel
+  int* work_list = arena_take<int>(ctx, (size_t)n * plan.slots * CAP);          // candidate entries to re-score
+  // everything that starts at zero sits in one block: [redo count, work count | row_key | row_overflow | cand_n], one memset
+  const size_t z_key = 256, z_ovf = z_key + arena_bytes((size_t)n, 8), z_cn = z_ovf + arena_bytes((size_t)n, 1);
+  const size_t z_bytes = z_cn + arena_bytes((size_t)n * plan.slots, 4);
+  char* zero = arena_take<char>(ctx, z_bytes);
+  if (!cand_v || !cand_i || !slot_top2 || !redo_list || !work_list || !zero) {
     set_error("match_tc: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
-  VFM_CUDA(cudaMemsetAsync(cand_n, 0, sizeof(int) * (size_t)n * plan.slots, ctx->stream));
-  VFM_CUDA(cudaMemsetAsync(redo, 0, sizeof(int), ctx->stream));
-  VFM_CUDA(cudaMemsetAsync(work, 0, sizeof(int), ctx->stream));
-  VFM_CUDA(cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)n, ctx->stream));
-  VFM_CUDA(cudaMemsetAsync(row_overflow, 0, (size_t)n, ctx->stream));
+  int* redo_count = reinterpret_cast<int*>(zero);
+  int* work_count = redo_count + 1;
+  unsigned long long* row_key = reinterpret_cast<unsigned long long*>(zero + z_key);   // top-1 mode: packed (score, index) maximum
+  uint8_t* row_overflow = reinterpret_cast<uint8_t*>(zero + z_ovf);
+  int* cand_n = reinterpret_cast<int*>(zero + z_cn);
+  VFM_CUDA(cudaMemsetAsync(zero, 0, z_bytes, ctx->stream));
   CUtensorMap map_a, map_b;
   VFM_TRY(make_map_f16(&map_a, a16, n, dp, TBM));
   VFM_TRY(make_map_f16(&map_b, b16, m, dp, plan.paired ? TBN / 2 : TBN));
@@ -1345,24 +1347,24 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
   const long long entries = (long long)n * plan.slots;
   const bool fold_pick = (sec == nullptr);   // only the best match is requested: the pick is folded into the re-score
   rerank_select_kernel<<<ceil_div(entries, 128), 128, 0, ctx->stream>>>((int)n, n_dev, plan.slots, P.top1, nz_a, cand_v, cand_n, slot_top2,
-                                                                       work + 1, work, row_overflow);
+                                                                       work_list, work_count, row_overflow);
   VFM_TRY(launch_check(ctx, "rerank_select_kernel"));
   if (dp <= 512)
-    rerank_dot_kernel<8><<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work + 1, work,
+    rerank_dot_kernel<8><<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work_list, work_count,
                                                                       fold_pick ? row_key : nullptr);
   else
-    rerank_dot_kernel<16><<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work + 1, work,
+    rerank_dot_kernel<16><<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(a32, b32, dp, plan.slots, cand_v, cand_i, work_list, work_count,
                                                                       fold_pick ? row_key : nullptr);
   VFM_TRY(launch_check(ctx, "rerank_dot_kernel"));
   if (fold_pick) {
-    rerank_finish_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>((int)n, n_dev, nz_a, row_key, row_overflow, idx, best, redo + 1, redo);
+    rerank_finish_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>((int)n, n_dev, nz_a, row_key, row_overflow, idx, best, redo_list, redo_count);
     VFM_TRY(launch_check(ctx, "rerank_finish_kernel"));
   } else {
     rerank_pick_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>((int)n, n_dev, (int)m, plan.slots, nz_a, cand_v, cand_i, cand_n, idx, best, sec,
-                                                                 redo + 1, redo);
+                                                                 redo_list, redo_count);
     VFM_TRY(launch_check(ctx, "rerank_pick_kernel"));
   }
-  exact_rows_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(a32, b32, (int)m, dp, redo + 1, redo, idx, best, sec);
+  exact_rows_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(a32, b32, (int)m, dp, redo_list, redo_count, idx, best, sec);
   VFM_TRY(launch_check(ctx, "exact_rows_kernel"));
   if (want_dbg) {
     static long long host[2048 * 8];
