@@ -188,8 +188,8 @@ def main():
     import vfm_registration_b200 as v
     from vfm_registration_b200 import synth
     ctx = v.get_context(local_rank)
-    if args.lanes:
-        ctx.set_lanes(args.lanes)
+    lanes = args.lanes or 5   # the library default
+    ctx.set_lanes(lanes)
     P = args.pairs_per_step
     peaks = load_peaks()
 
@@ -251,7 +251,7 @@ def main():
     timed(dev_pairs, 2, 1)
     alone_ms, alone_launches = ctx.group_time_ms(0)
     ctx.enable_timing(False)
-    ctx.set_lanes(args.lanes or 3)
+    ctx.set_lanes(lanes)
     ms_e2e, _, res_e2e = timed(pin_pairs, max(2, args.steps // 2), 2, host=True)
     e2e_steps = max(2, args.steps // 2)
     clocks = sampler.stop() if rank == 0 else None   # sampled over the device-resident and the host-buffer timed regions
@@ -305,7 +305,7 @@ def main():
             "dtype": "f32 match / f64 solve", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "parallelism": f"pairs sharded over {world} rank(s)",
                        "l2": f"{P} distinct pairs x 92 MB cycled per step (> 126 MB L2)", "algo": args.algo,
-                       "lanes": args.lanes or 3, "host_affinity": numa},
+                       "lanes": lanes, "host_affinity": numa},
             "hyps_per_sec": value * N_HYP, "recall_at_1m_5deg": recall,
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -66,7 +66,7 @@ class Context:
         _lib.check(self.lib.vfmreg_enable_timing(self.handle, int(on)))
 
     def set_lanes(self, lanes: int):
-        """Number of CUDA streams ``register_batch`` spreads consecutive (device-resident) pairs over (1..8, default 3)."""
+        """Number of CUDA streams ``register_batch`` spreads consecutive (device-resident) pairs over (1..8, default 5)."""
         _lib.check(self.lib.vfmreg_set_lanes(self.handle, int(lanes)), "vfmreg_set_lanes")
 
     def group_time_ms(self, group: int):

@@ -74,7 +74,7 @@ struct vfmreg_ctx {
   // batch entry points: a second compute lane.  Consecutive pairs alternate between the caller's stream and this one, so
   // the latency-bound small kernels of one pair (filters, re-rank, RANSAC) run beside the other pair's match kernel.
   static constexpr int MAX_LANES = 8;
-  int lanes = 3;                                   // vfmreg_set_lanes
+  int lanes = 5;                                   // vfmreg_set_lanes
   cudaStream_t lane_stream[MAX_LANES] = {};        // [0] unused: lane 0 is the caller's stream
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {};
   // batch mode: high-priority streams for the candidate-search kernels ([0] full, [1] pruned); null outside a batch
