@@ -4,18 +4,25 @@
 // Reference: faiss IndexFlatIP::search(k=1) at VoxelHashMap.cpp:486-495 (+ runner-up for the ratio test).
 //
 // Two phases
-//  1. match_tc_kernel -- fp16 x fp16 -> fp32 GEMM of the renormalised descriptors, S~ = A~ B~^T, never written to memory.
-//     Persistent CTAs (one per SM) walk a contiguous span of (128-row block, 256-column tile) pairs in row-block-major
-//     order.  Warp roles: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring of
-//     64-wide K chunks), warp 1 = MMA issuer (one elected lane, tcgen05.mma kind::f16 M128 N256 K16, accumulators
-//     double-buffered in TMEM: 2 x 256 columns), warps 2-5 = epilogue (tcgen05.ld 32x32b: one query row per thread).
-//     Each epilogue thread keeps the running approximate top-2 of its row and records every column whose approximate
-//     score is within `margin` of the running runner-up in a small shared-memory list (compacted when full); the
-//     lists are flushed per (row block, CTA) "slot".
-//  2. rerank_kernel -- for every query: gather the candidates of its slots, drop those below (approx runner-up - margin),
-//     recompute the survivors in the canonical fp32 order (fmaf chain over k ascending, from the fp32 rows) and take
-//     the top-2 with lowest-index tie-break.  Rows whose list overflowed (pathological ties) are redone by
-//     exact_rows_kernel, an exact scan of all columns.
+//  1. candidate search -- fp16 x fp16 -> fp32 GEMM of the renormalised descriptors, S~ = A~ B~^T, never written to memory.
+//     Three kernels share the epilogue:
+//       match_tc3_kernel (default)  CTA pairs, ONE tcgen05.mma.cta_group::2 (M256 N256 K16) per step drives both SMs; each
+//                                   CTA holds its 128 query rows (resident for D <= 384) and half of the 256-column tile
+//       match_tc2_kernel            CTA pairs, two independent M128 MMAs fed by TMA multicast (A/B runs: VFMREG_MATCH_V2=1)
+//       match_tc_kernel             single CTAs, both operands streamed (fewer than two row blocks; VFMREG_MATCH_V1=1)
+//     Persistent CTAs walk contiguous spans of (row block, 256-column tile) units in row-major order.  Warp roles: warp 0 =
+//     TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier ring of 64-wide K chunks), warp 1 = TMEM allocator + MMA
+//     issuer (one elected lane, accumulators double-buffered in TMEM: 2 x 256 columns), warps 2-5 = epilogue (tcgen05.ld
+//     32x32b: one query row per thread).  Each epilogue thread keeps the running approximate best (and runner-up when the
+//     caller needs it) of its row and records every column whose approximate score is within `margin` of it in a small
+//     shared-memory list (compacted when full); the lists are flushed per (row block, span) "slot".  The row count may
+//     live on the device (TcParams.n_dev: the pruned reverse search of register()'s mutual check), and rows may start
+//     from a known lower bound of their best score (TcParams.seed).
+//  2. re-rank -- rerank_select: drop the candidates below (approx best / runner-up - margin) and list the survivors;
+//     rerank_dot: recompute them in the canonical fp32 order (fmaf chain over k ascending, from the fp32 rows; 16 lanes
+//     per candidate hand the accumulator on by shuffle); top-1 mode folds the per-row pick into a packed atomic max
+//     (rerank_finish), top-2 mode picks per row (rerank_pick), lowest index on ties.  Rows whose list overflowed
+//     (pathological ties) are redone by exact_rows_kernel, an exact scan of all columns.
 //
 // Why the result is exact: |S~ - S| <= eps with eps bounded below; the exact best and runner-up of a span both have
 // S~ >= (final approx runner-up of that span) - 2 eps, the recording threshold only ever rises, so both are always in
@@ -23,8 +30,7 @@
 // + fp16 subnormal inputs (< 5e-5) + tensor-core fp32 accumulation (< D 2^-23) + canonical fp32 chain (< D 2^-24)
 // < 1.2e-3 for D <= 1024; MARGIN = 3e-3.  Only valid for renormalised inputs, which is what the caller guarantees.
 //
-// Bound: tensor pipe (2 N M D flop per launch).  L2->SM operand traffic of this first version is (128+256) x 128 B per
-// 64-wide K chunk per tile (both operands streamed).
+// Bound: tensor pipe (2 N M D flop per launch); measured 0.80-0.83 of the cuBLAS bf16 rate on 10k x 50k x 384.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
