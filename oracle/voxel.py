@@ -187,3 +187,23 @@ def register_frame_vfm(frame_xyz: np.ndarray, vmap: VoxelHashMapOracle, vfm_src_
         T, i2 = register_frame(frame_xyz, vmap, T1, max_dist, kernel, max_iterations - j, return_info=True)
         info["iterations"] = i2["iterations"]
     return (T, info) if return_info else T
+
+
+def build_local_map(map_poses, map_point_clouds, voxel_size: float = 0.25, feat_dim: int = 384, split_above: int = 1_000_000) -> np.ndarray:
+    """registration_node.py:557-581 with the oracle's voxel_down_sample (rows in input order)."""
+    frames = []
+    for pose, pcl in zip(map_poses, map_point_clouds):
+        pcl = np.asarray(pcl)
+        pcl = pcl[np.sum(pcl[:, 3:], axis=1) > 0]
+        pcl = voxel_down_sample(pcl, voxel_size).astype(pcl.dtype) if len(pcl) else pcl
+        pose = np.asarray(pose, dtype=np.float64)
+        xyz = pcl[:, :3].astype(np.float64) @ pose[:3, :3].T + pose[:3, 3]      # vfm_reg/utils.py:47-54
+        frames.append(np.c_[xyz, pcl[:, 3:]].astype(pcl.dtype))
+    local = np.concatenate(frames, axis=0).astype(np.float32)
+    if local.shape[0] > split_above:
+        mean_x = np.mean(local[:, :3], axis=0)[0]
+        local = np.concatenate([voxel_down_sample(local[local[:, 0] > mean_x], voxel_size),
+                                voxel_down_sample(local[local[:, 0] <= mean_x], voxel_size)], axis=0)
+    else:
+        local = voxel_down_sample(local, voxel_size)
+    return local[:, :3 + feat_dim]

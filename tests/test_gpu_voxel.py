@@ -217,3 +217,31 @@ def test_compat_register_frame_with_descriptors(vfm):
     rte, rre = synth.pose_errors(pose, s["T_gt"])
     assert rte < 0.05 and rre < 0.1
     assert np.array_equal(compat.register_frame(scan_arr, compat.VoxelHashMap(1.0, 100.0, 20), guess, 6.0, 0.5), guess)
+
+
+def test_build_local_map_and_prepare_scan_vs_oracle(vfm):
+    """registration_node.py:557-590 (local map accumulation, scan thinning) through scenes.py against the oracle chain;
+    both return rows in input order, so the arrays are equal element for element."""
+    from vfm_registration_b200 import scenes
+    rng = np.random.default_rng(12)
+    poses, clouds = [], []
+    for i in range(4):
+        a = 0.2 * i
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+        T[:3, 3] = [1.5 * i, -0.7 * i, 0.05 * i]
+        pts = _cloud(60 + i, 6000, span=8.0, dtype=np.float32)
+        feat = np.abs(rng.standard_normal((6000, 16))).astype(np.float32)
+        feat[rng.random(6000) < 0.3] = 0                       # points no camera saw: dropped before the thinning
+        feat[5] = [1.0] + [-1.0] + [0.0] * 14                  # sum == 0 but non-zero: dropped by the reference's sum test
+        poses.append(T)
+        clouds.append(np.c_[pts, feat])
+    got = scenes.build_local_map(poses, clouds, voxel_size=0.25, feat_dim=16)
+    want = ov.build_local_map(poses, clouds, voxel_size=0.25, feat_dim=16)
+    assert got.dtype == np.float32 and got.shape == want.shape and np.array_equal(got, want) and 5000 < len(got) < 17000
+    split = scenes.build_local_map(poses, clouds, voxel_size=0.25, feat_dim=16, split_above=1000)
+    assert np.array_equal(split, ov.build_local_map(poses, clouds, voxel_size=0.25, feat_dim=16, split_above=1000))
+    by_norm = scenes.build_local_map(poses, clouds, voxel_size=0.25, feat_dim=16, has_descriptor="norm")
+    assert len(by_norm) >= len(got)
+    scan = clouds[0][:, :3]
+    assert np.array_equal(scenes.prepare_scan(scan, 0.1), ov.voxel_down_sample(scan, 0.1))

@@ -31,3 +31,25 @@ def test_synth_pair_is_consistent():
     cos = (s["scan_feat"][inl] * s["map_feat"][s["perm"][inl]]).sum(1)
     assert 0.85 < cos.mean() < 0.95 and cos.min() > 0.8
     assert synth.pose_errors(s["T_gt"], s["T_gt"]) == (0.0, 0.0)
+
+
+def test_scene_json_reader():
+    """scene_*.json layout (mapping / registration lists) as the reference's prepare_scenes.py:122-131 reads it; the fixture is
+    synthetic with the reference files' keys and path shapes."""
+    import os
+    from vfm_registration_b200 import scenes
+    spec = scenes.read_scene_json(os.path.join(os.path.dirname(__file__), "golden", "scene_synthetic.json"))
+    assert len(spec.map_point_clouds) == 3 and spec.map_poses.shape == (3, 4, 4) and len(spec.map_images[0]) == 5
+    assert len(spec.scan_point_clouds) == 2 and spec.scan_poses.shape == (2, 4, 4)
+    assert np.allclose(spec.map_poses[:, 3], [0, 0, 0, 1]) and spec.scan_point_clouds[0].endswith("2000.bin")
+
+
+def test_scene_json_reader_on_reference_file_if_present():
+    import os
+    import pytest
+    from vfm_registration_b200 import scenes
+    ref = "/root/reference/data/nclt/scene_000.json"
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not mounted")
+    spec = scenes.read_scene_json(ref)
+    assert len(spec.map_point_clouds) == spec.map_poses.shape[0] == 168 and spec.scan_poses.shape == (5, 4, 4)
