@@ -245,3 +245,22 @@ def test_build_local_map_and_prepare_scan_vs_oracle(vfm):
     assert len(by_norm) >= len(got)
     scan = clouds[0][:, :3]
     assert np.array_equal(scenes.prepare_scan(scan, 0.1), ov.voxel_down_sample(scan, 0.1))
+
+
+def test_compat_icp_registration(vfm):
+    """RegistrationNode.icp_registration (registration_node.py:358-394) for (N, 3) clouds against the oracle chain."""
+    from vfm_registration_b200 import compat, synth
+    s = synth.make_pair(41, 9000, 4000, 8, inlier_frac=0.8)
+    guess = s["T_gt"].copy()
+    guess[:3, 3] += [0.3, -0.2, 0.02]
+    node = compat.RegistrationNode()
+    pose = node.icp_registration(s["map_xyz"], s["scan_xyz"], guess)
+    om = ov.VoxelHashMapOracle(1.0, 20)
+    om.add_points(s["map_xyz"])
+    vs = ov.voxel_down_sample(ov.voxel_down_sample(s["scan_xyz"], 0.5), 1.0)
+    want = ov.register_frame(vs.astype(np.float64), om, guess, 6.0, 2.0 / 3.0)
+    assert np.abs(pose - want).max() < 1e-9
+    rte, rre = synth.pose_errors(pose, s["T_gt"])
+    assert rte < 0.05 and rre < 0.1
+    with pytest.raises(ValueError, match="Invalid shape"):
+        node.icp_registration(s["map_xyz"], s["scan_xyz"][:, :2])

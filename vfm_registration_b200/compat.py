@@ -208,6 +208,20 @@ class RegistrationNode:
         pose = register_frame(scan_xyz, icp_map, ransac_pose, 3 * sigma, sigma / 3)  # :337-341
         return ransac_pose, pose
 
+    def icp_registration(self, voxel_map: np.ndarray, raw_scan: np.ndarray, initial_pose=None, dist: float = 3):
+        """registration_node.py:358-394: double-down-sample the scan, thin the map into a voxel hash map, ICP from
+        ``initial_pose`` with max correspondence distance ``dist * sigma`` and kernel ``sigma / dist``.  (N, 3) clouds run the
+        point-to-point loop, descriptor-carrying clouds the VFM-ICP overload -- as ``register_frame`` dispatches."""
+        voxel_map, raw_scan = np.asarray(voxel_map), np.asarray(raw_scan)
+        if voxel_map.ndim != 2 or raw_scan.ndim != 2 or raw_scan.shape[1] < 3 or voxel_map.shape[1] != raw_scan.shape[1]:
+            raise ValueError("Invalid shape")
+        voxel_scan = self._voxel_scan(raw_scan)
+        vmap = self._new_map()
+        vmap.add_points(voxel_map)
+        sigma = self.initial_threshold
+        pose0 = np.eye(4) if initial_pose is None else np.asarray(initial_pose, dtype=np.float64)
+        return register_frame(voxel_scan, vmap, pose0, dist * sigma, sigma / dist)
+
     def compute_errors(self, pose, gt_pose, method: str):
         t, r = metrics.compute_errors(np.asarray(pose), np.asarray(gt_pose))
         self.rot_errors.setdefault(method, []).append(r)

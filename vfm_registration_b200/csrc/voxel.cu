@@ -715,7 +715,7 @@ static void launch_insert(vfmreg_ctx* ctx, const void* pts, int64_t n, int cols,
 
 int voxel_downsample(vfmreg_ctx* ctx, const void* pts, int64_t n, int cols, int elem_size, double voxel_size, int32_t* keep_idx,
                      int32_t* count) {
-  VFM_CHECK_ARG(n > 0 && n < (1LL << 30), "voxel_downsample: bad point count %lld", (long long)n);
+  VFM_CHECK_ARG(n > 0 && n < (1LL << 28), "voxel_downsample: point count %lld outside (0, 2^28)", (long long)n);
   VFM_CHECK_ARG(cols >= 3 && (elem_size == 4 || elem_size == 8), "voxel_downsample: need >= 3 columns of float32 / float64");
   VFM_CHECK_ARG(voxel_size > 0.0, "voxel_downsample: voxel_size must be > 0");
   const uint32_t cap = table_capacity(n);
@@ -778,7 +778,7 @@ static void map_free(vfmreg_voxel_map* m) {
 
 int voxel_map_build(vfmreg_ctx* ctx, vfmreg_voxel_map* m, const double* xyz, int64_t n) {
   VFM_CHECK_ARG(m, "voxel_map_build: null map");
-  VFM_CHECK_ARG(n >= 0 && n < (1LL << 30), "voxel_map_build: bad point count");
+  VFM_CHECK_ARG(n >= 0 && n < (1LL << 28), "voxel_map_build: point count outside [0, 2^28)");
   VFM_CUDA(cudaStreamSynchronize(ctx->stream));
   map_free(m);
   if (n == 0) return VFMREG_OK;
