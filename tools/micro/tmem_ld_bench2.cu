@@ -1,5 +1,9 @@
-// Micro-benchmark 2: tcgen05.ld shapes (32x32b .x16/.x32/.x64/.x128) -- cycles per instruction and bytes/cycle per warp.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/_bin/tmem_ld_bench2 tools/micro/tmem_ld_bench2.cu
+// Micro-benchmark: tcgen05.ld shapes (32x32b .x16/.x32/.x64) on an otherwise idle SM -- cycles per instruction and bytes/cycle
+// per warp.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/_bin/tmem_ld_bench2 tools/micro/tmem_ld_bench2.cu
+// Only two of the loaded registers are consumed per load, so the loop is paced by the load itself.  (A first version
+// xor-ed all N registers into one accumulator and measured that dependent chain instead: 2.7 cycles per register, i.e. the
+// "85 cycles per .x32 load" once quoted.  The number that matters for the match epilogue -- ~245 cycles per .x32 load and SM
+// sub-partition WHILE tcgen05.mma runs -- comes from the kernel's own counters, profiles/r1_kernel_bench.txt.)
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -46,8 +50,7 @@ __global__ void __launch_bounds__(256, 1) bench(int iters, long long* out, uint3
   for (int i = 0; i < iters; ++i) {
     Ld<N>::ld(base + (uint32_t)((i * N) & 511 & ~(N - 1)), r);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < N; ++k) acc ^= r[k];
+    acc ^= r[0] ^ r[N - 1];
   }
   const long long t1 = clock64();
   if ((threadIdx.x & 31) == 0) out[warp] = t1 - t0;
