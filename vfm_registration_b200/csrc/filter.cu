@@ -1,6 +1,8 @@
 // Cosine gate + mutual check + ratio test -> ordered correspondence list (reference VoxelHashMap.cpp:501-511,
-// 587-600 and registration_node.py:530).  One CTA, ballot-based ordered stream compaction: n is at most a few
-// 10^4 queries, so this is a latency-sized kernel (reads 12-16 B, writes <= 8 B per query).
+// 587-600 and registration_node.py:530).  One CTA: every thread owns a run of consecutive queries, counts its keepers, one
+// block-wide scan gives its write position, a second pass writes them in order.  n is at most a few 10^4 queries, so this
+// is a latency-sized kernel (reads 12-16 B, writes <= 8 B per query); the pruned mutual check (gate -> gather the map rows
+// the gated queries point at -> reverse search over those rows -> keep the pairs that point back) lives here too.
 #include "common.cuh"
 
 namespace vfm {
