@@ -207,3 +207,25 @@ def build_local_map(map_poses, map_point_clouds, voxel_size: float = 0.25, feat_
     else:
         local = voxel_down_sample(local, voxel_size)
     return local[:, :3 + feat_dim]
+
+
+# ---- vectorised restatements for full-size checks (same results as the loops above, see tests/test_oracle_voxel.py) ----
+def _voxel_keys(xyz: np.ndarray, voxel_size: float) -> np.ndarray:
+    v = voxel_index(xyz, voxel_size) + (1 << 20)
+    return (v[:, 0] << 42) | (v[:, 1] << 21) | v[:, 2]
+
+
+def voxel_down_sample_index_fast(points: np.ndarray, voxel_size: float) -> np.ndarray:
+    """Indices (ascending) of the first point of every voxel."""
+    _, first = np.unique(_voxel_keys(points, voxel_size), return_index=True)
+    return np.sort(first)
+
+
+def voxel_map_kept_index_fast(xyz: np.ndarray, voxel_size: float, max_points: int) -> np.ndarray:
+    """Indices (ascending) of the points a VoxelHashMap keeps: the first max_points of every voxel in insertion order."""
+    keys = _voxel_keys(xyz, voxel_size)
+    order = np.argsort(keys, kind="stable")          # groups voxels, insertion order inside a voxel
+    ks = keys[order]
+    start = np.r_[0, np.flatnonzero(ks[1:] != ks[:-1]) + 1]
+    rank = np.arange(len(ks)) - np.repeat(start, np.diff(np.r_[start, len(ks)]))
+    return np.sort(order[rank < max_points])

@@ -264,3 +264,31 @@ def test_compat_icp_registration(vfm):
     assert rte < 0.05 and rre < 0.1
     with pytest.raises(ValueError, match="Invalid shape"):
         node.icp_registration(s["map_xyz"], s["scan_xyz"][:, :2])
+
+
+def test_voxel_operations_full_size(vfm):
+    """NCLT-scale inputs against the vectorised oracle restatements: 1 M points, a 200k x (3 + 384) cloud, a 200k-point map with
+    crowded voxels, and nearest neighbours checked against a KD-tree wherever the true neighbour is closer than one voxel."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(77)
+    big = (rng.uniform(-60, 60, (1_000_000, 3)) * np.array([1.0, 1.0, 0.1])).astype(np.float32)
+    for vs in (0.25, 1.0):
+        _, gi = vfm.voxel_down_sample(big, vs, return_index=True)
+        assert np.array_equal(gi, ov.voxel_down_sample_index_fast(big, vs))
+    wide = np.c_[big[:200_000], rng.standard_normal((200_000, 384)).astype(np.float32)]
+    out, gi = vfm.voxel_down_sample(wide, 0.5, return_index=True)
+    wi = ov.voxel_down_sample_index_fast(wide, 0.5)
+    assert np.array_equal(gi, wi) and np.array_equal(out, wide[wi])
+    dense = np.concatenate([big[:180_000].astype(np.float64), rng.normal(0, 0.3, (20_000, 3))], axis=0)   # ~10^4 points in a few voxels
+    m = vfm.VoxelMap(1.0, 20)
+    m.build(dense)
+    xyz, idx = m.points()
+    want = ov.voxel_map_kept_index_fast(dense, 1.0, 20)
+    assert np.array_equal(idx.cpu().numpy(), want) and np.array_equal(xyz.cpu().numpy(), dense[want])
+    kept = dense[want]
+    q = kept[rng.integers(0, len(kept), 20_000)] + rng.normal(0, 0.15, (20_000, 3))
+    tgt, valid, d2 = m.nearest(q, 1.0)
+    d, j = cKDTree(kept).query(q)
+    sure = d < 0.99                                    # the true neighbour then lies inside the 27 voxels
+    assert sure.mean() > 0.9 and valid.cpu().numpy()[sure].all()
+    assert np.array_equal(tgt.cpu().numpy()[sure], kept[j[sure]]) and np.allclose(np.sqrt(d2.cpu().numpy()[sure]), d[sure], rtol=0, atol=1e-12)

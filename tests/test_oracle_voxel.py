@@ -100,3 +100,13 @@ def test_vfm_icp_first_loop_prunes_outliers_and_converges():
     assert 1 <= j < 50 and len(s) <= 365 and np.abs(est - T).max() < 0.05
     e0, j0, (s0, _) = ov.vfm_icp_first_loop(np.zeros((0, 3)), np.zeros((0, 3)), T, 0.5)
     assert j0 == 0 and len(s0) == 0 and np.array_equal(e0, T)
+
+
+def test_vectorised_restatements_match_the_loops():
+    pts = np.concatenate([_cloud(21, 20000, span=6.0), _cloud(22, 50, span=0.4)], axis=0).astype(np.float32)
+    for vs in (0.25, 1.0):
+        assert np.array_equal(ov.voxel_down_sample_index_fast(pts, vs), ov.voxel_down_sample(pts, vs, return_index=True)[1])
+    for cap in (1, 5, 20):
+        m = ov.VoxelHashMapOracle(1.0, cap)
+        m.add_points(pts)
+        assert np.array_equal(ov.voxel_map_kept_index_fast(pts, 1.0, cap), m.point_cloud()[1])
