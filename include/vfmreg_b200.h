@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VFMREG_VERSION 100
+#define VFMREG_VERSION 200
 
 #if defined(__GNUC__)
 #define VFMREG_API __attribute__((visibility("default")))
@@ -166,6 +166,34 @@ VFMREG_API int vfmreg_register_batch_host(vfmreg_ctx* ctx, int32_t n_pairs, cons
                                const float* const* src_feats, const float* const* tgt_feats, const int64_t* n, const int64_t* m,
                                int32_t d, const vfmreg_register_params* params, const int32_t* const* sample_idx,
                                int32_t* const* corr_out, uint8_t* const* mask_out, vfmreg_register_result* results);
+
+/* Both batch entry points prepare (upload, renormalise, convert to fp16) a map ONCE for every run of consecutive pairs that
+ * pass the same tgt_xyz / tgt_feats pointers and m: the reference builds one local map per scene and registers the scene's
+ * 3-5 scans against it (registration_node.py:554-590). */
+
+/* ---------------------------------------------------------------------------------------------
+ * A map kept resident on the device across calls: what registration_node.py:554-580 builds once per scene
+ * (`local_map`) and VoxelHashMap keeps in `map_n_` (VoxelHashMap.cpp:746-757) for the scans that follow.
+ *   vfmreg_map_create    copies tgt_xyz (m x 3) and prepares tgt_feats (m x d) -- float32, HOST (host_buffers != 0) or
+ *                        device pointers; flags = VFMREG_NORMALIZE | VFMREG_ALGO_*; returns after the map is ready.
+ *   vfmreg_register_scans = vfmreg_register_batch[_host] with every pair's target = the resident map (params->flags must
+ *                        carry the NORMALIZE / ALGO bits the map was created with).
+ *   vfmreg_map_match     GetVFMCorrespondences' search against the resident map (VoxelHashMap.cpp:486-495): device queries
+ *                        (n x d), outputs as vfmreg_match_nn's idx01 / sim01 / sec01.  min_cos (NAN = none) may be passed
+ *                        when sec01 is NULL and the caller drops matches below it (VoxelHashMap.cpp:501-511): queries whose
+ *                        best match is below the gate may then report idx01 = -1, sim01 = -inf instead of that match.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vfmreg_map vfmreg_map;
+VFMREG_API int vfmreg_map_create(vfmreg_ctx* ctx, const float* tgt_xyz, const float* tgt_feats, int64_t m, int32_t d, uint32_t flags,
+                                 int32_t host_buffers, vfmreg_map** map);
+VFMREG_API void vfmreg_map_destroy(vfmreg_map* map);
+VFMREG_API int64_t vfmreg_map_size(const vfmreg_map* map);
+VFMREG_API int vfmreg_map_match(vfmreg_ctx* ctx, const vfmreg_map* map, const float* queries, int64_t n, float min_cos,
+                                int32_t* idx01, float* sim01, float* sec01);
+VFMREG_API int vfmreg_register_scans(vfmreg_ctx* ctx, const vfmreg_map* map, int32_t n_scans, const float* const* src_xyz,
+                                     const float* const* src_feats, const int64_t* n, const vfmreg_register_params* params,
+                                     const int32_t* const* sample_idx, int32_t host_buffers, int32_t* const* corr_out,
+                                     uint8_t* const* mask_out, vfmreg_register_result* results);
 
 /* ---------------------------------------------------------------------------------------------
  * a3/a4/a5  point -> pixel projection + feature gather + first-camera-wins scatter.

@@ -39,6 +39,16 @@ ORC_API int orc_num_threads(void) {
 #endif
 }
 
+/* The timed CPU baseline must use the cores the process may run on even when a launcher (torchrun) exported
+ * OMP_NUM_THREADS=1 for its workers. */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_simd(void) {
 #ifdef ORC_AVX2
     return 8;

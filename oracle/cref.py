@@ -44,6 +44,22 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the C oracle (overrides OMP_NUM_THREADS, which torchrun sets to 1 for its workers)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
+def use_all_cores() -> int:
+    """Run on every core the process is allowed on; returns the thread count."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    return set_num_threads(n)
+
+
 def renorm_l2(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float32)
     out = np.empty_like(x)

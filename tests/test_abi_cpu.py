@@ -36,7 +36,7 @@ def test_python_binding_covers_header(lib_path):
     from vfm_registration_b200 import _lib
     assert set(_lib.declared_symbols()) == set(_declared())
     lib = _lib.load()
-    assert lib.vfmreg_version() == 100
+    assert lib.vfmreg_version() == 200
 
 
 def test_struct_layouts_match_header(lib_path, tmp_path):

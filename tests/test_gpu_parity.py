@@ -320,3 +320,151 @@ def test_pruned_mutual_equals_full_search(vfm, m, n, d, min_cos):
     assert np.array_equal(got, want)
     if min_cos == 0.8 and n >= 3000:
         assert len(got) > 0.2 * n
+
+
+# ---- BASELINE-size parity pinned directly to the oracle (not to the repo's own exact kernel) ---------------------------
+def test_configs1_full_size_vs_c_oracle(vfm):
+    """BASELINE configs[1] (10k scan x 50k map x 384, mutual + cos >= 0.8, 8192 hypotheses, tau = 1 m) against oracle/c on all
+    six match arrays, then the correspondence list, winning hypothesis, inlier mask and transform of register()."""
+    s = synth.make_pair(2, 50_000, 10_000, 384)
+    c = cref.match_nn(s["scan_feat"], s["map_feat"], mutual=True)
+    g = vfm.match_nn(torch.from_numpy(s["scan_feat"]).cuda(), torch.from_numpy(s["map_feat"]).cuda(), mutual=True)
+    for k in ("idx01", "sim01", "sec01", "idx10", "sim10", "sec10"):
+        assert np.array_equal(getattr(g, k).cpu().numpy(), c[k]), k
+    corr = match.filter_correspondences(c["idx01"], c["sim01"], c["sec01"], c["idx10"], min_cos=0.8, mutual=True)
+    o = cref.ransac(s["scan_xyz"], s["map_xyz"], corr, None, 1.0, seed=42, n_hyp=8192)
+    for host in (True, False):
+        args = (s["scan_xyz"], s["map_xyz"], s["scan_feat"], s["map_feat"])
+        if not host:
+            args = tuple(torch.from_numpy(x).cuda() for x in args)
+        r = vfm.register(*args, min_cos=0.8, mutual=True, ransac_iters=8192, inlier_thresh=1.0, seed=42)
+        assert np.array_equal(r.corr, corr) and len(corr) > 2000
+        assert r.best_hyp == o["best"] and np.array_equal(r.inlier_mask, o["mask"]) and np.array_equal(r.T, o["T"])
+    # float64 NumPy oracle of the solve (independent arithmetic): same winner and mask, T within 1e-4 Frobenius
+    on = ransac.ransac(s["scan_xyz"], s["map_xyz"], corr, cref.sample_indices(42, 8192, len(corr)), 1.0)
+    assert on["best"] == r.best_hyp and np.array_equal(on["mask"], r.inlier_mask) and np.linalg.norm(on["T"] - r.T) < 1e-4
+
+
+def test_configs3_full_size_vs_c_oracle(vfm):
+    """BASELINE configs[3] (20k scan x 200k map x 768, ratio test 0.9, 65536 hypotheses) against oracle/c: top-2 arrays of
+    the forward search, then correspondences / winner / mask / transform of register()."""
+    s = synth.make_pair(4, 200_000, 20_000, 768, sigma_f=0.02)
+    c = cref.match_nn(s["scan_feat"], s["map_feat"])
+    a, b = torch.from_numpy(s["scan_feat"]).cuda(), torch.from_numpy(s["map_feat"]).cuda()
+    g = vfm.match_nn(a, b)
+    for k in ("idx01", "sim01", "sec01"):
+        assert np.array_equal(getattr(g, k).cpu().numpy(), c[k]), k
+    corr = match.filter_correspondences(c["idx01"], c["sim01"], c["sec01"], ratio=0.9)
+    o = cref.ransac(s["scan_xyz"], s["map_xyz"], corr, None, 1.0, seed=4, n_hyp=65536)
+    r = vfm.register(torch.from_numpy(s["scan_xyz"]).cuda(), torch.from_numpy(s["map_xyz"]).cuda(), a, b, min_cos=None, ratio=0.9,
+                     ransac_iters=65536, inlier_thresh=1.0, seed=4)
+    assert np.array_equal(r.corr, corr) and len(corr) > 3000
+    assert r.best_hyp == o["best"] and np.array_equal(r.inlier_mask, o["mask"]) and np.array_equal(r.T, o["T"])
+    rte, rre = synth.pose_errors(r.T, s["T_gt"])
+    assert rte < 1.0 and rre < 5.0
+
+
+def test_reference_shape_vs_c_oracle(vfm):
+    """The reference's own problem shape (~300 voxelised queries against a 200k-point map, 384-d, cosine gate)."""
+    rng = np.random.default_rng(77)
+    b = rng.standard_normal((200_000, 384)).astype(np.float32)
+    a = rng.standard_normal((300, 384)).astype(np.float32)
+    a[:120] = b[rng.integers(0, 200_000, 120)] + 0.02 * rng.standard_normal((120, 384)).astype(np.float32)
+    c = cref.match_nn(a, b)
+    g = vfm.match_nn(a, b)
+    for k in ("idx01", "sim01", "sec01"):
+        assert np.array_equal(getattr(g, k).cpu().numpy(), c[k]), k
+
+
+# ---- maps shared by the scans of a scene -----------------------------------------------------------------------------------
+def _scene(seed, m, ns, d):
+    """One map and len(ns) scans of it (each with its own planted pose)."""
+    base = synth.make_pair(seed, m, ns[0], d, scan_seed=seed * 100)
+    scans = [(base["scan_xyz"], base["scan_feat"], base["T_gt"])]
+    for k, n in enumerate(ns[1:]):
+        s = synth.make_pair(seed, m, n, d, scan_seed=seed * 100 + k + 1)
+        assert np.array_equal(s["map_feat"], base["map_feat"])
+        scans.append((s["scan_xyz"], s["scan_feat"], s["T_gt"]))
+    return base["map_xyz"], base["map_feat"], scans
+
+
+@pytest.mark.parametrize("kw", [dict(min_cos=0.8, mutual=True, inlier_thresh=1.0), dict(min_cos=0.8, inlier_thresh=1.0),
+                                dict(min_cos=None, ratio=0.9, inlier_thresh=1.0), dict(min_cos=0.5, mutual=True)])
+def test_shared_map_batches_equal_sequential(vfm, kw):
+    """register_batch with pairs that share their target objects (host and device), ResidentMap + register_scans (host and
+    device): every route returns exactly what per-pair register() calls return, and those equal the oracle chain."""
+    scenes = [_scene(300, 6000, (1500, 900, 2000), 128), _scene(301, 4000, (1000, 1000), 128), _scene(302, 5000, (700,), 128)]
+    pairs, want = [], []
+    for mx, mf, scans in scenes:
+        for sx, sf, _ in scans:
+            pairs.append((sx, mx, sf, mf))
+            want.append(vfm.register(sx, mx, sf, mf, ransac_iters=1024, seed=11, **kw))
+    # the sequential results against the oracle chain (first scene)
+    mx, mf, scans = scenes[0]
+    for (sx, sf, _), w in zip(scans, want):
+        m = cref.match_nn(sf, mf, mutual=True)
+        corr = match.filter_correspondences(m["idx01"], m["sim01"], m["sec01"], m["idx10"], min_cos=kw.get("min_cos"),
+                                            mutual=kw.get("mutual", False), ratio=kw.get("ratio"))
+        o = cref.ransac(sx, mx, corr, None, kw.get("inlier_thresh", 1e4), seed=11, n_hyp=1024)
+        assert np.array_equal(w.corr, corr) and w.best_hyp == o["best"] and np.array_equal(w.T, o["T"])
+        assert np.array_equal(w.inlier_mask, o["mask"])
+
+    def same(got):
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            gc = g.corr if isinstance(g.corr, np.ndarray) else g.corr.cpu().numpy()
+            gm = g.inlier_mask if isinstance(g.inlier_mask, np.ndarray) else g.inlier_mask.cpu().numpy()
+            assert np.array_equal(g.T, w.T) and np.array_equal(gc, w.corr) and np.array_equal(gm, w.inlier_mask)
+            assert g.best_hyp == w.best_hyp and g.fitness == w.fitness and g.rmse == w.rmse
+
+    same(vfm.register_batch(pairs, ransac_iters=1024, seed=11, **kw))
+    cache = {}
+    dev = lambda x: cache.setdefault(id(x), torch.from_numpy(x).cuda())  # noqa: E731  shared objects stay shared
+    same(vfm.register_batch([tuple(dev(x) for x in pr) for pr in pairs], ransac_iters=1024, seed=11, **kw))
+    vfm.get_context(0).set_lanes(2)      # more runs than ring slots: slot reuse across lanes
+    same(vfm.register_batch([tuple(dev(x) for x in pr) for pr in pairs * 3], ransac_iters=1024, seed=11, **kw)[len(pairs):2 * len(pairs)])
+    vfm.get_context(0).set_lanes(5)
+    i = 0
+    for mx, mf, scans in scenes:
+        for host in (True, False):
+            rm = vfm.ResidentMap(mx, mf) if host else vfm.ResidentMap(dev(mx), dev(mf))
+            sc = [(sx, sf) if host else (dev(sx), dev(sf)) for sx, sf, _ in scans]
+            got = vfm.register_scans(rm, sc, ransac_iters=1024, seed=11, **kw)
+            for g, w in zip(got, want[i:i + len(scans)]):
+                gc = g.corr if isinstance(g.corr, np.ndarray) else g.corr.cpu().numpy()
+                assert np.array_equal(g.T, w.T) and np.array_equal(gc, w.corr) and g.best_hyp == w.best_hyp
+            rm.close()
+        i += len(scans)
+
+
+def test_resident_map_match_and_gate_floor(vfm):
+    """ResidentMap.match: with the runner-up it equals match_nn; with a cosine gate handed to the search, every query whose
+    oracle best reaches the gate gets exactly the oracle's (index, score), every other query reports something the gate
+    drops (index -1 / -inf, or a score below the gate)."""
+    s = synth.make_pair(88, 30_000, 4000, 384)
+    a = s["scan_feat"].copy()
+    a[7] = 0
+    # queries close to the gate: blend a map row with noise so that the cosine lands around 0.8
+    rng = np.random.default_rng(3)
+    for i, t in zip(range(100, 160), np.linspace(0.65, 0.85, 60)):
+        v = rng.standard_normal(384).astype(np.float32)
+        v /= np.linalg.norm(v)
+        a[i] = s["map_feat"][i] + t * v
+    c = cref.match_nn(a, s["map_feat"])
+    rm = vfm.ResidentMap(s["map_xyz"], s["map_feat"])
+    g = rm.match(a)
+    for k in ("idx01", "sim01", "sec01"):
+        assert np.array_equal(getattr(g, k).cpu().numpy(), c[k]), k
+    for gate in (0.8, 0.3, 0.05, 0.99):
+        f = rm.match(a, min_cos=gate, second=False)
+        idx, sim = f.idx01.cpu().numpy(), f.sim01.cpu().numpy()
+        above = c["sim01"] >= gate
+        assert np.array_equal(idx[above], c["idx01"][above]) and np.array_equal(sim[above], c["sim01"][above])
+        assert np.all(sim[~above] < gate)
+        corr = vfm.filter_correspondences(f, min_cos=gate).cpu().numpy()
+        assert np.array_equal(corr, match.filter_correspondences(c["idx01"], c["sim01"], min_cos=gate))
+    assert 20 < int((c["sim01"][100:160] >= 0.8).sum()) < 50   # the gate really cuts through the blended queries
+    with pytest.raises(ValueError, match="Invalid shape"):
+        rm.match(a[:, :100])
+    with pytest.raises(ValueError, match="Invalid shape"):
+        vfm.ResidentMap(s["map_xyz"][:10], s["map_feat"])

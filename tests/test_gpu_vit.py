@@ -48,7 +48,7 @@ def test_vit_forward_vs_oracle(vfm, model, depth, hw, b):
 
 
 def test_image_feature_generator_compat(vfm):
-    gen = vfm.ImageFeatureGenerator("dinov2", use_featup=False, seed=1)
+    gen = vfm.ImageFeatureGenerator("dinov2", use_featup=False, seed=1, random_init=True)
     img = _images(np.random.default_rng(0), 1, 70, 82)[0]
     f = gen.get_image_features(img)
     assert f.shape == (16, 18, 384) and f.dtype == np.float32          # (16, patch_w, C) like the reference
@@ -110,7 +110,7 @@ def test_config3_images_to_transform(vfm):
     ks, ts = np.stack([kmat] * b), np.stack(ts)
     n_map, n_scan = 6000, 2000
     map_xyz = np.c_[rng.uniform(-20, 20, (n_map, 2)), rng.uniform(-2, 4, n_map)].astype(np.float32)
-    f = vfm.ViTFeaturizer("vits14", seed=4)
+    f = vfm.ViTFeaturizer("vits14", seed=4, random_init=True)
     map_desc = vfm.extract_features(imgs, map_xyz, ks, ts, featurizer=f)
     sel = rng.permutation(n_map)[:n_scan]
     t_gt = np.eye(4)
@@ -135,7 +135,7 @@ def test_vit_graph_replay_matches_eager(vfm):
     """The second and later calls with a given shape replay a captured CUDA graph: results must be bit-identical to the
     eager first call, for changing inputs, interleaved shapes and a batch that forces the staging buffers to grow."""
     rng = np.random.default_rng(2)
-    f = vfm.ViTFeaturizer("vits14", seed=5)
+    f = vfm.ViTFeaturizer("vits14", seed=5, random_init=True)
     a = torch.from_numpy(_images(rng, 2, 224, 224)).cuda()
     b = torch.from_numpy(_images(rng, 2, 224, 224)).cuda()
     c = torch.from_numpy(_images(rng, 1, 70, 82)).cuda()

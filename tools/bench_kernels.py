@@ -46,6 +46,26 @@ def bench_match(shapes=((10000, 50000, 384), (50000, 10000, 384), (4096, 4096, 3
                   f"= {fl / (gms / max(gl, 1)) / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def bench_match_modes(shapes=((10000, 50000, 384), (20000, 200000, 768), (300, 200000, 384))):
+    """The candidate-search kernel in its three recording modes against a resident map: top-2 (runner-up needed), top-1,
+    top-1 with the caller's cosine gate as the recording floor (what register() with min_cos runs)."""
+    from vfm_registration_b200 import synth
+    ctx = v.get_context(0)
+    for n, m, d in shapes:
+        s = synth.make_pair(2, m, n, d)   # 30 % of the queries have a planted match at cosine ~0.9
+        rm = v.ResidentMap(torch.from_numpy(s["map_xyz"]).cuda(), torch.from_numpy(s["map_feat"]).cuda())
+        a = torch.from_numpy(s["scan_feat"]).cuda()
+        fl = 2.0 * n * m * d
+        for name, kw in (("top-2", dict(second=True)), ("top-1", dict(second=False)), ("top-1 + gate 0.8", dict(second=False, min_cos=0.8))):
+            ctx.enable_timing(True)
+            ms = time_fn(lambda: rm.match(a, **kw), iters=10)
+            gms, gl = ctx.group_time_ms(0)
+            ctx.enable_timing(False)
+            print(f"match modes n={n} m={m} d={d} {name:17s}: call {ms:.3f} ms, search kernel {gms / max(gl, 1):.4f} ms "
+                  f"= {fl / (gms / max(gl, 1)) / 1e9:.1f} TFLOP/s", flush=True)
+        rm.close()
+
+
 def bench_ransac(shapes=((8192, 3000), (8192, 10000), (65536, 20000), (50000, 300))):
     from vfm_registration_b200 import synth
     ctx = v.get_context(0)
@@ -98,7 +118,7 @@ def bench_vit(batches=(6, 48)):
     rng = np.random.default_rng(0)
     for model in ("vits14", "vitb14", "vitl14"):
         depth, w, heads = features.PRESETS[model]
-        f = v.ViTFeaturizer(model, seed=1)
+        f = v.ViTFeaturizer(model, seed=1, random_init=True)
         for b in batches:
             imgs = torch.from_numpy(rng.integers(0, 255, (b, 224, 224, 3), dtype=np.uint8)).cuda()
             ctx.enable_timing(True)
@@ -125,7 +145,7 @@ def bench_extract(n=10000):
         ts.append(t)
     ts = np.stack(ts)
     for model in ("vits14", "vitl14"):
-        f = v.ViTFeaturizer(model, seed=1)
+        f = v.ViTFeaturizer(model, seed=1, random_init=True)
         imgs_d, pts_d = torch.from_numpy(imgs).cuda(), torch.from_numpy(pts).cuda()
         ms = time_fn(lambda: v.extract_features(imgs_d, pts_d, k, ts, featurizer=f), iters=10)
         ms_h = time_fn(lambda: v.extract_features(imgs, pts, k, ts, featurizer=f).cpu(), iters=10)
@@ -165,6 +185,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "match"
     if what == "match":
         bench_match()
+    elif what == "modes":
+        bench_match_modes()
     elif what == "ransac":
         bench_ransac()
     elif what == "voxel":

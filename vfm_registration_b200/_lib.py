@@ -67,6 +67,11 @@ _SIGS = {
     "vfmreg_register_batch": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(RegisterParams), _P, _P, _P, _P]),
     "vfmreg_register_batch_host": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(RegisterParams), _P, _P, _P,
                                              _P]),
+    "vfmreg_map_create": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(_P)]),
+    "vfmreg_map_destroy": (None, [_P]),
+    "vfmreg_map_size": (C.c_int64, [_P]),
+    "vfmreg_map_match": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, _P, _P, _P]),
+    "vfmreg_register_scans": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.POINTER(RegisterParams), _P, C.c_int32, _P, _P, _P]),
     "vfmreg_project_gather": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Camera), C.c_int32, _P, C.POINTER(C.c_int64), _P,
                                         C.POINTER(C.c_int64), C.c_int32, _P, _P, _P]),
     "vfmreg_vit_create": (C.c_int, [_P, C.POINTER(VitConfig), C.POINTER(_P)]),

@@ -25,7 +25,8 @@ from . import _lib
 from ._lib import VfmRegError
 
 __all__ = ["Context", "get_context", "match_nn", "filter_correspondences", "ransac_kabsch", "register", "RegResult",
-           "MatchResult", "RansacResult", "VfmRegError", "CameraSpec", "project_gather", "register_batch"]
+           "MatchResult", "RansacResult", "VfmRegError", "CameraSpec", "project_gather", "register_batch", "ResidentMap",
+           "register_scans"]
 
 _ALGO = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}
 
@@ -299,30 +300,49 @@ def register(source_pcd, target_pcd, src_feats, tgt_feats, *, normalize: bool = 
                      n_inliers=int(res.n_inliers))
 
 
-def _register_batch_device(ctx, pairs, p):
-    """CUDA-tensor inputs: everything is enqueued back to back, one host synchronisation per batch."""
+def _register_batch_device(ctx, pairs, p, resident=None):
+    """CUDA-tensor inputs: everything is enqueued back to back, one host synchronisation per batch.
+    ``resident``: every pair is (source_pcd, src_feats) against that ResidentMap."""
     dev = torch.device("cuda", ctx.device)
     k = len(pairs)
     keep, ns, ms = [], [], []
-    d = None
-    for (sx, tx, sf, tf) in pairs:
-        sx, tx, sf = _dev_f32(sx, dev, "source_pcd", 3), _dev_f32(tx, dev, "target_pcd", 3), _dev_f32(sf, dev, "src_feats")
-        d = sf.shape[1] if d is None else d
-        tf = _dev_f32(tf, dev, "tgt_feats", d)
-        if tuple(sf.shape) != (sx.shape[0], d) or tf.shape[0] != tx.shape[0]:
+    d = resident.d if resident is not None else None
+    conv = {}   # pairs that share a target object share its device copy: the library prepares that map once
+
+    def shared(x, name, cols):
+        key = id(x)
+        if key not in conv:
+            conv[key] = (x, _dev_f32(x, dev, name, cols))
+        return conv[key][1]
+
+    for pr in pairs:
+        if resident is not None:
+            sx, sf = _dev_f32(pr[0], dev, "source_pcd", 3), _dev_f32(pr[1], dev, "src_feats", d)
+            tx = tf = None
+        else:
+            sx, tx, sf = _dev_f32(pr[0], dev, "source_pcd", 3), shared(pr[1], "target_pcd", 3), _dev_f32(pr[2], dev, "src_feats")
+            d = sf.shape[1] if d is None else d
+            tf = shared(pr[3], "tgt_feats", d)
+        if tuple(sf.shape) != (sx.shape[0], d) or (tf is not None and tf.shape[0] != tx.shape[0]):
             raise ValueError("Invalid shape: points / descriptors mismatch")
         keep.append((sx, tx, sf, tf))
         ns.append(sx.shape[0])
-        ms.append(tx.shape[0])
+        ms.append(tx.shape[0] if tx is not None else resident.m)
     corr = [torch.empty((n, 2), dtype=torch.int32, device=dev) for n in ns]
     mask = [torch.empty(n, dtype=torch.uint8, device=dev) for n in ns]
     arr = lambda ptrs: (C.c_void_p * k)(*ptrs)  # noqa: E731
     res = (_lib.RegisterResult * k)()
     ctx.bind_stream()
-    _lib.check(ctx.lib.vfmreg_register_batch(
-        ctx.handle, k, arr([x[0].data_ptr() for x in keep]), arr([x[1].data_ptr() for x in keep]),
-        arr([x[2].data_ptr() for x in keep]), arr([x[3].data_ptr() for x in keep]), (C.c_int64 * k)(*ns), (C.c_int64 * k)(*ms), d,
-        C.byref(p), None, arr([t.data_ptr() for t in corr]), arr([t.data_ptr() for t in mask]), res), "vfmreg_register_batch")
+    if resident is not None:
+        _lib.check(ctx.lib.vfmreg_register_scans(
+            ctx.handle, resident.handle, k, arr([x[0].data_ptr() for x in keep]), arr([x[2].data_ptr() for x in keep]),
+            (C.c_int64 * k)(*ns), C.byref(p), None, 0, arr([t.data_ptr() for t in corr]), arr([t.data_ptr() for t in mask]), res),
+            "vfmreg_register_scans")
+    else:
+        _lib.check(ctx.lib.vfmreg_register_batch(
+            ctx.handle, k, arr([x[0].data_ptr() for x in keep]), arr([x[1].data_ptr() for x in keep]),
+            arr([x[2].data_ptr() for x in keep]), arr([x[3].data_ptr() for x in keep]), (C.c_int64 * k)(*ns), (C.c_int64 * k)(*ms), d,
+            C.byref(p), None, arr([t.data_ptr() for t in corr]), arr([t.data_ptr() for t in mask]), res), "vfmreg_register_batch")
     out = []
     for i in range(k):
         kc = int(res[i].n_corr)
@@ -340,7 +360,9 @@ def register_batch(pairs, *, normalize: bool = True, min_cos: Optional[float] = 
     HOST arrays: the copy of pair i+1 is overlapped with the solve of pair i (``vfmreg_register_batch_host``); pinned inputs
     (``torch.Tensor.pin_memory().numpy()``) make the copies asynchronous.  CUDA tensors: all pairs are enqueued back to
     back with a single host synchronisation (``vfmreg_register_batch``); ``corr`` / ``inlier_mask`` then stay on the device.
-    Returns a list of RegResult."""
+    Consecutive pairs that pass the SAME target objects (``target_pcd`` and ``tgt_feats``) share one upload / preparation of
+    that map -- the reference registers the 3-5 scans of a scene against one local map (registration_node.py:554-590).
+    Mixed host / CUDA inputs are moved to the host side.  Returns a list of RegResult."""
     ctx = get_context(device)
     k = len(pairs)
     if k == 0:
@@ -348,34 +370,58 @@ def register_batch(pairs, *, normalize: bool = True, min_cos: Optional[float] = 
     p = _params(normalize, min_cos, mutual, ratio, ransac_iters, inlier_thresh, seed, refit, algo)
     if all(isinstance(x, torch.Tensor) and x.is_cuda for pr in pairs for x in pr):
         return _register_batch_device(ctx, pairs, p)
+    return _register_batch_host(ctx, pairs, p)
+
+
+def _register_batch_host(ctx, pairs, p, resident=None):
+    """Host buffers; ``resident``: every pair is (source_pcd, src_feats) against that ResidentMap."""
+    k = len(pairs)
 
     def h(x, name, cols=None):
-        x = x.numpy() if isinstance(x, torch.Tensor) else x
+        x = x.cpu().numpy() if isinstance(x, torch.Tensor) else x
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 2 or (cols is not None and x.shape[1] != cols):
             raise ValueError(f"Invalid shape for {name}: {x.shape}")
         return x
 
+    conv = {}   # pairs that share a target object share its converted array: the library uploads / prepares that map once
+
+    def shared(x, name, cols):
+        key = id(x)
+        if key not in conv:
+            conv[key] = (x, h(x, name, cols))
+        return conv[key][1]
+
     keep, ns, ms = [], [], []
-    d = None
-    for (sx, tx, sf, tf) in pairs:
-        sx, tx, sf = h(sx, "source_pcd", 3), h(tx, "target_pcd", 3), h(sf, "src_feats")
-        d = sf.shape[1] if d is None else d
-        tf = h(tf, "tgt_feats", d)
-        if sf.shape != (sx.shape[0], d) or tf.shape[0] != tx.shape[0]:
+    d = resident.d if resident is not None else None
+    for pr in pairs:
+        if resident is not None:
+            sx, sf = h(pr[0], "source_pcd", 3), h(pr[1], "src_feats", d)
+            tx = tf = None
+        else:
+            sx, tx, sf = h(pr[0], "source_pcd", 3), shared(pr[1], "target_pcd", 3), h(pr[2], "src_feats")
+            d = sf.shape[1] if d is None else d
+            tf = shared(pr[3], "tgt_feats", d)
+        if sf.shape != (sx.shape[0], d) or (tf is not None and tf.shape[0] != tx.shape[0]):
             raise ValueError("Invalid shape: points / descriptors mismatch")
         keep.append((sx, tx, sf, tf))
         ns.append(sx.shape[0])
-        ms.append(tx.shape[0])
+        ms.append(tx.shape[0] if tx is not None else resident.m)
     corr = [torch.empty((n, 2), dtype=torch.int32).pin_memory() for n in ns]
     mask = [torch.empty(n, dtype=torch.uint8).pin_memory() for n in ns]
     arr = lambda ptrs: (C.c_void_p * k)(*ptrs)  # noqa: E731
     res = (_lib.RegisterResult * k)()
     ctx.bind_stream()
-    _lib.check(ctx.lib.vfmreg_register_batch_host(
-        ctx.handle, k, arr([x[0].ctypes.data for x in keep]), arr([x[1].ctypes.data for x in keep]),
-        arr([x[2].ctypes.data for x in keep]), arr([x[3].ctypes.data for x in keep]), (C.c_int64 * k)(*ns), (C.c_int64 * k)(*ms), d,
-        C.byref(p), None, arr([t.data_ptr() for t in corr]), arr([t.data_ptr() for t in mask]), res), "vfmreg_register_batch_host")
+    if resident is not None:
+        _lib.check(ctx.lib.vfmreg_register_scans(
+            ctx.handle, resident.handle, k, arr([x[0].ctypes.data for x in keep]), arr([x[2].ctypes.data for x in keep]),
+            (C.c_int64 * k)(*ns), C.byref(p), None, 1, arr([t.data_ptr() for t in corr]), arr([t.data_ptr() for t in mask]), res),
+            "vfmreg_register_scans")
+    else:
+        _lib.check(ctx.lib.vfmreg_register_batch_host(
+            ctx.handle, k, arr([x[0].ctypes.data for x in keep]), arr([x[1].ctypes.data for x in keep]),
+            arr([x[2].ctypes.data for x in keep]), arr([x[3].ctypes.data for x in keep]), (C.c_int64 * k)(*ns), (C.c_int64 * k)(*ms), d,
+            C.byref(p), None, arr([t.data_ptr() for t in corr]), arr([t.data_ptr() for t in mask]), res), "vfmreg_register_batch_host")
     out = []
     for i in range(k):
         kc = int(res[i].n_corr)
@@ -383,6 +429,87 @@ def register_batch(pairs, *, normalize: bool = True, min_cos: Optional[float] = 
                              inlier_mask=mask[i][:kc].numpy().astype(bool), fitness=float(res[i].fitness), rmse=float(res[i].rmse),
                              best_hyp=int(res[i].best_hyp), n_inliers=int(res[i].n_inliers)))
     return out
+
+
+class ResidentMap:
+    """A map kept on the device for the scans of one scene (``vfmreg_map_create``): coordinates + renormalised fp32 / fp16
+    descriptors, uploaded and prepared once.  The reference builds ``local_map`` once per scene
+    (registration_node.py:554-580) and registers every scan of the scene against it (:587-590).
+
+    ``target_pcd`` (M, 3) and ``tgt_feats`` (M, D): both NumPy / host tensors, or both CUDA tensors."""
+
+    def __init__(self, target_pcd, tgt_feats, *, normalize: bool = True, algo: str = "auto", device=None):
+        self.ctx = get_context(device)
+        host = [not (isinstance(x, torch.Tensor) and x.is_cuda) for x in (target_pcd, tgt_feats)]
+        if host[0] != host[1]:
+            raise ValueError("Invalid shape: target_pcd and tgt_feats must both be host arrays or both be CUDA tensors")
+        self.flags = (_lib.NORMALIZE if normalize else 0) | _ALGO[algo]
+        if host[0]:
+            def h(x, name, cols=None):
+                x = x.numpy() if isinstance(x, torch.Tensor) else x
+                x = np.ascontiguousarray(x, dtype=np.float32)
+                if x.ndim != 2 or (cols is not None and x.shape[1] != cols):
+                    raise ValueError(f"Invalid shape for {name}: {x.shape}")
+                return x
+            tx, tf = h(target_pcd, "target_pcd", 3), h(tgt_feats, "tgt_feats")
+            ptrs = (tx.ctypes.data, tf.ctypes.data)
+        else:
+            dev = torch.device("cuda", self.ctx.device)
+            tx, tf = _dev_f32(target_pcd, dev, "target_pcd", 3), _dev_f32(tgt_feats, dev, "tgt_feats")
+            ptrs = (tx.data_ptr(), tf.data_ptr())
+        if tf.shape[0] != tx.shape[0] or tx.shape[0] == 0:
+            raise ValueError(f"Invalid shape: {tx.shape[0]} points vs {tf.shape[0]} descriptors")
+        self.m, self.d = int(tx.shape[0]), int(tf.shape[1])
+        h_ = C.c_void_p()
+        self.ctx.bind_stream()
+        _lib.check(self.ctx.lib.vfmreg_map_create(self.ctx.handle, C.c_void_p(ptrs[0]), C.c_void_p(ptrs[1]), self.m, self.d,
+                                                 self.flags, int(host[0]), C.byref(h_)), "vfmreg_map_create")
+        self.handle = h_
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.vfmreg_map_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.m
+
+    def match(self, queries, *, min_cos: Optional[float] = None, second: bool = True) -> MatchResult:
+        """Top-1 (+ runner-up value when ``second``) of every query row in the resident map.  With ``second=False`` a
+        ``min_cos`` gate may be handed to the search: queries that cannot reach it report index -1, similarity -inf."""
+        dev = torch.device("cuda", self.ctx.device)
+        q = _dev_f32(queries, dev, "queries", self.d)
+        n = q.shape[0]
+        if n == 0:
+            raise ValueError("Invalid shape: empty query set")
+        res = MatchResult(torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float32, device=dev),
+                          torch.empty(n, dtype=torch.float32, device=dev) if second else None)
+        self.ctx.bind_stream()
+        _lib.check(self.ctx.lib.vfmreg_map_match(self.ctx.handle, self.handle, _ptr(q), n,
+                                                float("nan") if (min_cos is None or second) else float(min_cos),
+                                                _ptr(res.idx01), _ptr(res.sim01), _ptr(res.sec01)), "vfmreg_map_match")
+        return res
+
+
+def register_scans(resident: ResidentMap, scans, *, min_cos: Optional[float] = 0.8, mutual: bool = False,
+                   ratio: Optional[float] = None, ransac_iters: int = 50000, inlier_thresh: float = 1e4, seed: int = 42,
+                   refit: bool = False):
+    """``register`` of every (source_pcd, src_feats) in ``scans`` against one ResidentMap (``vfmreg_register_scans``):
+    host arrays are uploaded on a copy stream while the previous scan is solved; CUDA tensors are enqueued back to back.
+    Returns a list of RegResult."""
+    if len(scans) == 0:
+        return []
+    p = _params(bool(resident.flags & _lib.NORMALIZE), min_cos, mutual, ratio, ransac_iters, inlier_thresh, seed, refit, "auto")
+    p.flags = (p.flags & ~0xF00) | (resident.flags & 0xF00)
+    if all(isinstance(x, torch.Tensor) and x.is_cuda for pr in scans for x in pr):
+        return _register_batch_device(resident.ctx, scans, p, resident)
+    return _register_batch_host(resident.ctx, scans, p, resident)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

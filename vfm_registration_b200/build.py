@@ -12,8 +12,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_obj")
-LIB = os.path.join(HERE, "libvfmreg_b200.so")
+# VFM_BUILD_SUFFIX=epi8 builds a second library (libvfmreg_b200_epi8.so, objects in _obj_epi8) next to the product one, for
+# A/B runs of a compile-time knob: VFMREG_LIB selects it at load time
+_SUFFIX = os.environ.get("VFM_BUILD_SUFFIX", "")
+OBJ = os.path.join(HERE, "_obj" + ("_" + _SUFFIX if _SUFFIX else ""))
+LIB = os.path.join(HERE, "libvfmreg_b200" + ("_" + _SUFFIX if _SUFFIX else "") + ".so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -72,7 +75,7 @@ def build_all(force: bool = False, verbose: bool = False) -> str:
         with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
             f.write(log)
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++"] + ARCH + objs + ["-lcuda"]
+        cmd = [nvcc, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++"] + ARCH + objs + ["-lcuda", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -37,15 +37,16 @@ def register_frame(points, voxel_map: "VoxelHashMap", initial_guess, max_corresp
         raise ValueError("Invalid shape")
     T0 = np.asarray(initial_guess, dtype=np.float64)
     if points.shape[1] == 3:
-        core = voxel_map._map3 if len(voxel_map._map3) else voxel_map._mapn   # GetCorrespondences: map_ first, else map_n_
-        return _voxel.register_frame(points, core, T0, max_correspondance_distance, kernel)
+        if voxel_map.empty():
+            return T0.copy()                                                 # "if (voxel_map.Empty()) return initial_guess" (Registration.cpp:150)
+        return _voxel.register_frame(points, voxel_map._map3, T0, max_correspondance_distance, kernel)
     if voxel_map.empty_n():
         return T0.copy()                                                     # "if (voxel_map.EmptyN()) return initial_guess"
     source = metrics.transform_pcl(points, T0)
     vox, idx = voxel_down_sample(source, 5.0, return_index=True)
     if vox.shape[0] < 100:                                                   # "Voxelized too sparse. Keep input."
         vox, idx = source, np.arange(points.shape[0])
-    m = api.match_nn(vox[:, 3:], voxel_map._feat, normalize=True, device=voxel_map._ctx.device)
+    m = voxel_map.resident().match(vox[:, 3:], min_cos=0.8, second=False)
     corr = api.filter_correspondences(m, min_cos=0.8, device=voxel_map._ctx.device).cpu().numpy()
     vfm_src = points[idx[corr[:, 0]], :3].astype(np.float64)                 # before the initial guess (applied on the device)
     vfm_tgt = voxel_map._xyzn[corr[:, 1]]
@@ -65,6 +66,7 @@ class VoxelHashMap:
         self._xyz3 = np.zeros((0, 3), dtype=np.float64)   # kept points of map_, insertion order
         self._xyzn = np.zeros((0, 3), dtype=np.float64)   # kept points of map_n_
         self._feat: Optional[torch.Tensor] = None          # their descriptors (device, float32)
+        self._resident: Optional[api.ResidentMap] = None   # map_n_ prepared for the descriptor search (built on first use)
 
     def clear(self) -> None:
         self.__init__(self.voxel_size, self.max_distance, self.max_points_per_voxel, self._ctx.device)
@@ -94,6 +96,18 @@ class VoxelHashMap:
         f_all = f_new if self._feat is None else torch.cat([self._feat, f_new], dim=0)
         assert f_all.shape[0] == k_old + points.shape[0]
         self._feat = f_all[idx.long()]
+        self._resident = None
+
+    def resident(self) -> "api.ResidentMap":
+        """map_n_ as a device-resident, renormalised descriptor map: prepared once, then searched by every
+        get_vfm_correspondences / registration call until the next add_points (the reference re-dumps and re-normalises the
+        whole map inside every GetVFMCorrespondences call, VoxelHashMap.cpp:465-482)."""
+        if self._feat is None:
+            raise ValueError("Invalid shape")
+        if self._resident is None:
+            xyz = torch.from_numpy(self._xyzn.astype(np.float32)).to(self._feat.device)
+            self._resident = api.ResidentMap(xyz, self._feat, device=self._ctx.device)
+        return self._resident
 
     def empty(self) -> bool:
         return self._xyz3.shape[0] == 0
@@ -125,12 +139,15 @@ class VoxelHashMap:
         """(src_xyz[K,3] f64, tgt_xyz[K,3] f64) of the queries whose top-1 cosine is >= the threshold, in query order.
         The parameter keeps the reference's (mis)name: it is the minimum cosine similarity (mapping.py:120-131)."""
         points = np.asarray(points)
-        if points.ndim != 2 or self._feat is None or points.shape[1] != 3 + self._feat.shape[1]:
+        if points.ndim != 2 or points.shape[1] <= 3:
             raise ValueError("Invalid shape")
         if points.shape[0] == 0 or self.empty_n():
             return np.zeros((0, 3)), np.zeros((0, 3))  # the reference has UB here (VoxelHashMap.cpp:464)
-        m = api.match_nn(points[:, 3:], self._feat, normalize=True, device=self._ctx.device)
-        corr = api.filter_correspondences(m, min_cos=float(max_correspondance_distance), device=self._ctx.device).cpu().numpy()
+        if points.shape[1] != 3 + self._feat.shape[1]:
+            raise ValueError("Invalid shape")
+        min_cos = float(max_correspondance_distance)
+        m = self.resident().match(points[:, 3:], min_cos=min_cos, second=False)
+        corr = api.filter_correspondences(m, min_cos=min_cos, device=self._ctx.device).cpu().numpy()
         return points[corr[:, 0], :3].astype(np.float64), self._xyzn[corr[:, 1]]
 
 
@@ -188,13 +205,14 @@ class RegistrationNode:
         else:
             vmap = self._new_map()
             vmap.add_points(voxel_map)                     # descriptor map, thinned
-            feat_map = vmap._feat
+            res_map = vmap.resident()                      # prepared once for both attempts below
             voxel_scan = self._voxel_scan(raw_scan)        # (n, 3 + D); its xyz is the reference's `voxel_scan`
             scan_xyz = voxel_scan[:, :3]
             r = None
+            skw = dict(min_cos=self.min_cosine, ransac_iters=self.ransac_iters, inlier_thresh=self.max_dist, seed=self.seed)
             for leaf in (5.0, 1.0):                        # "Voxelized too sparse, retrying with a larger voxel size"
                 q = voxel_down_sample(voxel_scan, leaf)
-                r = api.register(q[:, :3], vmap._xyzn.astype(np.float32), q[:, 3:], feat_map, **kw)
+                r = api.register_scans(res_map, [(np.ascontiguousarray(q[:, :3]), np.ascontiguousarray(q[:, 3:]))], **skw)[0]
                 if len(r.corr) >= 75:
                     break
         ransac_pose = r.T

@@ -1,9 +1,22 @@
 // extern "C" surface of libvfmreg_b200.so (see include/vfmreg_b200.h).
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+
+// A map kept resident on the device for the scans of one scene (registration_node.py:554-590 builds one local map per
+// scene and registers 3-5 scans against it): raw float32 coordinates + the renormalised fp32 / fp16 descriptor rows.
+struct vfmreg_map {
+  vfmreg_ctx* ctx = nullptr;
+  int64_t m = 0;
+  int32_t d = 0;
+  uint32_t flags = 0;       // VFMREG_NORMALIZE | VFMREG_ALGO_* the rows were prepared with
+  char* slab = nullptr;     // one allocation: [xyz | prepared rows]
+  float* xyz = nullptr;
+  vfm::Prepared prep;
+};
 
 namespace vfm {
 
@@ -16,7 +29,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+void nvtx_push(const char* name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
+
 int arena_reserve(vfmreg_ctx* ctx, size_t bytes) {
+  ctx->arena.limit = 0;
   if (bytes <= ctx->arena.cap) return VFMREG_OK;
   VFM_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ctx->arena.base) VFM_CUDA(cudaFree(ctx->arena.base));
@@ -70,6 +87,22 @@ static int ensure_pinned(vfmreg_ctx* ctx, size_t bytes) {
   return VFMREG_OK;
 }
 
+static int ensure_hbuf(vfmreg_ctx* ctx, size_t bytes, const char* who) {
+  if (bytes <= ctx->hbuf_cap) return VFMREG_OK;
+  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_stream) VFM_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  if (ctx->hbuf) VFM_CUDA(cudaFree(ctx->hbuf));
+  ctx->hbuf = nullptr;
+  ctx->hbuf_cap = 0;
+  cudaError_t e = cudaMalloc(&ctx->hbuf, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaMalloc(%zu) failed: %s", who, bytes, cudaGetErrorString(e));
+    return VFMREG_ERR_ALLOC;
+  }
+  ctx->hbuf_cap = bytes;
+  return VFMREG_OK;
+}
+
 static inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
 
 static bool use_tc(uint32_t flags, int d) {
@@ -81,20 +114,44 @@ static bool use_tc(uint32_t flags, int d) {
 
 static inline int padded_dim(int d, uint32_t flags) { return round_up(d, use_tc(flags, d) ? 64 : 16); }
 
-// scratch needed by match_nn_impl beyond the caller-visible outputs
-static size_t match_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int d, uint32_t flags) {
+// ---- prepared descriptor sets ----------------------------------------------------------------------------------------
+// [fp32 rows (rows x dp) | fp16 rows (tensor path) | non-zero flags (tensor path)]
+static size_t prepared_bytes(int64_t rows, int d, uint32_t flags) {
   const int dp = padded_dim(d, flags);
-  const bool mutual = (flags & VFMREG_MUTUAL) != 0;
-  size_t s = arena_bytes((size_t)n * dp, 4) + arena_bytes((size_t)m * dp, 4);
-  if (use_tc(flags, d)) {
-    s += arena_bytes((size_t)n * dp, 2) + arena_bytes((size_t)m * dp, 2) + arena_bytes(n, 1) + arena_bytes(m, 1);
-    s += match_tc_scratch(ctx, n, m);
-    if (mutual) s += match_tc_scratch(ctx, m, n);
-  } else {
-    s += match_simt_scratch(ctx, n, m);
-    if (mutual) s += match_simt_scratch(ctx, m, n);
-  }
+  size_t s = arena_bytes((size_t)rows * dp, 4);
+  if (use_tc(flags, d)) s += arena_bytes((size_t)rows * dp, 2) + arena_bytes(rows, 1);
   return s;
+}
+
+// renormalise (or copy) x (rows x d) into `mem` on the context's stream
+static int prepare_into(vfmreg_ctx* ctx, const float* x, int64_t rows, int d, uint32_t flags, char* mem, Prepared* out) {
+  const bool tc = use_tc(flags, d);
+  const int dp = padded_dim(d, flags);
+  float* f32 = reinterpret_cast<float*>(mem);
+  uint16_t* f16 = nullptr;
+  uint8_t* nz = nullptr;
+  if (tc) {
+    f16 = reinterpret_cast<uint16_t*>(mem + arena_bytes((size_t)rows * dp, 4));
+    nz = reinterpret_cast<uint8_t*>(mem + arena_bytes((size_t)rows * dp, 4) + arena_bytes((size_t)rows * dp, 2));
+  }
+  NvtxRange r("normalize_rows");
+  VFM_TRY(normalize_rows(ctx, x, rows, d, dp, (flags & VFMREG_NORMALIZE) != 0, f32, f16, nz));
+  out->f32 = f32;
+  out->f16 = f16;
+  out->nz = nz;
+  out->rows = rows;
+  out->dp = dp;
+  out->tc = tc;
+  return VFMREG_OK;
+}
+
+static int prepare_arena(vfmreg_ctx* ctx, const float* x, int64_t rows, int d, uint32_t flags, Prepared* out) {
+  char* mem = arena_take<char>(ctx, prepared_bytes(rows, d, flags));
+  if (!mem) {
+    set_error("scratch arena too small for %lld x %d descriptor rows", (long long)rows, d);
+    return VFMREG_ERR_ALLOC;
+  }
+  return prepare_into(ctx, x, rows, d, flags, mem, out);
 }
 
 // VFMREG_FULL_MUTUAL=1 keeps the full reverse search inside register() (A/B comparison; results are identical)
@@ -112,31 +169,58 @@ static size_t pruned_scratch(vfmreg_ctx* ctx, int64_t n, int d, uint32_t flags) 
          arena_bytes(n, 1) + arena_bytes(n, 4) * 2 + match_tc_scratch(ctx, n, n, true);
 }
 
-static int match_nn_impl(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, int64_t m, int32_t d, uint32_t flags,
-                         int32_t* idx01, float* sim01, float* sec01, int32_t* idx10, float* sim10, float* sec10,
-                         const vfmreg_register_params* prune = nullptr, int32_t* corr = nullptr, int32_t* count = nullptr) {
-  const bool tc = use_tc(flags, d);
-  const int dp = padded_dim(d, flags);
-  float* an = arena_take<float>(ctx, (size_t)n * dp);
-  float* bn = arena_take<float>(ctx, (size_t)m * dp);
-  uint16_t *ah = nullptr, *bh = nullptr;
-  uint8_t *nza = nullptr, *nzb = nullptr;
-  if (tc) {
-    ah = arena_take<uint16_t>(ctx, (size_t)n * dp);
-    bh = arena_take<uint16_t>(ctx, (size_t)m * dp);
-    nza = arena_take<uint8_t>(ctx, n);
-    nzb = arena_take<uint8_t>(ctx, m);
+// scratch of the searches of one (a, b) pair beyond the prepared rows and the caller-visible outputs
+static size_t search_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int d, uint32_t flags, bool pruned) {
+  const bool mutual = (flags & VFMREG_MUTUAL) != 0;
+  size_t s = 0;
+  if (use_tc(flags, d)) {
+    s += match_tc_scratch(ctx, n, m);
+    if (pruned) s += pruned_scratch(ctx, n, d, flags);
+    else if (mutual) s += match_tc_scratch(ctx, m, n);
+  } else {
+    s += match_simt_scratch(ctx, n, m);
+    if (mutual) s += match_simt_scratch(ctx, m, n);
   }
-  if (!an || !bn || (tc && (!ah || !bh || !nza || !nzb))) {
-    set_error("match_nn: scratch arena too small");
+  return s;
+}
+
+// both searches with all six outputs (the public match_nn)
+static int search_full(vfmreg_ctx* ctx, const Prepared& A, const Prepared& B, uint32_t flags, int32_t* idx01, float* sim01,
+                       float* sec01, int32_t* idx10, float* sim10, float* sec10, float floor = NAN) {
+  if (flags & VFMREG_MUTUAL) VFM_CHECK_ARG(idx10, "match_nn: VFMREG_MUTUAL needs idx10");
+  if (A.tc) {
+    VFM_TRY(match_tc(ctx, A.f32, A.f16, A.nz, A.rows, B.f32, B.f16, B.rows, A.dp, idx01, sim01, sec01, nullptr, nullptr, floor));
+    if (flags & VFMREG_MUTUAL)
+      VFM_TRY(match_tc(ctx, B.f32, B.f16, B.nz, B.rows, A.f32, A.f16, A.rows, A.dp, idx10, sim10, sec10));
+  } else {
+    VFM_TRY(match_simt(ctx, A.f32, A.rows, B.f32, B.rows, A.dp, idx01, sim01, sec01));
+    if (flags & VFMREG_MUTUAL) VFM_TRY(match_simt(ctx, B.f32, B.rows, A.f32, A.rows, A.dp, idx10, sim10, sec10));
+  }
+  return VFMREG_OK;
+}
+
+// register(): forward search -> gate -> (mutual check) -> ordered correspondence list on the device.
+// A caller that gates on the cosine and does not need the runner-up hands the gate to the candidate search as a recording
+// floor: queries that cannot reach it report "no match" instead of their (rejected anyway) best.
+static int search_and_filter(vfmreg_ctx* ctx, const Prepared& A, const Prepared& B, const vfmreg_register_params* p, int32_t* corr,
+                             int32_t* count) {
+  const int64_t n = A.rows, m = B.rows;
+  const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
+  const bool use_ratio = !(p->ratio != p->ratio);
+  const bool pruned = A.tc && mutual && n <= m && !g_full_mutual;
+  const float floor = use_ratio ? NAN : p->min_cos;   // NAN when there is no gate either
+  int32_t* idx01 = arena_take<int32_t>(ctx, n);
+  float* sim01 = arena_take<float>(ctx, n);
+  float* sec01 = use_ratio ? arena_take<float>(ctx, n) : nullptr;
+  int32_t* idx10 = (mutual && !pruned) ? arena_take<int32_t>(ctx, m) : nullptr;
+  if (!idx01 || !sim01 || (use_ratio && !sec01) || (mutual && !pruned && !idx10)) {
+    set_error("register: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
-  const int norm = (flags & VFMREG_NORMALIZE) != 0;
-  VFM_TRY(normalize_rows(ctx, a, n, d, dp, norm, an, ah, nza));
-  VFM_TRY(normalize_rows(ctx, b, m, d, dp, norm, bn, bh, nzb));
-  if (prune) {
-    // register(): forward search, gate (cosine / ratio) -> candidate list (i, j) in query order, reverse search over the
-    // listed map rows only, then keep the candidates whose map row points back at them
+  if (pruned) {
+    // forward search, gate (cosine / ratio) -> candidate list (i, j) in query order, reverse search over the listed map
+    // rows only, then keep the candidates whose map row points back at them
+    const int dp = A.dp;
     int32_t* cand = arena_take<int32_t>(ctx, (size_t)n * 2);
     int32_t* cand_count = arena_take<int32_t>(ctx, 1);
     float* sel32 = arena_take<float>(ctx, (size_t)n * dp);
@@ -148,28 +232,396 @@ static int match_nn_impl(vfmreg_ctx* ctx, const float* a, int64_t n, const float
       set_error("register: scratch arena too small");
       return VFMREG_ERR_ALLOC;
     }
-    VFM_TRY(match_tc(ctx, an, ah, nza, n, bn, bh, m, dp, idx01, sim01, sec01));
-    VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, nullptr, n, prune->min_cos, prune->ratio, 0, cand, cand_count));
-    VFM_TRY(gather_rows(ctx, cand, cand_count, n, 1, dp, bn, bh, nzb, sel32, sel16, selnz, sim01, selsim));
+    VFM_TRY(match_tc(ctx, A.f32, A.f16, A.nz, n, B.f32, B.f16, m, dp, idx01, sim01, sec01, nullptr, nullptr, floor));
+    NvtxRange r("mutual_check");
+    VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, nullptr, n, p->min_cos, p->ratio, 0, cand, cand_count));
+    VFM_TRY(gather_rows(ctx, cand, cand_count, n, 1, dp, B.f32, B.f16, B.nz, sel32, sel16, selnz, sim01, selsim));
     // <b_j, a_i> has the same canonical value as <a_i, b_j> = sim01[i]: a lower bound of row j's best that starts the
     // candidate recording near the answer
-    VFM_TRY(match_tc(ctx, sel32, sel16, selnz, n, an, ah, n, dp, back, nullptr, nullptr, cand_count, selsim));
+    VFM_TRY(match_tc(ctx, sel32, sel16, selnz, n, A.f32, A.f16, n, dp, back, nullptr, nullptr, cand_count, selsim));
     return filter_mutual_list(ctx, cand, cand_count, back, n, corr, count);
   }
-  if (flags & VFMREG_MUTUAL) VFM_CHECK_ARG(idx10, "match_nn: VFMREG_MUTUAL needs idx10");
-  if (tc) {
-    VFM_TRY(match_tc(ctx, an, ah, nza, n, bn, bh, m, dp, idx01, sim01, sec01));
-    if (flags & VFMREG_MUTUAL) VFM_TRY(match_tc(ctx, bn, bh, nzb, m, an, ah, n, dp, idx10, sim10, sec10));
-  } else {
-    VFM_TRY(match_simt(ctx, an, n, bn, m, dp, idx01, sim01, sec01));
-    if (flags & VFMREG_MUTUAL) VFM_TRY(match_simt(ctx, bn, m, an, n, dp, idx10, sim10, sec10));
-  }
-  return VFMREG_OK;
+  VFM_TRY(search_full(ctx, A, B, p->flags, idx01, sim01, sec01, idx10, nullptr, nullptr, floor));
+  NvtxRange r("filter_corr");
+  return filter_corr(ctx, idx01, sim01, sec01, idx10, n, p->min_cos, p->ratio, mutual, corr, count);
 }
 
 }  // namespace vfm
 
 using namespace vfm;
+
+struct RegOut {
+  double* T;        // device, 16
+  int64_t* stats;   // device, 8 (stats[0..3] + correspondence count as int32 at [4])
+  int32_t* corr;    // device, n x 2
+  uint8_t* mask;    // device, n
+};
+
+// scratch of one scan against an already prepared map
+static size_t scan_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p) {
+  const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
+  const bool pruned = prune_mutual(n, m, d, p->flags);
+  return prepared_bytes(n, d, p->flags) + search_scratch(ctx, n, m, d, p->flags, pruned) + arena_bytes(n, 4) * 3 +
+         ((mutual && !pruned) ? arena_bytes(m, 4) : 0) + ransac_scratch((int32_t)n, p->n_hyp) + arena_bytes((size_t)n * 2, 4) +
+         arena_bytes(n, 1) + arena_bytes(16, 8) + arena_bytes(8, 8) + 4096;
+}
+
+// Enqueue one scan against a prepared map on ctx->stream (no host synchronisation).  The arena must already be reserved.
+static int scan_enqueue(vfmreg_ctx* ctx, const float* src_xyz, const float* src_feats, int64_t n, int32_t d, const float* tgt_xyz,
+                        const Prepared& B, const vfmreg_register_params* p, const int32_t* sample_idx, const RegOut& out) {
+  Prepared A;
+  VFM_TRY(prepare_arena(ctx, src_feats, n, d, p->flags, &A));
+  int32_t* count = reinterpret_cast<int32_t*>(out.stats + 4);
+  VFM_TRY(search_and_filter(ctx, A, B, p, out.corr, count));
+  NvtxRange r("ransac");
+  return ransac_solve(ctx, src_xyz, tgt_xyz, 0, out.corr, count, (int32_t)n, sample_idx, p->n_hyp, p->seed, p->inlier_thresh,
+                      p->refit, out.T, nullptr, nullptr, out.mask, out.stats);
+}
+
+static void fill_result(vfmreg_register_result* result, const char* pin, double thresh) {
+  memcpy(result->T, pin, 16 * sizeof(double));
+  const int64_t* st = reinterpret_cast<const int64_t*>(pin + 128);
+  result->best_hyp = st[0];
+  result->n_inliers = st[1];
+  result->sumq = st[2];
+  result->n_corr = st[3];
+  result->fitness = st[3] > 0 ? (double)st[1] / (double)st[3] : 0.0;
+  const double tau2 = thresh * thresh;
+  result->rmse = st[1] > 0 ? sqrt(((double)st[2] / 1099511627776.0) * tau2 / (double)st[1]) : 0.0;
+}
+
+// VFMREG_MATCH_STREAMS=0 keeps the candidate-search kernels on their lane's stream (A/B comparison)
+static bool g_match_streams = [] { const char* e = getenv("VFMREG_MATCH_STREAMS"); return !(e && e[0] == '0'); }();
+
+static int ensure_lanes(vfmreg_ctx* ctx, int lanes) {
+  if (!ctx->ev_fork) VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  if (!ctx->match_stream_owned[0]) {
+    int lo = 0, hi = 0;
+    VFM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
+    for (int i = 0; i < 2; ++i) VFM_CUDA(cudaStreamCreateWithPriority(&ctx->match_stream_owned[i], cudaStreamNonBlocking, hi));
+    for (int i = 0; i < vfmreg_ctx::MATCH_EVENTS; ++i) VFM_CUDA(cudaEventCreateWithFlags(&ctx->match_ev[i], cudaEventDisableTiming));
+  }
+  for (int l = 1; l < lanes; ++l) {
+    if (ctx->lane_stream[l]) continue;
+    VFM_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+    VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming));
+  }
+  return VFMREG_OK;
+}
+
+static int ensure_map_events(vfmreg_ctx* ctx, int count) {
+  if (count <= ctx->map_ev_cap) return VFMREG_OK;
+  cudaEvent_t* ev = static_cast<cudaEvent_t*>(realloc(ctx->map_ev, sizeof(cudaEvent_t) * count));
+  if (!ev) {
+    set_error("out of host memory");
+    return VFMREG_ERR_ALLOC;
+  }
+  ctx->map_ev = ev;
+  for (int i = ctx->map_ev_cap; i < count; ++i) {
+    ctx->map_ev[i] = nullptr;
+    VFM_CUDA(cudaEventCreateWithFlags(&ctx->map_ev[i], cudaEventDisableTiming));
+    ctx->map_ev_cap = i + 1;
+  }
+  return VFMREG_OK;
+}
+
+static int ensure_copy_stream(vfmreg_ctx* ctx) {
+  if (ctx->copy_stream) return VFMREG_OK;
+  VFM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+    VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+    VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_target_free[i], cudaEventDisableTiming));
+  }
+  return VFMREG_OK;
+}
+
+// Restores the context's stream when a batch entry point leaves (also on an error return in the middle of a batch).
+struct StreamGuard {
+  vfmreg_ctx* ctx;
+  cudaStream_t saved;
+  explicit StreamGuard(vfmreg_ctx* c) : ctx(c), saved(c->stream) {}
+  ~StreamGuard() {
+    ctx->stream = saved;
+    ctx->match_stream[0] = ctx->match_stream[1] = nullptr;
+    ctx->arena.limit = 0;
+  }
+};
+
+static int check_register_args(vfmreg_ctx* ctx, const void* a, const void* b, const void* c, const void* e, int64_t n,
+                               int64_t m, int32_t d, const vfmreg_register_params* p, const void* r) {
+  VFM_CHECK_ARG(ctx, "null context");
+  VFM_CHECK_ARG(a && b && c && e && p && r, "register: null pointer");
+  VFM_CHECK_ARG(n > 0 && m > 0 && d > 0, "register: empty input (n=%lld m=%lld d=%d)", (long long)n, (long long)m, d);
+  VFM_CHECK_ARG(n < (1LL << 30) && m < (1LL << 30), "register: more than 2^30 points");
+  VFM_CHECK_ARG(p->n_hyp > 0, "register: n_hyp must be positive");
+  VFM_CHECK_ARG(p->inlier_thresh > 0, "register: inlier_thresh must be > 0");
+  return VFMREG_OK;
+}
+
+// One entry of a batch: a scan, and the map it is registered against -- either raw arrays (prepared inside the call; a
+// run of consecutive pairs with the same tgt_feats / tgt_xyz / m shares one preparation) or a resident map.
+struct BatchView {
+  int32_t n_pairs;
+  const float* const* src_xyz;
+  const float* const* src_feats;
+  const int64_t* n;
+  const float* const* tgt_xyz;     // null when `map` is set
+  const float* const* tgt_feats;
+  const int64_t* m;
+  const vfmreg_map* map;           // resident map shared by every pair, or null
+  int32_t d;
+  const int32_t* const* sample_idx;
+  int32_t* const* corr_out;
+  uint8_t* const* mask_out;
+  int64_t m_of(int i) const { return map ? map->m : m[i]; }
+  bool same_target(int i, int j) const {
+    return map || (tgt_feats[i] == tgt_feats[j] && tgt_xyz[i] == tgt_xyz[j] && m[i] == m[j]);
+  }
+};
+
+static int check_batch(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_params* p, const vfmreg_register_result* results,
+                       size_t* scratch, int64_t* n_max, size_t* target_bytes, int* n_runs) {
+  VFM_CHECK_ARG(ctx && b.n_pairs > 0 && b.src_xyz && b.src_feats && b.n && p && results, "register batch: null pointer / empty batch");
+  VFM_CHECK_ARG(b.map || (b.tgt_xyz && b.tgt_feats && b.m), "register batch: null target arrays");
+  if (b.map) VFM_CHECK_ARG(b.map->ctx == ctx && b.map->d == b.d, "register_scans: the map belongs to another context or has %d-d descriptors", b.map->d);
+  *scratch = 0;
+  *n_max = 0;
+  *target_bytes = 0;
+  *n_runs = 0;
+  for (int i = 0; i < b.n_pairs; ++i) {
+    const int64_t m = b.m_of(i);
+    VFM_TRY(check_register_args(ctx, b.src_xyz[i], b.map ? (const void*)b.map : (const void*)b.tgt_xyz[i], b.src_feats[i],
+                                b.map ? (const void*)b.map : (const void*)b.tgt_feats[i], b.n[i], m, b.d, p, results));
+    const size_t sc = scan_scratch(ctx, b.n[i], m, b.d, p);
+    *scratch = sc > *scratch ? sc : *scratch;
+    *n_max = b.n[i] > *n_max ? b.n[i] : *n_max;
+    if (!b.map) {
+      const size_t tb = prepared_bytes(m, b.d, p->flags);
+      *target_bytes = tb > *target_bytes ? tb : *target_bytes;
+      if (i == 0 || !b.same_target(i, i - 1)) *n_runs += 1;
+    }
+  }
+  return VFMREG_OK;
+}
+
+// ---- device-resident inputs: pairs spread over `lanes` streams, prepared maps in a small ring of slots ------------------
+static int batch_device(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_params* params, vfmreg_register_result* results) {
+  size_t scratch = 0, target_bytes = 0;
+  int64_t n_max = 0;
+  int n_runs = 0;
+  VFM_TRY(check_batch(ctx, b, params, results, &scratch, &n_max, &target_bytes, &n_runs));
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  const int n_pairs = b.n_pairs;
+  const int lanes = ctx->lanes < n_pairs ? ctx->lanes : n_pairs;
+  const int ring = b.map ? 0 : (n_runs < lanes + 2 ? n_runs : lanes + 2);   // prepared-map slots
+  // scratch arena: [per-pair (T, stats) slots | prepared-map ring | per lane: fallback corr/mask + per-scan scratch]
+  const size_t slots_bytes = (size_t)n_pairs * 256;
+  const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
+  const size_t lane_bytes = out_bytes + scratch + 4096;
+  arena_reset(ctx);
+  VFM_TRY(arena_reserve(ctx, slots_bytes + (size_t)ring * target_bytes + lanes * lane_bytes + 8192));
+  VFM_TRY(ensure_pinned(ctx, slots_bytes));
+  char* slots = arena_take<char>(ctx, slots_bytes);
+  char* ring_mem = ring ? arena_take<char>(ctx, (size_t)ring * target_bytes) : nullptr;
+  if (!slots || (ring && !ring_mem)) {
+    set_error("register_batch: scratch arena too small");
+    return VFMREG_ERR_ALLOC;
+  }
+  const size_t mark = ctx->arena.off;
+  StreamGuard guard(ctx);
+  cudaStream_t lane_streams[vfmreg_ctx::MAX_LANES];
+  for (int l = 0; l < vfmreg_ctx::MAX_LANES; ++l) lane_streams[l] = ctx->stream;
+  if (lanes > 1) {
+    VFM_TRY(ensure_lanes(ctx, lanes));
+    VFM_CUDA(cudaEventRecord(ctx->ev_fork, guard.saved));          // inputs are ready in the caller's stream order
+    for (int l = 1; l < lanes; ++l) {
+      lane_streams[l] = ctx->lane_stream[l];
+      VFM_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
+    }
+    if (g_match_streams) {
+      ctx->match_stream[0] = ctx->match_stream_owned[0];
+      ctx->match_stream[1] = ctx->match_stream_owned[1];
+    }
+  }
+  // ring slot s: event [s * (1 + MAX_LANES)] = "prepared", events [.. + 1 + l] = "lane l is done with the slot's current map"
+  constexpr int EV_PER_SLOT = 1 + vfmreg_ctx::MAX_LANES;
+  if (ring) VFM_TRY(ensure_map_events(ctx, ring * EV_PER_SLOT));
+  uint32_t slot_lanes[vfmreg_ctx::MAX_LANES + 2] = {};   // lanes that used the slot's current map
+  Prepared slot_prep[vfmreg_ctx::MAX_LANES + 2];
+  int run = -1;
+  for (int i = 0; i < n_pairs; ++i) {
+    const int lane = i % lanes;
+    ctx->stream = lane_streams[lane];
+    const Prepared* B = b.map ? &b.map->prep : nullptr;
+    const float* tgt_xyz = b.map ? b.map->xyz : b.tgt_xyz[i];
+    int slot = -1;
+    if (!b.map) {
+      const bool first = (i == 0) || !b.same_target(i, i - 1);
+      if (first) ++run;
+      slot = run % ring;
+      cudaEvent_t* ev = ctx->map_ev + slot * EV_PER_SLOT;
+      if (first) {
+        // the slot's previous map may still be in use on other lanes
+        for (int l = 0; l < lanes; ++l)
+          if ((slot_lanes[slot] >> l) & 1u) VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ev[1 + l], 0));
+        slot_lanes[slot] = 0;
+        VFM_TRY(prepare_into(ctx, b.tgt_feats[i], b.m[i], b.d, params->flags, ring_mem + (size_t)slot * target_bytes, &slot_prep[slot]));
+        VFM_CUDA(cudaEventRecord(ev[0], ctx->stream));
+      } else {
+        VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ev[0], 0));
+      }
+      B = &slot_prep[slot];
+    }
+    // every pair of a lane reuses the lane's region (stream order); a pair may not run past its lane's end
+    ctx->arena.off = mark + (size_t)lane * lane_bytes;
+    ctx->arena.limit = ctx->arena.off + lane_bytes;
+    int32_t* corr_fb = arena_take<int32_t>(ctx, (size_t)n_max * 2);
+    uint8_t* mask_fb = arena_take<uint8_t>(ctx, n_max);
+    if (!corr_fb || !mask_fb) {
+      set_error("register_batch: scratch arena too small");
+      return VFMREG_ERR_ALLOC;
+    }
+    RegOut out;
+    out.corr = (b.corr_out && b.corr_out[i]) ? b.corr_out[i] : corr_fb;
+    out.mask = (b.mask_out && b.mask_out[i]) ? b.mask_out[i] : mask_fb;
+    out.T = (double*)(slots + (size_t)i * 256);
+    out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
+    VFM_TRY(scan_enqueue(ctx, b.src_xyz[i], b.src_feats[i], b.n[i], b.d, tgt_xyz, *B, params,
+                         b.sample_idx ? b.sample_idx[i] : nullptr, out));
+    if (slot >= 0) {
+      VFM_CUDA(cudaEventRecord(ctx->map_ev[slot * EV_PER_SLOT + 1 + lane], ctx->stream));
+      slot_lanes[slot] |= 1u << lane;
+    }
+  }
+  ctx->stream = guard.saved;
+  ctx->arena.limit = 0;
+  ctx->match_stream[0] = ctx->match_stream[1] = nullptr;   // every search was handed back to its lane by an event
+  for (int l = 1; l < lanes; ++l) {
+    VFM_CUDA(cudaEventRecord(ctx->ev_join[l], ctx->lane_stream[l]));
+    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
+  }
+  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, slots_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_pairs; ++i) fill_result(results + i, static_cast<const char*>(ctx->pinned) + (size_t)i * 256, params->inlier_thresh);
+  return VFMREG_OK;
+}
+
+// ---- host buffers: a copy stream uploads scan i+1 (and the next map) while scan i is matched and solved --------------------
+// Device staging (persistent, grown on demand): 2 raw map stages (fp32 descriptors as uploaded), 2 target slots (map xyz +
+// prepared rows), 2 scan stages (xyz + descriptors + sample indices), 2 (corr, mask) output stages, per-pair result slots.
+static int batch_host(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_params* params, vfmreg_register_result* results) {
+  size_t scratch = 0, target_bytes = 0;
+  int64_t n_max = 0;
+  int n_runs = 0;
+  VFM_TRY(check_batch(ctx, b, params, results, &scratch, &n_max, &target_bytes, &n_runs));
+  const int n_pairs = b.n_pairs, d = b.d;
+  size_t scan_stage = 0, raw_stage = 0, xyz_stage = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    const size_t s = arena_bytes((size_t)b.n[i] * 3, 4) + arena_bytes((size_t)b.n[i] * d, 4) +
+                     (b.sample_idx ? arena_bytes((size_t)params->n_hyp * 3, 4) : 0);
+    scan_stage = s > scan_stage ? s : scan_stage;
+    if (!b.map) {
+      const size_t r = arena_bytes((size_t)b.m[i] * d, 4), x = arena_bytes((size_t)b.m[i] * 3, 4);
+      raw_stage = r > raw_stage ? r : raw_stage;
+      xyz_stage = x > xyz_stage ? x : xyz_stage;
+    }
+  }
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  VFM_TRY(ensure_copy_stream(ctx));
+  const size_t slot_bytes = xyz_stage + target_bytes;
+  const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
+  const size_t o_raw = 0, o_slot = o_raw + 2 * raw_stage, o_scan = o_slot + 2 * slot_bytes, o_out = o_scan + 2 * scan_stage;
+  const size_t o_res = o_out + 2 * out_bytes, total = o_res + (size_t)n_pairs * 256;
+  VFM_TRY(ensure_hbuf(ctx, total, "register_batch_host"));
+  arena_reset(ctx);
+  VFM_TRY(arena_reserve(ctx, scratch));
+  VFM_TRY(ensure_pinned(ctx, (size_t)n_pairs * 256));
+  char* slots = ctx->hbuf + o_res;
+
+  struct Staged { float *sx, *sf; int32_t* si; };
+  auto scan_ptrs = [&](int i, int buf) {
+    char* p = ctx->hbuf + o_scan + (size_t)buf * scan_stage;
+    Staged s;
+    s.sx = (float*)p; p += arena_bytes((size_t)b.n[i] * 3, 4);
+    s.sf = (float*)p; p += arena_bytes((size_t)b.n[i] * d, 4);
+    s.si = (b.sample_idx && b.sample_idx[i]) ? (int32_t*)p : nullptr;
+    return s;
+  };
+  // maps are uploaded once per run of consecutive pairs that share them
+  auto enqueue_h2d = [&](int i, int run, bool first_of_run) -> int {
+    const int buf = i & 1;
+    if (first_of_run && !b.map) {
+      const int tb = run & 1;
+      if (run >= 2) VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_target_free[tb], 0));   // run - 2 has finished
+      char* slot = ctx->hbuf + o_slot + (size_t)tb * slot_bytes;
+      VFM_CUDA(cudaMemcpyAsync(slot, b.tgt_xyz[i], (size_t)b.m[i] * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+      VFM_CUDA(cudaMemcpyAsync(ctx->hbuf + o_raw + (size_t)tb * raw_stage, b.tgt_feats[i], (size_t)b.m[i] * d * 4,
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    if (i >= 2) VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));  // stage free again
+    const Staged s = scan_ptrs(i, buf);
+    VFM_CUDA(cudaMemcpyAsync(s.sx, b.src_xyz[i], (size_t)b.n[i] * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VFM_CUDA(cudaMemcpyAsync(s.sf, b.src_feats[i], (size_t)b.n[i] * d * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (s.si) VFM_CUDA(cudaMemcpyAsync(s.si, b.sample_idx[i], (size_t)params->n_hyp * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VFM_CUDA(cudaEventRecord(ctx->ev_ready[buf], ctx->copy_stream));
+    return VFMREG_OK;
+  };
+  auto is_first = [&](int i) { return !b.map && (i == 0 || !b.same_target(i, i - 1)); };
+  // the previous batch may still be reading the stages: order this batch's first copies after everything enqueued so far
+  VFM_CUDA(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
+  VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[0], 0));
+  int run_copy = -1, run = -1;
+  {
+    const bool f = is_first(0);
+    if (f) ++run_copy;
+    VFM_TRY(enqueue_h2d(0, run_copy, f));
+  }
+  Prepared prep[2];
+  for (int i = 0; i < n_pairs; ++i) {
+    const int buf = i & 1;
+    if (i + 1 < n_pairs) {   // overlaps with the compute of pair i
+      const bool f = is_first(i + 1);
+      if (f) ++run_copy;
+      VFM_TRY(enqueue_h2d(i + 1, run_copy, f));
+    }
+    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[buf], 0));
+    const Staged s = scan_ptrs(i, buf);
+    const Prepared* B = b.map ? &b.map->prep : nullptr;
+    const float* tgt_xyz = b.map ? b.map->xyz : nullptr;
+    int tb = 0;
+    if (!b.map) {
+      if (is_first(i)) {
+        ++run;
+        tb = run & 1;
+        char* slot = ctx->hbuf + o_slot + (size_t)tb * slot_bytes;
+        VFM_TRY(prepare_into(ctx, (const float*)(ctx->hbuf + o_raw + (size_t)tb * raw_stage), b.m[i], d, params->flags,
+                             slot + xyz_stage, &prep[tb]));
+      }
+      tb = run & 1;
+      B = &prep[tb];
+      tgt_xyz = (const float*)(ctx->hbuf + o_slot + (size_t)tb * slot_bytes);
+    }
+    RegOut out;
+    char* ob = ctx->hbuf + o_out + (size_t)buf * out_bytes;
+    out.corr = (int32_t*)ob;
+    out.mask = (uint8_t*)(ob + arena_bytes((size_t)n_max * 2, 4));
+    out.T = (double*)(slots + (size_t)i * 256);
+    out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
+    arena_reset(ctx);
+    VFM_TRY(scan_enqueue(ctx, s.sx, s.sf, b.n[i], d, tgt_xyz, *B, params, s.si, out));
+    VFM_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+    if (!b.map) VFM_CUDA(cudaEventRecord(ctx->ev_target_free[tb], ctx->stream));   // re-recorded by every pair of the run
+    if (b.corr_out && b.corr_out[i])
+      VFM_CUDA(cudaMemcpyAsync(b.corr_out[i], out.corr, (size_t)b.n[i] * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (b.mask_out && b.mask_out[i])
+      VFM_CUDA(cudaMemcpyAsync(b.mask_out[i], out.mask, (size_t)b.n[i], cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, (size_t)n_pairs * 256, cudaMemcpyDeviceToHost, ctx->stream));
+  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_pairs; ++i) fill_result(results + i, static_cast<const char*>(ctx->pinned) + (size_t)i * 256, params->inlier_thresh);
+  return VFMREG_OK;
+}
 
 extern "C" {
 
@@ -235,6 +687,7 @@ void vfmreg_destroy(vfmreg_ctx* ctx) {
     for (int i = 0; i < 2; ++i) {
       cudaEventDestroy(ctx->ev_ready[i]);
       cudaEventDestroy(ctx->ev_consumed[i]);
+      cudaEventDestroy(ctx->ev_target_free[i]);
     }
   }
   for (int l = 1; l < vfmreg_ctx::MAX_LANES; ++l) {
@@ -251,6 +704,9 @@ void vfmreg_destroy(vfmreg_ctx* ctx) {
     }
   for (int i = 0; i < vfmreg_ctx::MATCH_EVENTS; ++i)
     if (ctx->match_ev[i]) cudaEventDestroy(ctx->match_ev[i]);
+  for (int i = 0; i < ctx->map_ev_cap; ++i)
+    if (ctx->map_ev[i]) cudaEventDestroy(ctx->map_ev[i]);
+  free(ctx->map_ev);
   for (int g = 0; g < NUM_GROUPS; ++g) {
     for (int r = 0; r < vfmreg_ctx::EV_RING; ++r) {
       cudaEventDestroy(ctx->ev0[g][r]);
@@ -313,8 +769,11 @@ int vfmreg_match_nn(vfmreg_ctx* ctx, const float* a, int64_t n, const float* b, 
   VFM_CHECK_ARG(n > 0 && m > 0 && d > 0, "match_nn: empty input (n=%lld m=%lld d=%d)", (long long)n, (long long)m, d);
   VFM_CUDA(cudaSetDevice(ctx->device));
   arena_reset(ctx);
-  VFM_TRY(arena_reserve(ctx, match_scratch(ctx, n, m, d, flags)));
-  return match_nn_impl(ctx, a, n, b, m, d, flags, idx01, sim01, sec01, idx10, sim10, sec10);
+  VFM_TRY(arena_reserve(ctx, prepared_bytes(n, d, flags) + prepared_bytes(m, d, flags) + search_scratch(ctx, n, m, d, flags, false) + 4096));
+  Prepared A, B;
+  VFM_TRY(prepare_arena(ctx, a, n, d, flags, &A));
+  VFM_TRY(prepare_arena(ctx, b, m, d, flags, &B));
+  return search_full(ctx, A, B, flags, idx01, sim01, sec01, idx10, sim10, sec10);
 }
 
 int vfmreg_filter_correspondences(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const float* sec01,
@@ -337,352 +796,128 @@ int vfmreg_ransac(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int
                       counts, sumq, mask, stats);
 }
 
-struct RegOut {
-  double* T;        // device, 16
-  int64_t* stats;   // device, 8 (stats[0..3] + correspondence count as int32 at [4])
-  int32_t* corr;    // device, n x 2
-  uint8_t* mask;    // device, n
-};
-
-static size_t register_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p) {
-  const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
-  (void)mutual;
-  return match_scratch(ctx, n, m, d, p->flags) + (prune_mutual(n, m, d, p->flags) ? pruned_scratch(ctx, n, d, p->flags) : 0) +
-         ransac_scratch((int32_t)n, p->n_hyp) + arena_bytes(n, 4) * 3 + arena_bytes(m, 4) +
-         arena_bytes((size_t)n * 2, 4) + arena_bytes(n, 1) + arena_bytes(16, 8) + arena_bytes(8, 8) + 4096;
-}
-
-// Enqueue the whole path on ctx->stream (no host synchronisation).  The arena must already be reserved.
-static int register_enqueue(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
-                            const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p,
-                            const int32_t* sample_idx, const RegOut& out) {
-  const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
-  const bool use_ratio = !(p->ratio != p->ratio);
-  int32_t* idx01 = arena_take<int32_t>(ctx, n);
-  float* sim01 = arena_take<float>(ctx, n);
-  float* sec01 = arena_take<float>(ctx, n);
-  const bool pruned = prune_mutual(n, m, d, p->flags);
-  int32_t* idx10 = (mutual && !pruned) ? arena_take<int32_t>(ctx, m) : nullptr;
-  if (!idx01 || !sim01 || !sec01 || (mutual && !pruned && !idx10)) {
-    set_error("register: scratch arena too small");
-    return VFMREG_ERR_ALLOC;
-  }
-  int32_t* count = reinterpret_cast<int32_t*>(out.stats + 4);
-  if (pruned) {
-    VFM_TRY(match_nn_impl(ctx, src_feats, n, tgt_feats, m, d, p->flags, idx01, sim01, use_ratio ? sec01 : nullptr, nullptr,
-                          nullptr, nullptr, p, out.corr, count));
-  } else {
-    VFM_TRY(match_nn_impl(ctx, src_feats, n, tgt_feats, m, d, p->flags, idx01, sim01, use_ratio ? sec01 : nullptr, idx10,
-                          nullptr, nullptr));
-    VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, idx10, n, p->min_cos, p->ratio, mutual, out.corr, count));
-  }
-  return ransac_solve(ctx, src_xyz, tgt_xyz, 0, out.corr, count, (int32_t)n, sample_idx, p->n_hyp, p->seed, p->inlier_thresh,
-                      p->refit, out.T, nullptr, nullptr, out.mask, out.stats);
-}
-
-static void fill_result(vfmreg_register_result* result, const char* pin, double thresh) {
-  memcpy(result->T, pin, 16 * sizeof(double));
-  const int64_t* st = reinterpret_cast<const int64_t*>(pin + 128);
-  result->best_hyp = st[0];
-  result->n_inliers = st[1];
-  result->sumq = st[2];
-  result->n_corr = st[3];
-  result->fitness = st[3] > 0 ? (double)st[1] / (double)st[3] : 0.0;
-  const double tau2 = thresh * thresh;
-  result->rmse = st[1] > 0 ? sqrt(((double)st[2] / 1099511627776.0) * tau2 / (double)st[1]) : 0.0;
-}
-
-static int register_impl(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
-                         const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* p,
-                         const int32_t* sample_idx, int32_t* corr_dev, uint8_t* mask_dev, bool outputs_on_host,
-                         int32_t* corr_host, uint8_t* mask_host, vfmreg_register_result* result) {
-  VFM_TRY(arena_reserve(ctx, register_scratch(ctx, n, m, d, p)));
-  RegOut out;
-  out.corr = corr_dev ? corr_dev : arena_take<int32_t>(ctx, (size_t)n * 2);
-  out.mask = mask_dev ? mask_dev : arena_take<uint8_t>(ctx, n);
-  out.T = arena_take<double>(ctx, 16);
-  out.stats = arena_take<int64_t>(ctx, 8);
-  if (!out.corr || !out.mask || !out.T || !out.stats) {
-    set_error("register: scratch arena too small");
-    return VFMREG_ERR_ALLOC;
-  }
-  VFM_TRY(register_enqueue(ctx, src_xyz, tgt_xyz, src_feats, tgt_feats, n, m, d, p, sample_idx, out));
-  // small results -> pinned host staging -> caller
-  VFM_TRY(ensure_pinned(ctx, 256));
-  char* pin = static_cast<char*>(ctx->pinned);
-  VFM_CUDA(cudaMemcpyAsync(pin, out.T, 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  VFM_CUDA(cudaMemcpyAsync(pin + 128, out.stats, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (outputs_on_host) {
-    if (corr_host) VFM_CUDA(cudaMemcpyAsync(corr_host, out.corr, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (mask_host) VFM_CUDA(cudaMemcpyAsync(mask_host, out.mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  fill_result(result, pin, p->inlier_thresh);
-  return VFMREG_OK;
-}
-
-// VFMREG_MATCH_STREAMS=0 keeps the candidate-search kernels on their lane's stream (A/B comparison)
-static bool g_match_streams = [] { const char* e = getenv("VFMREG_MATCH_STREAMS"); return !(e && e[0] == '0'); }();
-
-static int ensure_lanes(vfmreg_ctx* ctx, int lanes) {
-  if (!ctx->ev_fork) VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-  if (!ctx->match_stream_owned[0]) {
-    int lo = 0, hi = 0;
-    VFM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
-    for (int i = 0; i < 2; ++i) VFM_CUDA(cudaStreamCreateWithPriority(&ctx->match_stream_owned[i], cudaStreamNonBlocking, hi));
-    for (int i = 0; i < vfmreg_ctx::MATCH_EVENTS; ++i) VFM_CUDA(cudaEventCreateWithFlags(&ctx->match_ev[i], cudaEventDisableTiming));
-  }
-  for (int l = 1; l < lanes; ++l) {
-    if (ctx->lane_stream[l]) continue;
-    VFM_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
-    VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming));
-  }
-  return VFMREG_OK;
-}
-
-// Restores the context's stream when a batch entry point leaves (also on an error return in the middle of a batch).
-struct StreamGuard {
-  vfmreg_ctx* ctx;
-  cudaStream_t saved;
-  explicit StreamGuard(vfmreg_ctx* c) : ctx(c), saved(c->stream) {}
-  ~StreamGuard() {
-    ctx->stream = saved;
-    ctx->match_stream[0] = ctx->match_stream[1] = nullptr;
-  }
-};
-
-static int check_register_args(vfmreg_ctx* ctx, const void* a, const void* b, const void* c, const void* e, int64_t n,
-                               int64_t m, int32_t d, const vfmreg_register_params* p, vfmreg_register_result* r) {
-  VFM_CHECK_ARG(ctx, "null context");
-  VFM_CHECK_ARG(a && b && c && e && p && r, "register: null pointer");
-  VFM_CHECK_ARG(n > 0 && m > 0 && d > 0, "register: empty input (n=%lld m=%lld d=%d)", (long long)n, (long long)m, d);
-  VFM_CHECK_ARG(n < (1LL << 30) && m < (1LL << 30), "register: more than 2^30 points");
-  VFM_CHECK_ARG(p->n_hyp > 0, "register: n_hyp must be positive");
-  VFM_CHECK_ARG(p->inlier_thresh > 0, "register: inlier_thresh must be > 0");
-  return VFMREG_OK;
-}
-
 int vfmreg_register(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
                     const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* params,
                     const int32_t* sample_idx, int32_t* corr_out, uint8_t* mask_out, vfmreg_register_result* result) {
-  VFM_TRY(check_register_args(ctx, src_xyz, tgt_xyz, src_feats, tgt_feats, n, m, d, params, result));
-  VFM_CUDA(cudaSetDevice(ctx->device));
-  arena_reset(ctx);
-  return register_impl(ctx, src_xyz, tgt_xyz, src_feats, tgt_feats, n, m, d, params, sample_idx, corr_out, mask_out, false,
-                       nullptr, nullptr, result);
+  const BatchView b{1, &src_xyz, &src_feats, &n, &tgt_xyz, &tgt_feats, &m, nullptr, d, sample_idx ? &sample_idx : nullptr,
+                    corr_out ? &corr_out : nullptr, mask_out ? &mask_out : nullptr};
+  return batch_device(ctx, b, params, result);
 }
 
 int vfmreg_register_host(vfmreg_ctx* ctx, const float* src_xyz, const float* tgt_xyz, const float* src_feats,
                          const float* tgt_feats, int64_t n, int64_t m, int32_t d, const vfmreg_register_params* params,
                          const int32_t* sample_idx, int32_t* corr_out, uint8_t* mask_out,
                          vfmreg_register_result* result) {
-  VFM_TRY(check_register_args(ctx, src_xyz, tgt_xyz, src_feats, tgt_feats, n, m, d, params, result));
-  VFM_CUDA(cudaSetDevice(ctx->device));
-  // device copies of the inputs live in a persistent buffer (grown on demand), separate from the scratch arena
-  const size_t b_sx = arena_bytes((size_t)n * 3, 4), b_tx = arena_bytes((size_t)m * 3, 4);
-  const size_t b_sf = arena_bytes((size_t)n * d, 4), b_tf = arena_bytes((size_t)m * d, 4);
-  const size_t b_si = sample_idx ? arena_bytes((size_t)params->n_hyp * 3, 4) : 0;
-  const size_t total = b_sx + b_tx + b_sf + b_tf + b_si;
-  if (total > ctx->hbuf_cap) {
-    VFM_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->hbuf) VFM_CUDA(cudaFree(ctx->hbuf));
-    ctx->hbuf = nullptr;
-    ctx->hbuf_cap = 0;
-    cudaError_t e = cudaMalloc(&ctx->hbuf, total);
-    if (e != cudaSuccess) {
-      set_error("register_host: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
-      return VFMREG_ERR_ALLOC;
-    }
-    ctx->hbuf_cap = total;
-  }
-  char* p = ctx->hbuf;
-  float* d_sx = (float*)p; p += b_sx;
-  float* d_tx = (float*)p; p += b_tx;
-  float* d_sf = (float*)p; p += b_sf;
-  float* d_tf = (float*)p; p += b_tf;
-  int32_t* d_si = sample_idx ? (int32_t*)p : nullptr;
-  VFM_CUDA(cudaMemcpyAsync(d_sx, src_xyz, (size_t)n * 3 * 4, cudaMemcpyHostToDevice, ctx->stream));
-  VFM_CUDA(cudaMemcpyAsync(d_tx, tgt_xyz, (size_t)m * 3 * 4, cudaMemcpyHostToDevice, ctx->stream));
-  VFM_CUDA(cudaMemcpyAsync(d_sf, src_feats, (size_t)n * d * 4, cudaMemcpyHostToDevice, ctx->stream));
-  VFM_CUDA(cudaMemcpyAsync(d_tf, tgt_feats, (size_t)m * d * 4, cudaMemcpyHostToDevice, ctx->stream));
-  if (sample_idx)
-    VFM_CUDA(cudaMemcpyAsync(d_si, sample_idx, (size_t)params->n_hyp * 3 * 4, cudaMemcpyHostToDevice, ctx->stream));
-  arena_reset(ctx);
-  return register_impl(ctx, d_sx, d_tx, d_sf, d_tf, n, m, d, params, d_si, nullptr, nullptr, true, corr_out, mask_out,
-                       result);
+  const BatchView b{1, &src_xyz, &src_feats, &n, &tgt_xyz, &tgt_feats, &m, nullptr, d, sample_idx ? &sample_idx : nullptr,
+                    corr_out ? &corr_out : nullptr, mask_out ? &mask_out : nullptr};
+  return batch_host(ctx, b, params, result);
 }
-
 
 int vfmreg_register_batch_host(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* src_xyz, const float* const* tgt_xyz,
                                const float* const* src_feats, const float* const* tgt_feats, const int64_t* n, const int64_t* m,
                                int32_t d, const vfmreg_register_params* params, const int32_t* const* sample_idx,
                                int32_t* const* corr_out, uint8_t* const* mask_out, vfmreg_register_result* results) {
-  VFM_CHECK_ARG(ctx && n_pairs > 0 && src_xyz && tgt_xyz && src_feats && tgt_feats && n && m && params && results,
-                "register_batch_host: null pointer / empty batch");
-  size_t stage_bytes = 0, scratch = 0;
-  int64_t n_max = 0;
-  for (int i = 0; i < n_pairs; ++i) {
-    VFM_TRY(check_register_args(ctx, src_xyz[i], tgt_xyz[i], src_feats[i], tgt_feats[i], n[i], m[i], d, params, results + i));
-    const size_t b = arena_bytes((size_t)n[i] * 3, 4) + arena_bytes((size_t)m[i] * 3, 4) + arena_bytes((size_t)n[i] * d, 4) +
-                     arena_bytes((size_t)m[i] * d, 4) + (sample_idx ? arena_bytes((size_t)params->n_hyp * 3, 4) : 0);
-    stage_bytes = b > stage_bytes ? b : stage_bytes;
-    const size_t sc = register_scratch(ctx, n[i], m[i], d, params);
-    scratch = sc > scratch ? sc : scratch;
-    n_max = n[i] > n_max ? n[i] : n_max;
-  }
-  VFM_CUDA(cudaSetDevice(ctx->device));
-  if (!ctx->copy_stream) {
-    VFM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
-      VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
-    }
-  }
-  // persistent device buffer: 2 input stages + 2 (corr, mask) output stages + per-pair (T, stats) slots
-  const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
-  const size_t total = 2 * stage_bytes + 2 * out_bytes + (size_t)n_pairs * 256;
-  if (total > ctx->hbuf_cap) {
-    VFM_CUDA(cudaStreamSynchronize(ctx->stream));
-    VFM_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-    if (ctx->hbuf) VFM_CUDA(cudaFree(ctx->hbuf));
-    ctx->hbuf = nullptr;
-    ctx->hbuf_cap = 0;
-    cudaError_t e = cudaMalloc(&ctx->hbuf, total);
-    if (e != cudaSuccess) {
-      set_error("register_batch_host: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
-      return VFMREG_ERR_ALLOC;
-    }
-    ctx->hbuf_cap = total;
-  }
-  arena_reset(ctx);
-  VFM_TRY(arena_reserve(ctx, scratch));
-  VFM_TRY(ensure_pinned(ctx, (size_t)n_pairs * 256));
-  char* slots = ctx->hbuf + 2 * stage_bytes + 2 * out_bytes;
-
-  struct Staged { float *sx, *tx, *sf, *tf; int32_t* si; };
-  auto stage_ptrs = [&](int i, int buf) {
-    char* p = ctx->hbuf + (size_t)buf * stage_bytes;
-    Staged s;
-    s.sx = (float*)p; p += arena_bytes((size_t)n[i] * 3, 4);
-    s.tx = (float*)p; p += arena_bytes((size_t)m[i] * 3, 4);
-    s.sf = (float*)p; p += arena_bytes((size_t)n[i] * d, 4);
-    s.tf = (float*)p; p += arena_bytes((size_t)m[i] * d, 4);
-    s.si = (sample_idx && sample_idx[i]) ? (int32_t*)p : nullptr;
-    return s;
-  };
-  auto enqueue_h2d = [&](int i) -> int {
-    const int buf = i & 1;
-    if (i >= 2) VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));  // stage free again
-    const Staged s = stage_ptrs(i, buf);
-    VFM_CUDA(cudaMemcpyAsync(s.sx, src_xyz[i], (size_t)n[i] * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    VFM_CUDA(cudaMemcpyAsync(s.tx, tgt_xyz[i], (size_t)m[i] * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    VFM_CUDA(cudaMemcpyAsync(s.sf, src_feats[i], (size_t)n[i] * d * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    VFM_CUDA(cudaMemcpyAsync(s.tf, tgt_feats[i], (size_t)m[i] * d * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    if (s.si) VFM_CUDA(cudaMemcpyAsync(s.si, sample_idx[i], (size_t)params->n_hyp * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    VFM_CUDA(cudaEventRecord(ctx->ev_ready[buf], ctx->copy_stream));
-    return VFMREG_OK;
-  };
-  // the previous batch may still be reading the stages: order this batch's first copies after everything enqueued so far
-  VFM_CUDA(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
-  VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[0], 0));
-  VFM_TRY(enqueue_h2d(0));
-  for (int i = 0; i < n_pairs; ++i) {
-    const int buf = i & 1;
-    if (i + 1 < n_pairs) VFM_TRY(enqueue_h2d(i + 1));  // overlaps with the compute of pair i
-    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[buf], 0));
-    const Staged s = stage_ptrs(i, buf);
-    RegOut out;
-    char* ob = ctx->hbuf + 2 * stage_bytes + (size_t)buf * out_bytes;
-    out.corr = (int32_t*)ob;
-    out.mask = (uint8_t*)(ob + arena_bytes((size_t)n_max * 2, 4));
-    out.T = (double*)(slots + (size_t)i * 256);
-    out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
-    arena_reset(ctx);
-    VFM_TRY(register_enqueue(ctx, s.sx, s.tx, s.sf, s.tf, n[i], m[i], d, params, s.si, out));
-    VFM_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
-    if (corr_out && corr_out[i])
-      VFM_CUDA(cudaMemcpyAsync(corr_out[i], out.corr, (size_t)n[i] * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (mask_out && mask_out[i]) VFM_CUDA(cudaMemcpyAsync(mask_out[i], out.mask, (size_t)n[i], cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, (size_t)n_pairs * 256, cudaMemcpyDeviceToHost, ctx->stream));
-  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < n_pairs; ++i) fill_result(results + i, static_cast<const char*>(ctx->pinned) + (size_t)i * 256, params->inlier_thresh);
-  return VFMREG_OK;
+  const BatchView b{n_pairs, src_xyz, src_feats, n, tgt_xyz, tgt_feats, m, nullptr, d, sample_idx, corr_out, mask_out};
+  return batch_host(ctx, b, params, results);
 }
-
 
 int vfmreg_register_batch(vfmreg_ctx* ctx, int32_t n_pairs, const float* const* src_xyz, const float* const* tgt_xyz,
                           const float* const* src_feats, const float* const* tgt_feats, const int64_t* n, const int64_t* m,
                           int32_t d, const vfmreg_register_params* params, const int32_t* const* sample_idx,
                           int32_t* const* corr_out, uint8_t* const* mask_out, vfmreg_register_result* results) {
-  VFM_CHECK_ARG(ctx && n_pairs > 0 && src_xyz && tgt_xyz && src_feats && tgt_feats && n && m && params && results,
-                "register_batch: null pointer / empty batch");
-  size_t scratch = 0;
-  int64_t n_max = 0;
-  for (int i = 0; i < n_pairs; ++i) {
-    VFM_TRY(check_register_args(ctx, src_xyz[i], tgt_xyz[i], src_feats[i], tgt_feats[i], n[i], m[i], d, params, results + i));
-    const size_t sc = register_scratch(ctx, n[i], m[i], d, params);
-    scratch = sc > scratch ? sc : scratch;
-    n_max = n[i] > n_max ? n[i] : n_max;
-  }
+  const BatchView b{n_pairs, src_xyz, src_feats, n, tgt_xyz, tgt_feats, m, nullptr, d, sample_idx, corr_out, mask_out};
+  return batch_device(ctx, b, params, results);
+}
+
+// ---- resident maps ---------------------------------------------------------------------------------------------------
+int vfmreg_map_create(vfmreg_ctx* ctx, const float* tgt_xyz, const float* tgt_feats, int64_t m, int32_t d, uint32_t flags,
+                      int32_t host_buffers, vfmreg_map** out) {
+  VFM_CHECK_ARG(ctx && out, "map_create: null pointer");
+  *out = nullptr;
+  VFM_CHECK_ARG(tgt_xyz && tgt_feats, "map_create: null pointer");
+  VFM_CHECK_ARG(m > 0 && m < (1LL << 30) && d > 0, "map_create: empty map (m=%lld d=%d)", (long long)m, d);
   VFM_CUDA(cudaSetDevice(ctx->device));
-  // scratch arena: [per-pair (T, stats) slots | per lane: fallback corr/mask + per-pair scratch (reused in stream order)]
-  const int lanes = ctx->lanes < n_pairs ? ctx->lanes : n_pairs;
-  const size_t slots_bytes = (size_t)n_pairs * 256;
-  const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
-  const size_t lane_bytes = out_bytes + scratch + 4096;
-  arena_reset(ctx);
-  VFM_TRY(arena_reserve(ctx, slots_bytes + lanes * lane_bytes + 4096));
-  VFM_TRY(ensure_pinned(ctx, slots_bytes));
-  char* slots = arena_take<char>(ctx, slots_bytes);
-  if (!slots) {
-    set_error("register_batch: scratch arena too small");
+  flags &= (VFMREG_NORMALIZE | VFMREG_ALGO_MASK);
+  const size_t b_xyz = arena_bytes((size_t)m * 3, 4), b_prep = prepared_bytes(m, d, flags);
+  vfmreg_map* map = new vfmreg_map();
+  cudaError_t e = cudaMalloc(&map->slab, b_xyz + b_prep);
+  if (e != cudaSuccess) {
+    delete map;
+    set_error("map_create: cudaMalloc(%zu) failed: %s", b_xyz + b_prep, cudaGetErrorString(e));
     return VFMREG_ERR_ALLOC;
   }
-  const size_t mark = ctx->arena.off;
-  StreamGuard guard(ctx);
-  cudaStream_t lane_streams[vfmreg_ctx::MAX_LANES];
-  for (int l = 0; l < vfmreg_ctx::MAX_LANES; ++l) lane_streams[l] = ctx->stream;
-  if (lanes > 1) {
-    VFM_TRY(ensure_lanes(ctx, lanes));
-    VFM_CUDA(cudaEventRecord(ctx->ev_fork, guard.saved));          // inputs are ready in the caller's stream order
-    for (int l = 1; l < lanes; ++l) {
-      lane_streams[l] = ctx->lane_stream[l];
-      VFM_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
+  map->ctx = ctx;
+  map->m = m;
+  map->d = d;
+  map->flags = flags;
+  map->xyz = reinterpret_cast<float*>(map->slab);
+  int rc = VFMREG_OK;
+  const float* feats_dev = tgt_feats;
+  do {
+    if (host_buffers) {
+      // raw descriptors pass through the scratch arena on their way to the prepared rows
+      arena_reset(ctx);
+      if ((rc = arena_reserve(ctx, arena_bytes((size_t)m * d, 4))) != VFMREG_OK) break;
+      float* raw = arena_take<float>(ctx, (size_t)m * d);
+      if (cudaMemcpyAsync(raw, tgt_feats, (size_t)m * d * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+          cudaMemcpyAsync(map->xyz, tgt_xyz, (size_t)m * 3 * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        set_error("map_create: host -> device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = VFMREG_ERR_CUDA;
+        break;
+      }
+      feats_dev = raw;
+    } else if (cudaMemcpyAsync(map->xyz, tgt_xyz, (size_t)m * 3 * 4, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+      set_error("map_create: device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = VFMREG_ERR_CUDA;
+      break;
     }
-    if (g_match_streams) {
-      ctx->match_stream[0] = ctx->match_stream_owned[0];
-      ctx->match_stream[1] = ctx->match_stream_owned[1];
+    if ((rc = prepare_into(ctx, feats_dev, m, d, flags, map->slab + b_xyz, &map->prep)) != VFMREG_OK) break;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {   // the map may be used from any stream afterwards
+      set_error("map_create: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = VFMREG_ERR_CUDA;
     }
+  } while (0);
+  if (rc != VFMREG_OK) {
+    cudaFree(map->slab);
+    delete map;
+    return rc;
   }
-  for (int i = 0; i < n_pairs; ++i) {
-    const int lane = i % lanes;
-    ctx->stream = lane_streams[lane];
-    ctx->arena.off = mark + (size_t)lane * lane_bytes;   // every pair of a lane reuses the lane's region (stream order)
-    int32_t* corr_fb = arena_take<int32_t>(ctx, (size_t)n_max * 2);
-    uint8_t* mask_fb = arena_take<uint8_t>(ctx, n_max);
-    if (!corr_fb || !mask_fb) {
-      set_error("register_batch: scratch arena too small");
-      return VFMREG_ERR_ALLOC;
-    }
-    RegOut out;
-    out.corr = (corr_out && corr_out[i]) ? corr_out[i] : corr_fb;
-    out.mask = (mask_out && mask_out[i]) ? mask_out[i] : mask_fb;
-    out.T = (double*)(slots + (size_t)i * 256);
-    out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
-    VFM_TRY(register_enqueue(ctx, src_xyz[i], tgt_xyz[i], src_feats[i], tgt_feats[i], n[i], m[i], d, params,
-                             sample_idx ? sample_idx[i] : nullptr, out));
-  }
-  ctx->stream = guard.saved;
-  ctx->match_stream[0] = ctx->match_stream[1] = nullptr;   // every search was handed back to its lane by an event
-  for (int l = 1; l < lanes; ++l) {
-    VFM_CUDA(cudaEventRecord(ctx->ev_join[l], ctx->lane_stream[l]));
-    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
-  }
-  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, slots_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < n_pairs; ++i) fill_result(results + i, static_cast<const char*>(ctx->pinned) + (size_t)i * 256, params->inlier_thresh);
+  *out = map;
   return VFMREG_OK;
+}
+
+void vfmreg_map_destroy(vfmreg_map* map) {
+  if (!map) return;
+  cudaSetDevice(map->ctx->device);
+  cudaDeviceSynchronize();
+  cudaFree(map->slab);
+  delete map;
+}
+
+int64_t vfmreg_map_size(const vfmreg_map* map) { return map ? map->m : 0; }
+
+int vfmreg_map_match(vfmreg_ctx* ctx, const vfmreg_map* map, const float* queries, int64_t n, float min_cos, int32_t* idx01,
+                     float* sim01, float* sec01) {
+  VFM_CHECK_ARG(ctx && map && queries && idx01, "map_match: null pointer");
+  VFM_CHECK_ARG(map->ctx == ctx, "map_match: the map belongs to another context");
+  VFM_CHECK_ARG(n > 0, "map_match: empty query set");
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  arena_reset(ctx);
+  VFM_TRY(arena_reserve(ctx, prepared_bytes(n, map->d, map->flags) + search_scratch(ctx, n, map->m, map->d, map->flags, false) + 4096));
+  Prepared A;
+  VFM_TRY(prepare_arena(ctx, queries, n, map->d, map->flags, &A));
+  return search_full(ctx, A, map->prep, map->flags, idx01, sim01, sec01, nullptr, nullptr, nullptr, sec01 ? NAN : min_cos);
+}
+
+int vfmreg_register_scans(vfmreg_ctx* ctx, const vfmreg_map* map, int32_t n_scans, const float* const* src_xyz,
+                          const float* const* src_feats, const int64_t* n, const vfmreg_register_params* params,
+                          const int32_t* const* sample_idx, int32_t host_buffers, int32_t* const* corr_out, uint8_t* const* mask_out,
+                          vfmreg_register_result* results) {
+  VFM_CHECK_ARG(ctx && map, "register_scans: null pointer");
+  VFM_CHECK_ARG(params && ((params->flags ^ map->flags) & (VFMREG_NORMALIZE | VFMREG_ALGO_MASK)) == 0,
+                "register_scans: the map was prepared with other NORMALIZE / ALGO flags");
+  const BatchView b{n_scans, src_xyz, src_feats, n, nullptr, nullptr, nullptr, map, map->d, sample_idx, corr_out, mask_out};
+  return host_buffers ? batch_host(ctx, b, params, results) : batch_device(ctx, b, params, results);
 }
 
 }  // extern "C"

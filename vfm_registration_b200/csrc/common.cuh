@@ -1,6 +1,7 @@
 // Shared internals of libvfmreg_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -43,6 +44,18 @@ struct Arena {
   char* base = nullptr;
   size_t cap = 0;
   size_t off = 0;
+  size_t limit = 0;   // end of the region the current carve may use (0 = the whole slab): a batch lane must not run into the next
+};
+
+// A descriptor set ready for the search: renormalised fp32 rows (rows x dp, zero padded), and on the tensor-core path
+// their fp16 copy and per-row non-zero flags.
+struct Prepared {
+  const float* f32 = nullptr;
+  const uint16_t* f16 = nullptr;
+  const uint8_t* nz = nullptr;
+  int64_t rows = 0;
+  int dp = 0;
+  bool tc = false;
 };
 
 }  // namespace vfm
@@ -70,7 +83,7 @@ struct vfmreg_ctx {
   size_t hbuf_cap = 0;
   // register_batch_host: second stream + events for the double-buffered H2D / compute pipeline
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_ready[2] = {}, ev_consumed[2] = {};
+  cudaEvent_t ev_ready[2] = {}, ev_consumed[2] = {}, ev_target_free[2] = {};
   // batch entry points: a second compute lane.  Consecutive pairs alternate between the caller's stream and this one, so
   // the latency-bound small kernels of one pair (filters, re-rank, RANSAC) run beside the other pair's match kernel.
   static constexpr int MAX_LANES = 8;
@@ -83,6 +96,13 @@ struct vfmreg_ctx {
   cudaStream_t match_stream_owned[2] = {};
   cudaEvent_t match_ev[MATCH_EVENTS] = {};
   int match_ev_head = 0;
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per context, not per process
+  bool tc_attr_set = false;
+  uint64_t gemm_attr_mask = 0;     // vit_gemm_kernel<EPI, BN> instantiations already opted in
+  size_t attention_smem_attr = 0;  // largest dynamic shared memory size attention_kernel was opted in for
+  // events that order the pairs of a batch after the preparation of the map they share (grown on demand)
+  cudaEvent_t* map_ev = nullptr;
+  int map_ev_cap = 0;
 };
 
 namespace vfm {
@@ -92,12 +112,20 @@ inline void arena_reset(vfmreg_ctx* ctx) { ctx->arena.off = 0; }
 template <typename T>
 inline T* arena_take(vfmreg_ctx* ctx, size_t count) {
   size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
-  if (ctx->arena.off + bytes > ctx->arena.cap) return nullptr;
+  if (ctx->arena.off + bytes > (ctx->arena.limit ? ctx->arena.limit : ctx->arena.cap)) return nullptr;
   T* p = reinterpret_cast<T*>(ctx->arena.base + ctx->arena.off);
   ctx->arena.off += bytes;
   return p;
 }
 inline size_t arena_bytes(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
+
+// NVTX ranges per stage (visible in nsys / ncu --nvtx; free when no tool is attached)
+void nvtx_push(const char* name);
+void nvtx_pop();
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtx_push(name); }
+  ~NvtxRange() { nvtx_pop(); }
+};
 
 void group_begin(vfmreg_ctx* ctx, int group);
 void group_end(vfmreg_ctx* ctx, int group, int n_launches);
@@ -126,7 +154,7 @@ size_t match_simt_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m);
 // match_tc.cu: tcgen05 fp16 candidate search + exact fp32 re-rank; same results as match_simt (renormalised inputs only)
 int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
              const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev = nullptr,
-             const float* seed = nullptr);
+             const float* seed = nullptr, float floor = NAN);
 size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic = false);
 // gather the fp32 / fp16 rows and non-zero flags of b listed in column `col` of the (count, 2) list `pairs`
 int gather_rows(vfmreg_ctx* ctx, const int32_t* pairs, const int32_t* count, int64_t max_rows, int col, int dp, const float* b32,

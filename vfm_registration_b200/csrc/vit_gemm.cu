@@ -200,10 +200,10 @@ __global__ void __launch_bounds__(192, 1)
 
 template <int EPI, int BN>
 static int launch_gemm(vfmreg_ctx* ctx, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  const uint64_t bit = 1ull << (EPI * 3 + (BN == 256 ? 0 : (BN == 192 ? 1 : 2)));   // per device (= per context), not per process
+  if (!(ctx->gemm_attr_mask & bit)) {
     VFM_CUDA(cudaFuncSetAttribute(vit_gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSMEM_TOTAL));
-    attr_set = true;
+    ctx->gemm_attr_mask |= bit;
   }
   const int total = ceil_div(ep.m, GBM) * (ep.n / BN);
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;

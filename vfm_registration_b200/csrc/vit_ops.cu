@@ -346,10 +346,9 @@ int vit_attention(vfmreg_ctx* ctx, const __nv_bfloat16* qkv, int b, int t, int h
   const int tp = (t + 63) / 64 * 64;
   const size_t smem = (size_t)(2 * tp + ATT_WARPS * 16) * ATT_LD * 2;
   VFM_CHECK_ARG(smem <= 200 * 1024, "attention: %d tokens per image do not fit the shared-memory K/V staging", t);
-  static size_t attr = 0;
-  if (smem > attr) {
+  if (smem > ctx->attention_smem_attr) {   // per device (= per context)
     VFM_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    ctx->attention_smem_attr = smem;
   }
   // query splits: enough CTAs for two per SM, at least one round of 8 query tiles each
   const int n_tiles = (t + 15) / 16;

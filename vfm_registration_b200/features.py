@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import warnings
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -71,7 +72,7 @@ class ViTFeaturizer:
     """DINOv2 ViT (+ FeatUp ChannelNorm) on the device: uint8 images in, (B, 16, patch_w, C) float32 token grid out."""
 
     def __init__(self, model: str = "vits14", state_dict: Optional[Dict[str, torch.Tensor]] = None, *, seed: int = 0,
-                 channel_norm: bool = True, patch_h: int = 16, ln_eps: float = 1e-6, cn_eps: float = 1e-4, device=None):
+                 random_init: bool = False, channel_norm: bool = True, patch_h: int = 16, ln_eps: float = 1e-6, cn_eps: float = 1e-4, device=None):
         if model not in PRESETS:
             raise ValueError(f"Unsupported foundation model: {model}")  # image_features.py:52-54
         self.depth, self.width, self.heads = PRESETS[model]
@@ -83,6 +84,14 @@ class ViTFeaturizer:
         _lib.check(self.ctx.lib.vfmreg_vit_create(self.ctx.handle, C.byref(cfg), C.byref(h)), "vfmreg_vit_create")
         self.handle = h
         self._grids = set()
+        if state_dict is None:
+            # The reference always loads pretrained DINOv2 weights (image_features.py:39-42); descriptors of a randomly
+            # initialised network are meaningless, so that has to be asked for explicitly (benchmarks, tests).
+            if not random_init:
+                raise ValueError("ViTFeaturizer needs a DINOv2 state_dict (dinov2-hub or transformers naming); pass "
+                                 "random_init=True for randomly initialised weights (benchmarks / tests only)")
+            warnings.warn(f"ViTFeaturizer({model!r}): randomly initialised weights (seed {seed}) -- descriptors carry no "
+                          "semantics; use for benchmarks and tests only", RuntimeWarning, stacklevel=2)
         sd = state_dict if state_dict is not None else random_state_dict(model, seed)
         if "embeddings.cls_token" in sd:
             sd = _from_hf(sd)
@@ -154,14 +163,14 @@ class ImageFeatureGenerator:
     B200 path never needs it: ``create_descriptors`` / ``extract_features`` sample the token grid directly."""
 
     def __init__(self, foundation_model: str = "dinov2", use_featup: bool = False, *, model: str = "vits14",
-                 state_dict=None, seed: int = 0, device=None):
+                 state_dict=None, seed: int = 0, random_init: bool = False, device=None):
         if foundation_model != "dinov2":
             raise ValueError(f"Unsupported foundation model: {foundation_model}")
         if use_featup:
             raise NotImplementedError("the FeatUp upsampler is not on the hot path (use_featup=False, registration_node.py:57)")
         self.foundation_model_name, self.use_featup = foundation_model, use_featup
         self.patch_size, self.patch_h = 14, 16
-        self.vit = ViTFeaturizer(model, state_dict, seed=seed, device=device)
+        self.vit = ViTFeaturizer(model, state_dict, seed=seed, random_init=random_init, device=device)
         self.feature_size = self.vit.width
 
     def get_image_features(self, image: np.ndarray, upsample: bool = False, cache_file: str = "") -> np.ndarray:
@@ -172,14 +181,15 @@ class ImageFeatureGenerator:
 
 
 def extract_features(images, points, K, T_cam_from_lidar, *, featurizer: Optional[ViTFeaturizer] = None, model: str = "vits14",
-                     crop=None, reject_black: bool = True, state_dict=None, seed: int = 0, device=None) -> torch.Tensor:
+                     crop=None, reject_black: bool = True, state_dict=None, seed: int = 0, random_init: bool = False,
+                     device=None) -> torch.Tensor:
     """Per-point descriptors (N, D) float32 (CUDA tensor): DINOv2 patch features of B surround images sampled at the
     projection of every LiDAR point; zeros for unseen points; the first camera that sees a point wins
     (prepare_scenes.py:50-107 with project_pcl_to_image of dataloader/nclt.py:311-366).
 
     images (B, H, W, 3) uint8; points (N, 3) float32 in the LiDAR frame; K (B, 3, 3); T_cam_from_lidar (B, 4, 4)."""
     if featurizer is None:
-        featurizer = ViTFeaturizer(model, state_dict, seed=seed, device=device)
+        featurizer = ViTFeaturizer(model, state_dict, seed=seed, random_init=random_init, device=device)
     if isinstance(images, torch.Tensor):
         images_np = None
         imgs_t = images
