@@ -135,6 +135,7 @@ static int prepare_into(vfmreg_ctx* ctx, const float* x, int64_t rows, int d, ui
     nz = reinterpret_cast<uint8_t*>(mem + arena_bytes((size_t)rows * dp, 4) + arena_bytes((size_t)rows * dp, 2));
   }
   NvtxRange r("normalize_rows");
+  GroupScope g(ctx, GROUP_NORMALIZE, 1);
   VFM_TRY(normalize_rows(ctx, x, rows, d, dp, (flags & VFMREG_NORMALIZE) != 0, f32, f16, nz));
   out->f32 = f32;
   out->f16 = f16;
@@ -199,51 +200,124 @@ static int search_full(vfmreg_ctx* ctx, const Prepared& A, const Prepared& B, ui
   return VFMREG_OK;
 }
 
-// register(): forward search -> gate -> (mutual check) -> ordered correspondence list on the device.
+// register(): forward search -> gate -> (mutual check) -> ordered correspondence list on the device, in three stages so
+// that a batch can run a stage for a whole group of pairs before the next one (batch_run):
+//   1  renormalise the scan, start the forward search (on the tensor-core path only the search kernel is enqueued);
+//   2  re-rank, gate; pruned mutual check: gather the map rows the gated queries point at and start the reverse search
+//      over them; otherwise the final correspondence list;
+//   3  pruned mutual check: re-rank of the reverse search, keep the candidates whose map row points back.
 // A caller that gates on the cosine and does not need the runner-up hands the gate to the candidate search as a recording
 // floor: queries that cannot reach it report "no match" instead of their (rejected anyway) best.
-static int search_and_filter(vfmreg_ctx* ctx, const Prepared& A, const Prepared& B, const vfmreg_register_params* p, int32_t* corr,
-                             int32_t* count) {
+struct ScanState {
+  Prepared A;
+  bool pruned = false, full_reverse = false;
+  int32_t *idx01 = nullptr, *idx10 = nullptr;
+  float *sim01 = nullptr, *sec01 = nullptr;
+  int32_t *cand = nullptr, *cand_count = nullptr, *back = nullptr;
+  float *sel32 = nullptr, *selsim = nullptr;
+  uint16_t* sel16 = nullptr;
+  uint8_t* selnz = nullptr;
+  TcPending fwd, rev;
+  size_t arena_off = 0, arena_limit = 0;   // where the next stage goes on carving the pair's scratch region
+};
+
+static inline void state_save(vfmreg_ctx* ctx, ScanState* st) {
+  st->arena_off = ctx->arena.off;
+  st->arena_limit = ctx->arena.limit;
+}
+static inline void state_restore(vfmreg_ctx* ctx, const ScanState& st) {
+  ctx->arena.off = st.arena_off;
+  ctx->arena.limit = st.arena_limit;
+}
+
+static int search_stage1(vfmreg_ctx* ctx, const Prepared& A, const Prepared& B, const vfmreg_register_params* p, ScanState* st) {
   const int64_t n = A.rows, m = B.rows;
   const bool mutual = (p->flags & VFMREG_MUTUAL) != 0;
   const bool use_ratio = !(p->ratio != p->ratio);
-  const bool pruned = A.tc && mutual && n <= m && !g_full_mutual;
   const float floor = use_ratio ? NAN : p->min_cos;   // NAN when there is no gate either
-  int32_t* idx01 = arena_take<int32_t>(ctx, n);
-  float* sim01 = arena_take<float>(ctx, n);
-  float* sec01 = use_ratio ? arena_take<float>(ctx, n) : nullptr;
-  int32_t* idx10 = (mutual && !pruned) ? arena_take<int32_t>(ctx, m) : nullptr;
-  if (!idx01 || !sim01 || (use_ratio && !sec01) || (mutual && !pruned && !idx10)) {
+  st->A = A;
+  st->pruned = A.tc && mutual && n <= m && !g_full_mutual;
+  st->full_reverse = mutual && !st->pruned;
+  st->idx01 = arena_take<int32_t>(ctx, n);
+  st->sim01 = arena_take<float>(ctx, n);
+  st->sec01 = use_ratio ? arena_take<float>(ctx, n) : nullptr;
+  st->idx10 = st->full_reverse ? arena_take<int32_t>(ctx, m) : nullptr;
+  if (!st->idx01 || !st->sim01 || (use_ratio && !st->sec01) || (st->full_reverse && !st->idx10)) {
     set_error("register: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
-  if (pruned) {
-    // forward search, gate (cosine / ratio) -> candidate list (i, j) in query order, reverse search over the listed map
-    // rows only, then keep the candidates whose map row points back at them
+  if (st->pruned) {
     const int dp = A.dp;
-    int32_t* cand = arena_take<int32_t>(ctx, (size_t)n * 2);
-    int32_t* cand_count = arena_take<int32_t>(ctx, 1);
-    float* sel32 = arena_take<float>(ctx, (size_t)n * dp);
-    uint16_t* sel16 = arena_take<uint16_t>(ctx, (size_t)n * dp);
-    uint8_t* selnz = arena_take<uint8_t>(ctx, n);
-    int32_t* back = arena_take<int32_t>(ctx, n);
-    float* selsim = arena_take<float>(ctx, n);
-    if (!cand || !cand_count || !sel32 || !sel16 || !selnz || !back || !selsim) {
+    st->cand = arena_take<int32_t>(ctx, (size_t)n * 2);
+    st->cand_count = arena_take<int32_t>(ctx, 1);
+    st->sel32 = arena_take<float>(ctx, (size_t)n * dp);
+    st->sel16 = arena_take<uint16_t>(ctx, (size_t)n * dp);
+    st->selnz = arena_take<uint8_t>(ctx, n);
+    st->back = arena_take<int32_t>(ctx, n);
+    st->selsim = arena_take<float>(ctx, n);
+    if (!st->cand || !st->cand_count || !st->sel32 || !st->sel16 || !st->selnz || !st->back || !st->selsim) {
       set_error("register: scratch arena too small");
       return VFMREG_ERR_ALLOC;
     }
-    VFM_TRY(match_tc(ctx, A.f32, A.f16, A.nz, n, B.f32, B.f16, m, dp, idx01, sim01, sec01, nullptr, nullptr, floor));
-    NvtxRange r("mutual_check");
-    VFM_TRY(filter_corr(ctx, idx01, sim01, sec01, nullptr, n, p->min_cos, p->ratio, 0, cand, cand_count));
-    VFM_TRY(gather_rows(ctx, cand, cand_count, n, 1, dp, B.f32, B.f16, B.nz, sel32, sel16, selnz, sim01, selsim));
-    // <b_j, a_i> has the same canonical value as <a_i, b_j> = sim01[i]: a lower bound of row j's best that starts the
-    // candidate recording near the answer
-    VFM_TRY(match_tc(ctx, sel32, sel16, selnz, n, A.f32, A.f16, n, dp, back, nullptr, nullptr, cand_count, selsim));
-    return filter_mutual_list(ctx, cand, cand_count, back, n, corr, count);
   }
-  VFM_TRY(search_full(ctx, A, B, p->flags, idx01, sim01, sec01, idx10, nullptr, nullptr, floor));
-  NvtxRange r("filter_corr");
-  return filter_corr(ctx, idx01, sim01, sec01, idx10, n, p->min_cos, p->ratio, mutual, corr, count);
+  if (A.tc) {
+    VFM_TRY(match_tc_begin(ctx, A.f32, A.f16, A.nz, n, B.f32, B.f16, m, A.dp, st->idx01, st->sim01, st->sec01, nullptr, nullptr, floor,
+                           &st->fwd));
+    if (st->full_reverse)
+      VFM_TRY(match_tc_begin(ctx, B.f32, B.f16, B.nz, m, A.f32, A.f16, n, A.dp, st->idx10, nullptr, nullptr, nullptr, nullptr, NAN,
+                             &st->rev));
+  } else {
+    VFM_TRY(match_simt(ctx, A.f32, n, B.f32, m, A.dp, st->idx01, st->sim01, st->sec01));
+    if (st->full_reverse) VFM_TRY(match_simt(ctx, B.f32, m, A.f32, n, A.dp, st->idx10, nullptr, nullptr));
+  }
+  state_save(ctx, st);
+  return VFMREG_OK;
+}
+
+// `searches_done`: the event behind the last search of the group (null: wait for this pair's own searches)
+static int search_stage2(vfmreg_ctx* ctx, const Prepared& B, const vfmreg_register_params* p, int32_t* corr, int32_t* count,
+                         ScanState* st, cudaEvent_t searches_done) {
+  state_restore(ctx, *st);
+  const Prepared& A = st->A;
+  const int64_t n = A.rows;
+  if (A.tc) {
+    VFM_TRY(match_tc_finish(ctx, st->fwd, searches_done));
+    if (st->full_reverse) VFM_TRY(match_tc_finish(ctx, st->rev, searches_done));
+  }
+  if (st->pruned) {
+    NvtxRange r("gate_and_gather");
+    {
+      GroupScope g(ctx, GROUP_FILTER, 1);
+      VFM_TRY(filter_corr(ctx, st->idx01, st->sim01, st->sec01, nullptr, n, p->min_cos, p->ratio, 0, st->cand, st->cand_count));
+    }
+    {
+      GroupScope g(ctx, GROUP_GATHER, 1);
+      // <b_j, a_i> has the same canonical value as <a_i, b_j> = sim01[i]: a lower bound of row j's best that starts the
+      // candidate recording of the reverse search near the answer
+      VFM_TRY(gather_rows(ctx, st->cand, st->cand_count, n, 1, A.dp, B.f32, B.f16, B.nz, st->sel32, st->sel16, st->selnz, st->sim01,
+                          st->selsim));
+    }
+    VFM_TRY(match_tc_begin(ctx, st->sel32, st->sel16, st->selnz, n, A.f32, A.f16, n, A.dp, st->back, nullptr, nullptr, st->cand_count,
+                           st->selsim, NAN, &st->rev));
+  } else {
+    NvtxRange r("filter_corr");
+    GroupScope g(ctx, GROUP_FILTER, 1);
+    VFM_TRY(filter_corr(ctx, st->idx01, st->sim01, st->sec01, st->idx10, n, p->min_cos, p->ratio, (p->flags & VFMREG_MUTUAL) != 0, corr,
+                        count));
+  }
+  state_save(ctx, st);
+  return VFMREG_OK;
+}
+
+static int search_stage3(vfmreg_ctx* ctx, int32_t* corr, int32_t* count, ScanState* st, cudaEvent_t searches_done) {
+  state_restore(ctx, *st);
+  if (!st->pruned) return VFMREG_OK;
+  VFM_TRY(match_tc_finish(ctx, st->rev, searches_done));
+  NvtxRange r("mutual_check");
+  GroupScope g(ctx, GROUP_MUTUAL, 1);
+  VFM_TRY(filter_mutual_list(ctx, st->cand, st->cand_count, st->back, st->A.rows, corr, count));
+  state_save(ctx, st);
+  return VFMREG_OK;
 }
 
 }  // namespace vfm
@@ -266,13 +340,19 @@ static size_t scan_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, int32_t d, con
          arena_bytes(n, 1) + arena_bytes(16, 8) + arena_bytes(8, 8) + 4096;
 }
 
-// Enqueue one scan against a prepared map on ctx->stream (no host synchronisation).  The arena must already be reserved.
-static int scan_enqueue(vfmreg_ctx* ctx, const float* src_xyz, const float* src_feats, int64_t n, int32_t d, const float* tgt_xyz,
-                        const Prepared& B, const vfmreg_register_params* p, const int32_t* sample_idx, const RegOut& out) {
+// One scan against a prepared map, enqueued on ctx->stream stage by stage (no host synchronisation; the arena must
+// already be reserved); stage 3 ends with the RANSAC solve.
+static int scan_stage1(vfmreg_ctx* ctx, const float* src_feats, int64_t n, int32_t d, const Prepared& B, const vfmreg_register_params* p,
+                       ScanState* st) {
   Prepared A;
   VFM_TRY(prepare_arena(ctx, src_feats, n, d, p->flags, &A));
+  return search_stage1(ctx, A, B, p, st);
+}
+
+static int scan_stage3(vfmreg_ctx* ctx, const float* src_xyz, int64_t n, const float* tgt_xyz, const vfmreg_register_params* p,
+                       const int32_t* sample_idx, const RegOut& out, ScanState* st, cudaEvent_t searches_done) {
   int32_t* count = reinterpret_cast<int32_t*>(out.stats + 4);
-  VFM_TRY(search_and_filter(ctx, A, B, p, out.corr, count));
+  VFM_TRY(search_stage3(ctx, out.corr, count, st, searches_done));
   NvtxRange r("ransac");
   return ransac_solve(ctx, src_xyz, tgt_xyz, 0, out.corr, count, (int32_t)n, sample_idx, p->n_hyp, p->seed, p->inlier_thresh,
                       p->refit, out.T, nullptr, nullptr, out.mask, out.stats);
@@ -290,15 +370,18 @@ static void fill_result(vfmreg_register_result* result, const char* pin, double 
   result->rmse = st[1] > 0 ? sqrt(((double)st[2] / 1099511627776.0) * tau2 / (double)st[1]) : 0.0;
 }
 
-// VFMREG_MATCH_STREAMS=0 keeps the candidate-search kernels on their lane's stream (A/B comparison)
+// VFMREG_MATCH_STREAMS=0 keeps every candidate search on its lane's stream instead of the batch's search stream (A/B)
 static bool g_match_streams = [] { const char* e = getenv("VFMREG_MATCH_STREAMS"); return !(e && e[0] == '0'); }();
 
 static int ensure_lanes(vfmreg_ctx* ctx, int lanes) {
-  if (!ctx->ev_fork) VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-  if (!ctx->match_stream_owned[0]) {
+  if (!ctx->ev_fork) {
+    VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    VFM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming));
+  }
+  if (!ctx->match_stream_owned) {
     int lo = 0, hi = 0;
     VFM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
-    for (int i = 0; i < 2; ++i) VFM_CUDA(cudaStreamCreateWithPriority(&ctx->match_stream_owned[i], cudaStreamNonBlocking, hi));
+    VFM_CUDA(cudaStreamCreateWithPriority(&ctx->match_stream_owned, cudaStreamNonBlocking, hi));
     for (int i = 0; i < vfmreg_ctx::MATCH_EVENTS; ++i) VFM_CUDA(cudaEventCreateWithFlags(&ctx->match_ev[i], cudaEventDisableTiming));
   }
   for (int l = 1; l < lanes; ++l) {
@@ -343,7 +426,7 @@ struct StreamGuard {
   explicit StreamGuard(vfmreg_ctx* c) : ctx(c), saved(c->stream) {}
   ~StreamGuard() {
     ctx->stream = saved;
-    ctx->match_stream[0] = ctx->match_stream[1] = nullptr;
+    ctx->match_stream = nullptr;
     ctx->arena.limit = 0;
   }
 };
@@ -405,26 +488,63 @@ static int check_batch(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_registe
   return VFMREG_OK;
 }
 
-// ---- device-resident inputs: pairs spread over `lanes` streams, prepared maps in a small ring of slots ------------------
-static int batch_device(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_params* params, vfmreg_register_result* results) {
+// ---- the batch engine --------------------------------------------------------------------------------------------------
+// Every pair goes through three stages on its own CUDA stream ("lane"; pair i uses lane i % lanes, lane 0 = the caller's
+// stream): 1 = renormalise the scan (and prepare the run's map when the pair opens one) and start the forward search,
+// 2 = re-rank, gate, gather and start the pruned reverse search, 3 = re-rank of the reverse search, mutual filter, RANSAC.
+// The search kernels of all lanes go to ONE high-priority search stream (match_tc_begin); a search needs every SM (one
+// 209 KB CTA each) and more than half of the L2 -> SM bandwidth, so what runs beside it matters -- the two schedules below
+// differ in exactly that (measurements: profiles/r2_stage_times.txt, tools/corun.py).
+// Prepared maps live in a small ring of slots; a run of consecutive pairs with the same target shares one slot.
+//   device inputs: the arrays are used in place.
+//   host inputs:   a copy stream uploads the scans of later pairs (and the map of a run, once) while the current ones are
+//                  processed: 2 x lanes scan stages (xyz + descriptors + sample indices) and (corr, mask) output stages, raw map
+//                  stages beside the prepared-map slots -- persistent device staging (ctx->hbuf), grown on demand.
+static bool g_grouped = [] { const char* e = getenv("VFMREG_SCHEDULE"); return e && e[0] == 'g'; }();
+
+static int batch_run(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_params* params, vfmreg_register_result* results,
+                     bool host) {
   size_t scratch = 0, target_bytes = 0;
   int64_t n_max = 0;
   int n_runs = 0;
   VFM_TRY(check_batch(ctx, b, params, results, &scratch, &n_max, &target_bytes, &n_runs));
   VFM_CUDA(cudaSetDevice(ctx->device));
-  const int n_pairs = b.n_pairs;
+  const int n_pairs = b.n_pairs, d = b.d;
   const int lanes = ctx->lanes < n_pairs ? ctx->lanes : n_pairs;
-  const int ring = b.map ? 0 : (n_runs < lanes + 2 ? n_runs : lanes + 2);   // prepared-map slots
-  // scratch arena: [per-pair (T, stats) slots | prepared-map ring | per lane: fallback corr/mask + per-scan scratch]
+  constexpr int MAX_RING = 2 * vfmreg_ctx::MAX_LANES + 2;
+  const int ring_cap = host ? 2 * lanes : lanes + 2;
+  const int ring = b.map ? 0 : (n_runs < ring_cap ? n_runs : ring_cap);     // prepared-map slots
+  const int stages = host ? (n_pairs < 2 * lanes ? n_pairs : 2 * lanes) : 0;  // host: scan / output stages
+  size_t scan_stage = 0, raw_stage = 0, xyz_stage = 0;
+  if (host) {
+    for (int i = 0; i < n_pairs; ++i) {
+      const size_t s = arena_bytes((size_t)b.n[i] * 3, 4) + arena_bytes((size_t)b.n[i] * d, 4) +
+                       (b.sample_idx ? arena_bytes((size_t)params->n_hyp * 3, 4) : 0);
+      scan_stage = s > scan_stage ? s : scan_stage;
+      if (!b.map) {
+        const size_t r = arena_bytes((size_t)b.m[i] * d, 4), x = arena_bytes((size_t)b.m[i] * 3, 4);
+        raw_stage = r > raw_stage ? r : raw_stage;
+        xyz_stage = x > xyz_stage ? x : xyz_stage;
+      }
+    }
+  }
   const size_t slots_bytes = (size_t)n_pairs * 256;
   const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
+  // host staging: [ring x (raw map | map xyz | prepared map) | stages x scan | stages x (corr, mask)]
+  const size_t hslot = raw_stage + xyz_stage + target_bytes;
+  const size_t o_scan = (size_t)ring * hslot, o_out = o_scan + (size_t)stages * scan_stage;
+  if (host) {
+    VFM_TRY(ensure_hbuf(ctx, o_out + (size_t)stages * out_bytes, "register_batch_host"));
+    VFM_TRY(ensure_copy_stream(ctx));
+  }
+  // scratch arena: [per-pair (T, stats) slots | device inputs: prepared-map ring | per lane: fallback corr/mask + per-scan scratch]
   const size_t lane_bytes = out_bytes + scratch + 4096;
   arena_reset(ctx);
-  VFM_TRY(arena_reserve(ctx, slots_bytes + (size_t)ring * target_bytes + lanes * lane_bytes + 8192));
+  VFM_TRY(arena_reserve(ctx, slots_bytes + (host ? 0 : (size_t)ring * target_bytes) + lanes * lane_bytes + 8192));
   VFM_TRY(ensure_pinned(ctx, slots_bytes));
   char* slots = arena_take<char>(ctx, slots_bytes);
-  char* ring_mem = ring ? arena_take<char>(ctx, (size_t)ring * target_bytes) : nullptr;
-  if (!slots || (ring && !ring_mem)) {
+  char* ring_mem = (ring && !host) ? arena_take<char>(ctx, (size_t)ring * target_bytes) : nullptr;
+  if (!slots || (ring && !host && !ring_mem)) {
     set_error("register_batch: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
@@ -432,6 +552,7 @@ static int batch_device(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_regist
   StreamGuard guard(ctx);
   cudaStream_t lane_streams[vfmreg_ctx::MAX_LANES];
   for (int l = 0; l < vfmreg_ctx::MAX_LANES; ++l) lane_streams[l] = ctx->stream;
+  cudaStream_t ks = nullptr;   // the search stream
   if (lanes > 1) {
     VFM_TRY(ensure_lanes(ctx, lanes));
     VFM_CUDA(cudaEventRecord(ctx->ev_fork, guard.saved));          // inputs are ready in the caller's stream order
@@ -440,187 +561,201 @@ static int batch_device(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_regist
       VFM_CUDA(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
     }
     if (g_match_streams) {
-      ctx->match_stream[0] = ctx->match_stream_owned[0];
-      ctx->match_stream[1] = ctx->match_stream_owned[1];
+      ks = ctx->match_stream_owned;
+      VFM_CUDA(cudaStreamWaitEvent(ks, ctx->ev_fork, 0));
+      ctx->match_stream = ks;
     }
   }
-  // ring slot s: event [s * (1 + MAX_LANES)] = "prepared", events [.. + 1 + l] = "lane l is done with the slot's current map"
+  // events: ring slot s: [s * EV_PER_SLOT] = "prepared", [.. + 1 + l] = "lane l is done with the slot's current map";
+  //         scan stage k (host): [stage_ev + 2k] = "uploaded", [stage_ev + 2k + 1] = "consumed, outputs copied back"
   constexpr int EV_PER_SLOT = 1 + vfmreg_ctx::MAX_LANES;
-  if (ring) VFM_TRY(ensure_map_events(ctx, ring * EV_PER_SLOT));
-  uint32_t slot_lanes[vfmreg_ctx::MAX_LANES + 2] = {};   // lanes that used the slot's current map
-  Prepared slot_prep[vfmreg_ctx::MAX_LANES + 2];
-  int run = -1;
-  for (int i = 0; i < n_pairs; ++i) {
-    const int lane = i % lanes;
-    ctx->stream = lane_streams[lane];
-    const Prepared* B = b.map ? &b.map->prep : nullptr;
-    const float* tgt_xyz = b.map ? b.map->xyz : b.tgt_xyz[i];
-    int slot = -1;
-    if (!b.map) {
-      const bool first = (i == 0) || !b.same_target(i, i - 1);
-      if (first) ++run;
-      slot = run % ring;
-      cudaEvent_t* ev = ctx->map_ev + slot * EV_PER_SLOT;
-      if (first) {
-        // the slot's previous map may still be in use on other lanes
-        for (int l = 0; l < lanes; ++l)
-          if ((slot_lanes[slot] >> l) & 1u) VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ev[1 + l], 0));
-        slot_lanes[slot] = 0;
-        VFM_TRY(prepare_into(ctx, b.tgt_feats[i], b.m[i], b.d, params->flags, ring_mem + (size_t)slot * target_bytes, &slot_prep[slot]));
-        VFM_CUDA(cudaEventRecord(ev[0], ctx->stream));
-      } else {
-        VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ev[0], 0));
-      }
-      B = &slot_prep[slot];
-    }
-    // every pair of a lane reuses the lane's region (stream order); a pair may not run past its lane's end
-    ctx->arena.off = mark + (size_t)lane * lane_bytes;
-    ctx->arena.limit = ctx->arena.off + lane_bytes;
-    int32_t* corr_fb = arena_take<int32_t>(ctx, (size_t)n_max * 2);
-    uint8_t* mask_fb = arena_take<uint8_t>(ctx, n_max);
-    if (!corr_fb || !mask_fb) {
-      set_error("register_batch: scratch arena too small");
-      return VFMREG_ERR_ALLOC;
-    }
-    RegOut out;
-    out.corr = (b.corr_out && b.corr_out[i]) ? b.corr_out[i] : corr_fb;
-    out.mask = (b.mask_out && b.mask_out[i]) ? b.mask_out[i] : mask_fb;
-    out.T = (double*)(slots + (size_t)i * 256);
-    out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
-    VFM_TRY(scan_enqueue(ctx, b.src_xyz[i], b.src_feats[i], b.n[i], b.d, tgt_xyz, *B, params,
-                         b.sample_idx ? b.sample_idx[i] : nullptr, out));
-    if (slot >= 0) {
-      VFM_CUDA(cudaEventRecord(ctx->map_ev[slot * EV_PER_SLOT + 1 + lane], ctx->stream));
-      slot_lanes[slot] |= 1u << lane;
-    }
-  }
-  ctx->stream = guard.saved;
-  ctx->arena.limit = 0;
-  ctx->match_stream[0] = ctx->match_stream[1] = nullptr;   // every search was handed back to its lane by an event
-  for (int l = 1; l < lanes; ++l) {
-    VFM_CUDA(cudaEventRecord(ctx->ev_join[l], ctx->lane_stream[l]));
-    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
-  }
-  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, slots_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  VFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < n_pairs; ++i) fill_result(results + i, static_cast<const char*>(ctx->pinned) + (size_t)i * 256, params->inlier_thresh);
-  return VFMREG_OK;
-}
-
-// ---- host buffers: a copy stream uploads scan i+1 (and the next map) while scan i is matched and solved --------------------
-// Device staging (persistent, grown on demand): 2 raw map stages (fp32 descriptors as uploaded), 2 target slots (map xyz +
-// prepared rows), 2 scan stages (xyz + descriptors + sample indices), 2 (corr, mask) output stages, per-pair result slots.
-static int batch_host(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_params* params, vfmreg_register_result* results) {
-  size_t scratch = 0, target_bytes = 0;
-  int64_t n_max = 0;
-  int n_runs = 0;
-  VFM_TRY(check_batch(ctx, b, params, results, &scratch, &n_max, &target_bytes, &n_runs));
-  const int n_pairs = b.n_pairs, d = b.d;
-  size_t scan_stage = 0, raw_stage = 0, xyz_stage = 0;
-  for (int i = 0; i < n_pairs; ++i) {
-    const size_t s = arena_bytes((size_t)b.n[i] * 3, 4) + arena_bytes((size_t)b.n[i] * d, 4) +
-                     (b.sample_idx ? arena_bytes((size_t)params->n_hyp * 3, 4) : 0);
-    scan_stage = s > scan_stage ? s : scan_stage;
-    if (!b.map) {
-      const size_t r = arena_bytes((size_t)b.m[i] * d, 4), x = arena_bytes((size_t)b.m[i] * 3, 4);
-      raw_stage = r > raw_stage ? r : raw_stage;
-      xyz_stage = x > xyz_stage ? x : xyz_stage;
-    }
-  }
-  VFM_CUDA(cudaSetDevice(ctx->device));
-  VFM_TRY(ensure_copy_stream(ctx));
-  const size_t slot_bytes = xyz_stage + target_bytes;
-  const size_t out_bytes = arena_bytes((size_t)n_max * 2, 4) + arena_bytes(n_max, 1);
-  const size_t o_raw = 0, o_slot = o_raw + 2 * raw_stage, o_scan = o_slot + 2 * slot_bytes, o_out = o_scan + 2 * scan_stage;
-  const size_t o_res = o_out + 2 * out_bytes, total = o_res + (size_t)n_pairs * 256;
-  VFM_TRY(ensure_hbuf(ctx, total, "register_batch_host"));
-  arena_reset(ctx);
-  VFM_TRY(arena_reserve(ctx, scratch));
-  VFM_TRY(ensure_pinned(ctx, (size_t)n_pairs * 256));
-  char* slots = ctx->hbuf + o_res;
+  const int stage_ev = ring * EV_PER_SLOT;
+  VFM_TRY(ensure_map_events(ctx, stage_ev + 2 * stages));
+  uint32_t slot_lanes[MAX_RING] = {};   // lanes that used the slot's current map
+  Prepared slot_prep[MAX_RING];
 
   struct Staged { float *sx, *sf; int32_t* si; };
-  auto scan_ptrs = [&](int i, int buf) {
-    char* p = ctx->hbuf + o_scan + (size_t)buf * scan_stage;
+  auto scan_ptrs = [&](int i) {
+    char* p = ctx->hbuf + o_scan + (size_t)(i % stages) * scan_stage;
     Staged s;
     s.sx = (float*)p; p += arena_bytes((size_t)b.n[i] * 3, 4);
     s.sf = (float*)p; p += arena_bytes((size_t)b.n[i] * d, 4);
     s.si = (b.sample_idx && b.sample_idx[i]) ? (int32_t*)p : nullptr;
     return s;
   };
-  // maps are uploaded once per run of consecutive pairs that share them
-  auto enqueue_h2d = [&](int i, int run, bool first_of_run) -> int {
-    const int buf = i & 1;
-    if (first_of_run && !b.map) {
-      const int tb = run & 1;
-      if (run >= 2) VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_target_free[tb], 0));   // run - 2 has finished
-      char* slot = ctx->hbuf + o_slot + (size_t)tb * slot_bytes;
-      VFM_CUDA(cudaMemcpyAsync(slot, b.tgt_xyz[i], (size_t)b.m[i] * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-      VFM_CUDA(cudaMemcpyAsync(ctx->hbuf + o_raw + (size_t)tb * raw_stage, b.tgt_feats[i], (size_t)b.m[i] * d * 4,
-                               cudaMemcpyHostToDevice, ctx->copy_stream));
+  auto is_first = [&](int i) { return !b.map && (i == 0 || !b.same_target(i, i - 1)); };
+  // host inputs: upload of pair j on the copy stream (its map first when it opens a run)
+  int copy_next = 0, copy_run = -1;
+  auto enqueue_h2d = [&](int j) -> int {
+    cudaStream_t cs = ctx->copy_stream;
+    if (is_first(j)) {
+      ++copy_run;
+      const int slot = copy_run % ring;
+      cudaEvent_t* ev = ctx->map_ev + slot * EV_PER_SLOT;
+      for (int l = 0; l < lanes; ++l)      // the slot's previous map may still be in use
+        if ((slot_lanes[slot] >> l) & 1u) VFM_CUDA(cudaStreamWaitEvent(cs, ev[1 + l], 0));
+      slot_lanes[slot] = 0;
+      char* mem = ctx->hbuf + (size_t)slot * hslot;
+      VFM_CUDA(cudaMemcpyAsync(mem, b.tgt_feats[j], (size_t)b.m[j] * d * 4, cudaMemcpyHostToDevice, cs));
+      VFM_CUDA(cudaMemcpyAsync(mem + raw_stage, b.tgt_xyz[j], (size_t)b.m[j] * 3 * 4, cudaMemcpyHostToDevice, cs));
     }
-    if (i >= 2) VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));  // stage free again
-    const Staged s = scan_ptrs(i, buf);
-    VFM_CUDA(cudaMemcpyAsync(s.sx, b.src_xyz[i], (size_t)b.n[i] * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    VFM_CUDA(cudaMemcpyAsync(s.sf, b.src_feats[i], (size_t)b.n[i] * d * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    if (s.si) VFM_CUDA(cudaMemcpyAsync(s.si, b.sample_idx[i], (size_t)params->n_hyp * 3 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    VFM_CUDA(cudaEventRecord(ctx->ev_ready[buf], ctx->copy_stream));
+    cudaEvent_t* sev = ctx->map_ev + stage_ev + 2 * (j % stages);
+    if (j >= stages) VFM_CUDA(cudaStreamWaitEvent(cs, sev[1], 0));   // stage free again (pair j - stages is done with it)
+    const Staged s = scan_ptrs(j);
+    VFM_CUDA(cudaMemcpyAsync(s.sx, b.src_xyz[j], (size_t)b.n[j] * 3 * 4, cudaMemcpyHostToDevice, cs));
+    VFM_CUDA(cudaMemcpyAsync(s.sf, b.src_feats[j], (size_t)b.n[j] * d * 4, cudaMemcpyHostToDevice, cs));
+    if (s.si) VFM_CUDA(cudaMemcpyAsync(s.si, b.sample_idx[j], (size_t)params->n_hyp * 3 * 4, cudaMemcpyHostToDevice, cs));
+    VFM_CUDA(cudaEventRecord(sev[0], cs));
     return VFMREG_OK;
   };
-  auto is_first = [&](int i) { return !b.map && (i == 0 || !b.same_target(i, i - 1)); };
-  // the previous batch may still be reading the stages: order this batch's first copies after everything enqueued so far
-  VFM_CUDA(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
-  VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[0], 0));
-  int run_copy = -1, run = -1;
-  {
-    const bool f = is_first(0);
-    if (f) ++run_copy;
-    VFM_TRY(enqueue_h2d(0, run_copy, f));
+  if (host) {
+    // the previous call may still be reading the staging buffers: order this batch's copies after everything enqueued so far
+    VFM_CUDA(cudaEventRecord(ctx->ev_consumed[0], guard.saved));
+    VFM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[0], 0));
   }
-  Prepared prep[2];
-  for (int i = 0; i < n_pairs; ++i) {
-    const int buf = i & 1;
-    if (i + 1 < n_pairs) {   // overlaps with the compute of pair i
-      const bool f = is_first(i + 1);
-      if (f) ++run_copy;
-      VFM_TRY(enqueue_h2d(i + 1, run_copy, f));
-    }
-    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[buf], 0));
-    const Staged s = scan_ptrs(i, buf);
-    const Prepared* B = b.map ? &b.map->prep : nullptr;
-    const float* tgt_xyz = b.map ? b.map->xyz : nullptr;
-    int tb = 0;
-    if (!b.map) {
-      if (is_first(i)) {
-        ++run;
-        tb = run & 1;
-        char* slot = ctx->hbuf + o_slot + (size_t)tb * slot_bytes;
-        VFM_TRY(prepare_into(ctx, (const float*)(ctx->hbuf + o_raw + (size_t)tb * raw_stage), b.m[i], d, params->flags,
-                             slot + xyz_stage, &prep[tb]));
-      }
-      tb = run & 1;
-      B = &prep[tb];
-      tgt_xyz = (const float*)(ctx->hbuf + o_slot + (size_t)tb * slot_bytes);
-    }
+  auto next_event = [&]() {
+    cudaEvent_t ev = ctx->match_ev[ctx->match_ev_head];
+    ctx->match_ev_head = (ctx->match_ev_head + 1) % vfmreg_ctx::MATCH_EVENTS;
+    return ev;
+  };
+  struct PairCtx {
+    Staged st;
+    const float* tgt_xyz;
+    const Prepared* B;
+    int slot;
     RegOut out;
-    char* ob = ctx->hbuf + o_out + (size_t)buf * out_bytes;
-    out.corr = (int32_t*)ob;
-    out.mask = (uint8_t*)(ob + arena_bytes((size_t)n_max * 2, 4));
-    out.T = (double*)(slots + (size_t)i * 256);
-    out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
-    arena_reset(ctx);
-    VFM_TRY(scan_enqueue(ctx, s.sx, s.sf, b.n[i], d, tgt_xyz, *B, params, s.si, out));
-    VFM_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
-    if (!b.map) VFM_CUDA(cudaEventRecord(ctx->ev_target_free[tb], ctx->stream));   // re-recorded by every pair of the run
-    if (b.corr_out && b.corr_out[i])
-      VFM_CUDA(cudaMemcpyAsync(b.corr_out[i], out.corr, (size_t)b.n[i] * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (b.mask_out && b.mask_out[i])
-      VFM_CUDA(cudaMemcpyAsync(b.mask_out[i], out.mask, (size_t)b.n[i], cudaMemcpyDeviceToHost, ctx->stream));
+    ScanState state;
+  };
+  PairCtx pc[vfmreg_ctx::MAX_LANES];   // pair i lives in pc[i % lanes] from its stage 1 to its stage 3
+  int run = -1;
+  auto stage1 = [&](int i) -> int {
+    const int k = i % lanes;
+    PairCtx& c = pc[k];
+    ctx->stream = lane_streams[k];
+    c.st = host ? scan_ptrs(i) : Staged{nullptr, nullptr, nullptr};
+    if (host) VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->map_ev[stage_ev + 2 * (i % stages)], 0));
+    c.B = b.map ? &b.map->prep : nullptr;
+    c.tgt_xyz = b.map ? b.map->xyz : (host ? nullptr : b.tgt_xyz[i]);
+    c.slot = -1;
+    if (!b.map) {
+      const bool first = is_first(i);
+      if (first) ++run;
+      const int slot = run % ring;
+      c.slot = slot;
+      cudaEvent_t* ev = ctx->map_ev + slot * EV_PER_SLOT;
+      char* hmem = host ? ctx->hbuf + (size_t)slot * hslot : nullptr;
+      if (first) {
+        if (!host) {   // (host inputs: the copy stream waited for the slot's previous users before overwriting it)
+          for (int l = 0; l < lanes; ++l)
+            if ((slot_lanes[slot] >> l) & 1u) VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ev[1 + l], 0));
+          slot_lanes[slot] = 0;
+        }
+        VFM_TRY(prepare_into(ctx, host ? (const float*)hmem : b.tgt_feats[i], b.m[i], d, params->flags,
+                             host ? hmem + raw_stage + xyz_stage : ring_mem + (size_t)slot * target_bytes, &slot_prep[slot]));
+        VFM_CUDA(cudaEventRecord(ev[0], ctx->stream));
+      } else {
+        VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ev[0], 0));
+      }
+      c.B = &slot_prep[slot];
+      if (host) c.tgt_xyz = (const float*)(hmem + raw_stage);
+    }
+    // every pair of a lane reuses the lane's region (stream order); a pair may not run past its lane's end
+    ctx->arena.off = mark + (size_t)k * lane_bytes;
+    ctx->arena.limit = ctx->arena.off + lane_bytes;
+    if (host) {
+      char* ob = ctx->hbuf + o_out + (size_t)(i % stages) * out_bytes;
+      c.out.corr = (int32_t*)ob;
+      c.out.mask = (uint8_t*)(ob + arena_bytes((size_t)n_max * 2, 4));
+    } else {
+      int32_t* corr_fb = arena_take<int32_t>(ctx, (size_t)n_max * 2);
+      uint8_t* mask_fb = arena_take<uint8_t>(ctx, n_max);
+      if (!corr_fb || !mask_fb) {
+        set_error("register_batch: scratch arena too small");
+        return VFMREG_ERR_ALLOC;
+      }
+      c.out.corr = (b.corr_out && b.corr_out[i]) ? b.corr_out[i] : corr_fb;
+      c.out.mask = (b.mask_out && b.mask_out[i]) ? b.mask_out[i] : mask_fb;
+    }
+    c.out.T = (double*)(slots + (size_t)i * 256);
+    c.out.stats = (int64_t*)(slots + (size_t)i * 256 + 128);
+    return scan_stage1(ctx, host ? c.st.sf : b.src_feats[i], b.n[i], d, *c.B, params, &c.state);
+  };
+  auto stage2 = [&](int i, cudaEvent_t searches_done) -> int {
+    PairCtx& c = pc[i % lanes];
+    ctx->stream = lane_streams[i % lanes];
+    return search_stage2(ctx, *c.B, params, c.out.corr, reinterpret_cast<int32_t*>(c.out.stats + 4), &c.state, searches_done);
+  };
+  auto stage3 = [&](int i, cudaEvent_t searches_done) -> int {
+    const int k = i % lanes;
+    PairCtx& c = pc[k];
+    ctx->stream = lane_streams[k];
+    VFM_TRY(scan_stage3(ctx, host ? c.st.sx : b.src_xyz[i], b.n[i], c.tgt_xyz, params,
+                        host ? c.st.si : (b.sample_idx ? b.sample_idx[i] : nullptr), c.out, &c.state, searches_done));
+    if (host) {
+      if (b.corr_out && b.corr_out[i])
+        VFM_CUDA(cudaMemcpyAsync(b.corr_out[i], c.out.corr, (size_t)b.n[i] * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      if (b.mask_out && b.mask_out[i])
+        VFM_CUDA(cudaMemcpyAsync(b.mask_out[i], c.out.mask, (size_t)b.n[i], cudaMemcpyDeviceToHost, ctx->stream));
+      VFM_CUDA(cudaEventRecord(ctx->map_ev[stage_ev + 2 * (i % stages) + 1], ctx->stream));
+    }
+    if (c.slot >= 0) {
+      VFM_CUDA(cudaEventRecord(ctx->map_ev[c.slot * EV_PER_SLOT + 1 + k], ctx->stream));
+      slot_lanes[c.slot] |= 1u << k;
+    }
+    if (lanes > 1) VFM_CUDA(cudaEventRecord(ctx->ev_join[k], ctx->stream));
+    return VFMREG_OK;
+  };
+  if (!g_grouped && lanes >= 3) {
+    // PIPELINED schedule (default): stage 1 of pair i, stage 2 of pair i - 1, stage 3 of pair i - 2, ...  The search stream
+    // sees F(i), P(i-1), F(i+1), P(i), ... back to back; the small kernels of a pair run beside the searches of its successors
+    // (about half of their time is hidden that way, tools/corun.py) and take about 10 % off the search kernel's rate.
+    for (int i = 0; i < n_pairs + 2; ++i) {
+      if (host)   // pair j reuses the stage of pair j - stages, whose stage 3 must already be enqueued (pairs <= i - 3 are)
+        for (; copy_next < n_pairs && copy_next < i + stages - 2; ++copy_next) VFM_TRY(enqueue_h2d(copy_next));
+      if (i < n_pairs) VFM_TRY(stage1(i));
+      if (i >= 1 && i - 1 < n_pairs) VFM_TRY(stage2(i - 1, nullptr));
+      if (i >= 2) VFM_TRY(stage3(i - 2, nullptr));
+    }
+  } else {
+    // GROUPED schedule (VFMREG_SCHEDULE=grouped, or fewer than 3 lanes): groups of `lanes` pairs, stage by stage; a search
+    // kernel never shares the GPU with a small kernel (it then runs at the rate it has alone), the small kernels of a
+    // group overlap each other.
+    for (int g0 = 0; g0 < n_pairs; g0 += lanes) {
+      const int gn = (n_pairs - g0) < lanes ? (n_pairs - g0) : lanes;
+      if (host)   // this group's and the next group's uploads: pair j reuses the stage of pair j - stages, whose group is enqueued
+        for (; copy_next < n_pairs && copy_next < g0 + stages; ++copy_next) VFM_TRY(enqueue_h2d(copy_next));
+      if (ks && g0 > 0)   // the previous group's stage 3 has the GPU to itself
+        for (int l = 0; l < lanes; ++l) VFM_CUDA(cudaStreamWaitEvent(ks, ctx->ev_join[l], 0));
+      cudaEvent_t searches_done = nullptr;
+      for (int k = 0; k < gn; ++k) VFM_TRY(stage1(g0 + k));
+      if (ks) {
+        searches_done = next_event();
+        VFM_CUDA(cudaEventRecord(searches_done, ks));
+      }
+      for (int k = 0; k < gn; ++k) VFM_TRY(stage2(g0 + k, searches_done));
+      if (ks) {
+        searches_done = next_event();
+        VFM_CUDA(cudaEventRecord(searches_done, ks));
+      }
+      for (int k = 0; k < gn; ++k) VFM_TRY(stage3(g0 + k, searches_done));
+    }
   }
-  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, (size_t)n_pairs * 256, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->stream = guard.saved;
+  ctx->arena.limit = 0;
+  ctx->match_stream = nullptr;   // every search was handed back to its lane by an event
+  for (int l = 1; l < lanes; ++l) VFM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
+  VFM_CUDA(cudaMemcpyAsync(ctx->pinned, slots, slots_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   VFM_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n_pairs; ++i) fill_result(results + i, static_cast<const char*>(ctx->pinned) + (size_t)i * 256, params->inlier_thresh);
   return VFMREG_OK;
+}
+
+static int batch_device(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_params* params, vfmreg_register_result* results) {
+  return batch_run(ctx, b, params, results, false);
+}
+
+static int batch_host(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_params* params, vfmreg_register_result* results) {
+  return batch_run(ctx, b, params, results, true);
 }
 
 extern "C" {
@@ -696,12 +831,14 @@ void vfmreg_destroy(vfmreg_ctx* ctx) {
     cudaStreamDestroy(ctx->lane_stream[l]);
     cudaEventDestroy(ctx->ev_join[l]);
   }
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  for (int i = 0; i < 2; ++i)
-    if (ctx->match_stream_owned[i]) {
-      cudaStreamSynchronize(ctx->match_stream_owned[i]);
-      cudaStreamDestroy(ctx->match_stream_owned[i]);
-    }
+  if (ctx->ev_fork) {
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join[0]);
+  }
+  if (ctx->match_stream_owned) {
+    cudaStreamSynchronize(ctx->match_stream_owned);
+    cudaStreamDestroy(ctx->match_stream_owned);
+  }
   for (int i = 0; i < vfmreg_ctx::MATCH_EVENTS; ++i)
     if (ctx->match_ev[i]) cudaEventDestroy(ctx->match_ev[i]);
   for (int i = 0; i < ctx->map_ev_cap; ++i)

@@ -8,6 +8,8 @@
 
 #include "../../include/vfmreg_b200.h"
 
+struct vfmreg_ctx;
+
 namespace vfm {
 
 void set_error(const char* fmt, ...);
@@ -36,7 +38,18 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // GROUP_MATCH_PRUNED: the candidate-search launches whose row count lives on the device (pruned reverse search)
-enum { GROUP_MATCH = 0, GROUP_RANSAC = 1, GROUP_PROJECT = 2, GROUP_VIT = 3, GROUP_MATCH_PRUNED = 4, NUM_GROUPS = 5 };
+// groups >= 5: the small kernels of a pair, stage by stage (tools/stage_times.py)
+enum { GROUP_MATCH = 0, GROUP_RANSAC = 1, GROUP_PROJECT = 2, GROUP_VIT = 3, GROUP_MATCH_PRUNED = 4, GROUP_NORMALIZE = 5,
+       GROUP_RERANK = 6, GROUP_FILTER = 7, GROUP_GATHER = 8, GROUP_MUTUAL = 9, GROUP_KABSCH = 10, GROUP_FINALIZE = 11,
+       NUM_GROUPS = 12 };
+
+// times everything enqueued on the context's stream inside a scope as one interval of `group`
+struct GroupScope {
+  vfmreg_ctx* ctx;
+  int group, launches;
+  GroupScope(vfmreg_ctx* c, int g, int n);
+  ~GroupScope();
+};
 
 // Bump allocator over one cudaMalloc'd slab.  Scratch is carved per API call and reused by the next call on the
 // same stream (stream order makes that safe); growing the slab synchronises the stream first.
@@ -86,14 +99,14 @@ struct vfmreg_ctx {
   cudaEvent_t ev_ready[2] = {}, ev_consumed[2] = {}, ev_target_free[2] = {};
   // batch entry points: a second compute lane.  Consecutive pairs alternate between the caller's stream and this one, so
   // the latency-bound small kernels of one pair (filters, re-rank, RANSAC) run beside the other pair's match kernel.
-  static constexpr int MAX_LANES = 8;
-  int lanes = 5;                                   // vfmreg_set_lanes
+  static constexpr int MAX_LANES = 16;
+  int lanes = 8;                                   // vfmreg_set_lanes: pairs per group
   cudaStream_t lane_stream[MAX_LANES] = {};        // [0] unused: lane 0 is the caller's stream
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {};
-  // batch mode: high-priority streams for the candidate-search kernels ([0] full, [1] pruned); null outside a batch
-  static constexpr int MATCH_EVENTS = 32;
-  cudaStream_t match_stream[2] = {};
-  cudaStream_t match_stream_owned[2] = {};
+  // batch mode: high-priority streams for the candidate-search kernels; null outside a batch
+  static constexpr int MATCH_EVENTS = 128;
+  cudaStream_t match_stream = nullptr;         // the batch's search stream while a batch is being enqueued, else null
+  cudaStream_t match_stream_owned = nullptr;
   cudaEvent_t match_ev[MATCH_EVENTS] = {};
   int match_ev_head = 0;
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per context, not per process
@@ -129,6 +142,8 @@ struct NvtxRange {
 
 void group_begin(vfmreg_ctx* ctx, int group);
 void group_end(vfmreg_ctx* ctx, int group, int n_launches);
+inline GroupScope::GroupScope(vfmreg_ctx* c, int g, int n) : ctx(c), group(g), launches(n) { group_begin(c, g); }
+inline GroupScope::~GroupScope() { group_end(ctx, group, launches); }
 
 inline int launch_check(vfmreg_ctx* ctx, const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -156,6 +171,24 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
              const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev = nullptr,
              const float* seed = nullptr, float floor = NAN);
 size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic = false);
+// the two halves of match_tc: candidate search, then re-rank (see match_tc.cu)
+struct TcPending {
+  const float *a32 = nullptr, *b32 = nullptr;
+  const uint8_t* nz_a = nullptr;
+  int64_t n = 0, m = 0;
+  int dp = 0, slots = 0, top1 = 0, floor_mode = 0;
+  const int* n_dev = nullptr;
+  float* cand_v = nullptr;
+  int *cand_i = nullptr, *cand_n = nullptr;
+  void* slot_top2 = nullptr;
+  int32_t* idx = nullptr;
+  float *best = nullptr, *sec = nullptr;
+  cudaEvent_t done = nullptr;   // recorded behind the search kernel on the batch's search stream (null outside a batch)
+};
+int match_tc_begin(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
+                   const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev, const float* seed,
+                   float floor, TcPending* pending);
+int match_tc_finish(vfmreg_ctx* ctx, const TcPending& pending, cudaEvent_t wait_for);
 // gather the fp32 / fp16 rows and non-zero flags of b listed in column `col` of the (count, 2) list `pairs`
 int gather_rows(vfmreg_ctx* ctx, const int32_t* pairs, const int32_t* count, int64_t max_rows, int col, int dp, const float* b32,
                 const void* b16, const uint8_t* nzb, float* o32, void* o16, uint8_t* onz, const float* sim = nullptr,

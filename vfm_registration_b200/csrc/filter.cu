@@ -1,25 +1,36 @@
 // Cosine gate + mutual check + ratio test -> ordered correspondence list (reference VoxelHashMap.cpp:501-511,
-// 587-600 and registration_node.py:530).  One CTA: every thread owns a run of consecutive queries, counts its keepers, one
-// block-wide scan gives its write position, a second pass writes them in order.  n is at most a few 10^4 queries, so this
-// is a latency-sized kernel (reads 12-16 B, writes <= 8 B per query); the pruned mutual check (gate -> gather the map rows
-// the gated queries point at -> reverse search over those rows -> keep the pairs that point back) lives here too.
+// 587-600 and registration_node.py:530).  One CTA per list (ordered_compact below).  n is at most a few 10^4 queries, so
+// this is a latency-sized kernel (reads 12-16 B, writes <= 8 B per query); the pruned mutual check (gate -> gather the map
+// rows the gated queries point at -> reverse search over those rows -> keep the pairs that point back) lives here too.
 #include "common.cuh"
 
 namespace vfm {
 
-// exclusive prefix of one int per thread over a 1024-thread CTA; *total = sum
-__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* wsum, int& total) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// One-CTA ordered compaction.  FILTER_THREADS = 512 threads (16 warps x 32 registers: small enough to be placed at once
+// beside the candidate-search CTA of a neighbouring pair -- these kernels sit on the latency chain between a pair's two
+// searches).  The index range is walked in chunks of CHUNK_TILES tiles of 512 consecutive indices: every thread first
+// evaluates its element of each tile (coalesced, independent loads -> one memory round trip per chunk) into a bit mask,
+// one block-wide scan over the (tile, warp) counts gives every warp its write position, then the kept elements are written
+// in index order.
+constexpr int FILTER_THREADS = 512;
+constexpr int FILTER_WARPS = FILTER_THREADS / 32;
+constexpr int CHUNK_TILES = 32;
+static_assert(CHUNK_TILES * FILTER_WARPS == FILTER_THREADS, "one scan entry per thread");
+
+// exclusive prefix of one int per thread over the CTA; total = sum (all threads)
+__device__ __forceinline__ int block_exclusive_scan(int v, int* wsum, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   int incl = v;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     const int u = __shfl_up_sync(0xffffffffu, incl, off);
     if (lane >= off) incl += u;
   }
+  __syncthreads();   // wsum may still be read by the previous call
   if (lane == 31) wsum[w] = incl;
   __syncthreads();
   if (w == 0) {
-    int x = wsum[lane];
+    int x = lane < nw ? wsum[lane] : 0;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const int u = __shfl_up_sync(0xffffffffu, x, off);
@@ -32,10 +43,47 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* wsum, int& 
   return (w > 0 ? wsum[w - 1] : 0) + incl - v;
 }
 
+// keep(i) -> bool, emit(i, pos) writes element i at output position pos; returns the number of kept elements
+template <class Keep, class Emit>
+__device__ __forceinline__ int ordered_compact(int n, Keep keep, Emit emit) {
+  __shared__ int wsum[32];
+  __shared__ int wbase[CHUNK_TILES * FILTER_WARPS];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  int running = 0;
+  for (int c0 = 0; c0 < n; c0 += CHUNK_TILES * FILTER_THREADS) {
+    uint32_t mask = 0;
+#pragma unroll 8
+    for (int r = 0; r < CHUNK_TILES; ++r) {
+      const int i = c0 + r * FILTER_THREADS + t;
+      if (i < n && keep(i)) mask |= 1u << r;
+    }
+    __syncthreads();   // wbase of the previous chunk has been consumed
+#pragma unroll
+    for (int r = 0; r < CHUNK_TILES; ++r) {
+      const unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1u);
+      if (lane == 0) wbase[r * FILTER_WARPS + w] = __popc(b);
+    }
+    __syncthreads();
+    int total;
+    const int excl = block_exclusive_scan(wbase[t], wsum, total);   // entry t = (tile t / 16, warp t % 16): index order
+    __syncthreads();
+    wbase[t] = running + excl;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < CHUNK_TILES; ++r) {
+      const bool mine = (mask >> r) & 1u;
+      const unsigned b = __ballot_sync(0xffffffffu, mine);
+      if (mine) emit(c0 + r * FILTER_THREADS + t, wbase[r * FILTER_WARPS + w] + __popc(b & ((1u << lane) - 1u)));
+    }
+    running += total;
+  }
+  return running;
+}
+
 __device__ __forceinline__ bool corr_keep(const int32_t* __restrict__ idx01, const float* __restrict__ sim01, const float* __restrict__ sec01,
                                           const int32_t* __restrict__ idx10, int i, float min_cos, float ratio2, int use_cos,
-                                          int use_ratio, int mutual, int& j) {
-  j = idx01[i];
+                                          int use_ratio, int mutual) {
+  const int j = idx01[i];
   bool keep = j >= 0;
   if (keep && use_cos) keep = sim01[i] >= min_cos;
   if (keep && mutual) keep = idx10[j] == i;
@@ -43,25 +91,16 @@ __device__ __forceinline__ bool corr_keep(const int32_t* __restrict__ idx01, con
   return keep;
 }
 
-// Thread t owns the consecutive queries [t * per, (t + 1) * per): count, one block-wide scan, write -- two passes over
-// at most a few 10^4 queries, three barriers in total.
-__global__ void __launch_bounds__(1024) filter_corr_kernel(const int32_t* __restrict__ idx01, const float* __restrict__ sim01,
-                                                          const float* __restrict__ sec01, const int32_t* __restrict__ idx10,
-                                                          int n, float min_cos, float ratio2, int use_cos, int use_ratio,
-                                                          int mutual, int32_t* __restrict__ corr, int32_t* __restrict__ count) {
-  __shared__ int wsum[32];
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
-  int mine = 0, j;
-  for (int i = lo; i < hi; ++i) mine += corr_keep(idx01, sim01, sec01, idx10, i, min_cos, ratio2, use_cos, use_ratio, mutual, j) ? 1 : 0;
-  int total;
-  int pos = block_exclusive_scan_1024(mine, wsum, total);
-  for (int i = lo; i < hi; ++i)
-    if (corr_keep(idx01, sim01, sec01, idx10, i, min_cos, ratio2, use_cos, use_ratio, mutual, j)) {
-      corr[2 * pos] = i;
-      corr[2 * pos + 1] = j;
-      ++pos;
-    }
+__global__ void __launch_bounds__(FILTER_THREADS) filter_corr_kernel(const int32_t* __restrict__ idx01, const float* __restrict__ sim01,
+                                                                    const float* __restrict__ sec01, const int32_t* __restrict__ idx10,
+                                                                    int n, float min_cos, float ratio2, int use_cos, int use_ratio,
+                                                                    int mutual, int32_t* __restrict__ corr, int32_t* __restrict__ count) {
+  const int total = ordered_compact(
+      n, [&](int i) { return corr_keep(idx01, sim01, sec01, idx10, i, min_cos, ratio2, use_cos, use_ratio, mutual); },
+      [&](int i, int pos) {
+        corr[2 * pos] = i;
+        corr[2 * pos + 1] = idx01[i];
+      });
   if (threadIdx.x == 0) *count = total;
 }
 
@@ -72,8 +111,8 @@ int filter_corr(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const
   VFM_CHECK_ARG(!use_ratio || sec01, "ratio test needs sec01");
   VFM_CHECK_ARG(!mutual || idx10, "mutual filter needs idx10");
   VFM_CHECK_ARG(n < (1LL << 31), "n too large");
-  filter_corr_kernel<<<1, 1024, 0, ctx->stream>>>(idx01, sim01, sec01, idx10, (int)n, min_cos, ratio * ratio, use_cos,
-                                                 use_ratio, mutual, corr, count);
+  filter_corr_kernel<<<1, FILTER_THREADS, 0, ctx->stream>>>(idx01, sim01, sec01, idx10, (int)n, min_cos, ratio * ratio, use_cos,
+                                                           use_ratio, mutual, corr, count);
   return launch_check(ctx, "filter_corr");
 }
 
@@ -116,31 +155,22 @@ int gather_rows(vfmreg_ctx* ctx, const int32_t* pairs, const int32_t* count, int
   return launch_check(ctx, "gather_rows");
 }
 
-__global__ void __launch_bounds__(1024) filter_mutual_list_kernel(const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_count,
-                                                                 const int32_t* __restrict__ back, int max_rows,
-                                                                 int32_t* __restrict__ corr, int32_t* __restrict__ count) {
-  __shared__ int wsum[32];
+__global__ void __launch_bounds__(FILTER_THREADS) filter_mutual_list_kernel(const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_count,
+                                                                           const int32_t* __restrict__ back, int max_rows,
+                                                                           int32_t* __restrict__ corr, int32_t* __restrict__ count) {
   const int n = min(*cand_count, max_rows);
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
-  int mine = 0;
-  for (int k = lo; k < hi; ++k) mine += (back[k] == cand[2 * k]) ? 1 : 0;
-  int total;
-  int pos = block_exclusive_scan_1024(mine, wsum, total);
-  for (int k = lo; k < hi; ++k) {
-    const int i = cand[2 * k];
-    if (back[k] == i) {
-      corr[2 * pos] = i;
-      corr[2 * pos + 1] = cand[2 * k + 1];
-      ++pos;
-    }
-  }
+  const int total = ordered_compact(
+      n, [&](int k) { return back[k] == cand[2 * k]; },
+      [&](int k, int pos) {
+        corr[2 * pos] = cand[2 * k];
+        corr[2 * pos + 1] = cand[2 * k + 1];
+      });
   if (threadIdx.x == 0) *count = total;
 }
 
 int filter_mutual_list(vfmreg_ctx* ctx, const int32_t* cand, const int32_t* cand_count, const int32_t* back, int64_t max_rows,
                        int32_t* corr, int32_t* count) {
-  filter_mutual_list_kernel<<<1, 1024, 0, ctx->stream>>>(cand, cand_count, back, (int)max_rows, corr, count);
+  filter_mutual_list_kernel<<<1, FILTER_THREADS, 0, ctx->stream>>>(cand, cand_count, back, (int)max_rows, corr, count);
   return launch_check(ctx, "filter_mutual_list");
 }
 

@@ -21,8 +21,8 @@
 //  2. re-rank -- rerank_rows_kernel, one warp per query row: rebuild the row's final threshold from the per-slot
 //     approximate top-2, drop the candidates below it, recompute the survivors (typically 1-3) in the canonical fp32 order
 //     (fmaf chain over k ascending, from the fp32 rows; 16 lanes per candidate hand the accumulator on by shuffle) and pick
-//     the exact best / runner-up, lowest index on ties.  Rows whose list overflowed (pathological ties) are redone by
-//     exact_rows_kernel, an exact scan of all columns.
+//     the exact best / runner-up, lowest index on ties.  A list that overflowed (pathological ties) keeps its largest
+//     entries and the largest score it dropped; only if that score could still matter is the row scanned exactly.
 //
 // Why the result is exact: |S~ - S| <= eps with eps bounded below; the exact best and runner-up of a span both have
 // S~ >= (final approx runner-up of that span) - 2 eps, the recording threshold only ever rises, so both are always in
@@ -35,6 +35,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -74,13 +76,14 @@ struct TcParams {
   float* cand_v;         // [n][slots][CAP]
   int* cand_i;
   int* cand_n;           // [n][slots]: count | overflow << 30
-  float2* slot_top2;     // [n][slots]: approximate (best, runner-up) of the slot's column span
+  float4* slot_top2;     // [n][slots]: approximate (best, runner-up) of the slot's column span, largest score dropped on overflow
   int top1;              // 1: only the best match is needed (runner-up value not requested): threshold = best - margin
   const int* n_dev;      // optional: the number of query rows actually present (<= n), produced earlier on the stream
   const float* seed;     // optional (top1 only): per query row a known lower bound of its exact best score (the pruned
                          // reverse search knows <b_j, a_i> = sim01[i]); recording starts at seed - margin instead of -inf
   float floor;           // top1 only: recording never starts below this (cosine gate - margin), -inf = none
 };
+
 
 // number of query rows of this launch: the host-side bound, or the device-side count when the caller's row list was
 // compacted on the GPU (the pruned reverse search of the mutual check)
@@ -89,8 +92,8 @@ __device__ __forceinline__ int tc_rows(const TcParams& P) { return P.n_dev ? min
 // per-thread epilogue state of one query row inside one span
 struct EpiRow {
   float best, second, thr;
+  float lost;   // largest approximate score that had to be dropped because the list was full (-inf: none)
   int cnt;
-  bool ovf;
 };
 
 __device__ __forceinline__ void epi_row_begin(const TcParams& P, EpiRow& s, int row, int n_rows) {
@@ -103,7 +106,7 @@ __device__ __forceinline__ void epi_row_begin(const TcParams& P, EpiRow& s, int 
   }
   s.thr = active ? t : INFINITY;   // inactive rows (padding, all-zero queries) never record
   s.cnt = 0;
-  s.ovf = false;
+  s.lost = -INFINITY;
 }
 
 // slot of (row block, span): spans are numbered from the first CTA (cluster) whose span contains the row block's first unit
@@ -117,8 +120,8 @@ __device__ __forceinline__ void flush_slot(const TcParams& P, int n_rows, int ro
   while (c0 > 0 && (total_units * c0) / g > first_unit) --c0;
   const int slot = (int)(worker - c0) * HALVES + half;
   const long long o = ((long long)row * P.slots + slot);
-  P.cand_n[o] = s.cnt | (s.ovf ? (1 << 30) : 0);
-  P.slot_top2[o] = make_float2(s.best, s.second);
+  P.cand_n[o] = s.cnt | (s.lost > -INFINITY ? (1 << 30) : 0);
+  P.slot_top2[o] = make_float4(s.best, s.second, s.lost, 0.0f);
   for (int e = 0; e < s.cnt; ++e) {
     P.cand_v[o * CAP + e] = ring_v[e * EPI_THREADS + etid];
     P.cand_i[o * CAP + e] = ring_i[e * EPI_THREADS + etid];
@@ -147,7 +150,25 @@ __device__ __forceinline__ void push_candidate(float v, int col, int etid, float
     ring_i[s.cnt * EPI_THREADS + etid] = col;
     ++s.cnt;
   } else {
-    s.ovf = true;
+    // CAP entries within the margin of the threshold and one more: keep the CAP largest and remember the largest score
+    // that was dropped -- the re-rank only needs the exact fallback if that score could still matter at the end
+    int lo = 0;
+    float lo_v = ring_v[etid];
+#pragma unroll 1
+    for (int e = 1; e < CAP; ++e) {
+      const float ev = ring_v[e * EPI_THREADS + etid];
+      if (ev < lo_v) {
+        lo_v = ev;
+        lo = e;
+      }
+    }
+    if (v > lo_v) {
+      ring_v[lo * EPI_THREADS + etid] = v;
+      ring_i[lo * EPI_THREADS + etid] = col;
+      s.lost = fmaxf(s.lost, lo_v);
+    } else {
+      s.lost = fmaxf(s.lost, v);
+    }
   }
   if (v > s.best) {
     s.second = s.best;
@@ -347,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     s.best = s.second = -INFINITY;
     s.thr = INFINITY;
     s.cnt = 0;
-    s.ovf = false;
+    s.lost = -INFINITY;
     long long it = 0;
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int rb = (int)(t / P.col_tiles), ct = (int)(t % P.col_tiles);
@@ -535,7 +556,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     s.best = s.second = -INFINITY;
     s.thr = INFINITY;
     s.cnt = 0;
-    s.ovf = false;
+    s.lost = -INFINITY;
     long long it = 0;
     const uint32_t tempty_leader0 = mapa_cluster(tempty0, 0);
     for (long long u = u_begin; u < u_end; ++u, ++it) {
@@ -570,36 +591,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// canonical fp32 inner product: fmaf chain over k ascending (dp % 32 == 0 here, rows 16-byte aligned).  The chain is
-// sequential by definition; the loads are not: 8 float4 of each row are requested before the 32 dependent fmaf run.
-__device__ __forceinline__ float canon_dot(const float* __restrict__ x, const float* __restrict__ y, int dp) {
-  float acc = 0.0f;
-  const float4* x4 = reinterpret_cast<const float4*>(x);
-  const float4* y4 = reinterpret_cast<const float4*>(y);
-#pragma unroll 1
-  for (int k = 0; k < dp / 4; k += 8) {
-    float4 a[8], b[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      a[u] = __ldg(x4 + k + u);
-      b[u] = __ldg(y4 + k + u);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      acc = fmaf(a[u].x, b[u].x, acc);
-      acc = fmaf(a[u].y, b[u].y, acc);
-      acc = fmaf(a[u].z, b[u].z, acc);
-      acc = fmaf(a[u].w, b[u].w, acc);
-    }
-  }
-  return acc;
-}
-
 // multiset top-2 merge of (x1 >= x2) into (t1 >= t2)
 __device__ __forceinline__ void top2_merge(float& t1, float& t2, float x1, float x2) {
   const float lo = fminf(t1, x1);
   t1 = fmaxf(t1, x1);
   t2 = fmaxf(fmaxf(t2, x2), lo);
+}
+
+// Exact scan of all columns by one warp, for the (rare) query rows whose candidate list overflowed in a way that matters:
+// lane l takes columns 4 (32 t + l) .. + 3 -- four independent canonical fmaf chains per lane -- keeps its exact best (lowest
+// index on ties: columns ascend inside a lane and '>' is strict) and runner-up, then the lanes are merged by (score, index).
+__device__ __noinline__ void exact_row_scan(const float* __restrict__ ar, const float* __restrict__ b, int m, int dp, float& b1,
+                                            int& bi, float& b2) {
+  const int lane = threadIdx.x & 31;
+  b1 = b2 = -INFINITY;
+  bi = 0x7fffffff;
+  const float4* a4 = reinterpret_cast<const float4*>(ar);
+  for (int j0 = 4 * lane; j0 < m; j0 += 128) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float4* r4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r4[u] = reinterpret_cast<const float4*>(b + (long long)min(j0 + u, m - 1) * dp);
+    for (int k = 0; k < dp / 4; ++k) {
+      const float4 x = __ldg(a4 + k);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 y = __ldg(r4[u] + k);
+        acc[u] = fmaf(x.x, y.x, acc[u]);
+        acc[u] = fmaf(x.y, y.y, acc[u]);
+        acc[u] = fmaf(x.z, y.z, acc[u]);
+        acc[u] = fmaf(x.w, y.w, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 + u >= m) continue;
+      if (acc[u] > b1) {
+        b2 = b1;
+        b1 = acc[u];
+        bi = j0 + u;
+      } else if (acc[u] > b2) {
+        b2 = acc[u];
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const float y1 = __shfl_xor_sync(0xffffffffu, b1, off), y2 = __shfl_xor_sync(0xffffffffu, b2, off);
+    const int yi = __shfl_xor_sync(0xffffffffu, bi, off);
+    const bool y_wins = (y1 > b1) || (y1 == b1 && yi < bi);
+    const float lo = y_wins ? b1 : y1;
+    b2 = fmaxf(fmaxf(b2, y2), lo);
+    if (y_wins) {
+      b1 = y1;
+      bi = yi;
+    }
+  }
 }
 
 // Re-rank: one warp per query row.
@@ -611,15 +658,14 @@ __device__ __forceinline__ void top2_merge(float& t1, float& t2, float x1, float
 //           is then walked lane by lane, the accumulator handed on by shuffle -- the same operation order as one thread running
 //           the whole chain;
 //   pick    exact best (lowest index on ties) and runner-up value (multiset) -> idx / best / sec.
-// Rows whose list overflowed go to exact_rows_kernel.  With a gate floor (`floor_mode`) a row may have no candidate at all:
+// Rows whose list overflowed in a way that matters are scanned exactly by their warp (exact_row_scan).  With a gate floor (`floor_mode`) a row may have no candidate at all:
 // its best is below the caller's gate and it reports index -1 / score -inf.
 template <int PER_MAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
     rerank_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, int dp, int n, const int* __restrict__ n_dev, int m,
                        int slots, int top1, int floor_mode, const uint8_t* __restrict__ nz, const float* __restrict__ cand_v,
-                       const int* __restrict__ cand_i, const int* __restrict__ cand_n, const float2* __restrict__ slot_top2,
-                       int32_t* __restrict__ idx, float* __restrict__ best, float* __restrict__ sec, int* __restrict__ redo_list,
-                       int* __restrict__ redo_count) {
+                       const int* __restrict__ cand_i, const int* __restrict__ cand_n, const float4* __restrict__ slot_top2,
+                       int32_t* __restrict__ idx, float* __restrict__ best, float* __restrict__ sec) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -634,44 +680,74 @@ __global__ void __launch_bounds__(256)
     return;
   }
   const long long srow = (long long)row * slots;
+  // ---- one round trip: per-slot counts and approximate top-2, and (speculatively) the first 64 candidate entries
+  const int entries = slots * CAP;
+  int cn_l = 0;
+  float4 tt_l = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
+  if (lane < slots) {
+    cn_l = cand_n[srow + lane];
+    tt_l = slot_top2[srow + lane];
+  }
+  float pv0 = 0.0f, pv1 = 0.0f;
+  int pi0 = 0, pi1 = 0;
+  if (lane < entries) {
+    pv0 = cand_v[srow * CAP + lane];
+    pi0 = cand_i[srow * CAP + lane];
+  }
+  if (32 + lane < entries) {
+    pv1 = cand_v[srow * CAP + 32 + lane];
+    pi1 = cand_i[srow * CAP + 32 + lane];
+  }
   // ---- pass 1
-  float t1 = -INFINITY, t2 = -INFINITY;
-  bool overflow = false;
+  float t1 = -INFINITY, t2 = -INFINITY, lost = -INFINITY;
   for (int s = lane; s < slots; s += 32) {
-    const int c = cand_n[srow + s];
+    const int c = (s == lane) ? cn_l : cand_n[srow + s];
     if ((c & 0xFFFF) == 0 && !((c >> 30) & 1)) continue;
-    overflow |= ((c >> 30) & 1) != 0;
-    const float2 t = slot_top2[srow + s];
+    const float4 t = (s == lane) ? tt_l : slot_top2[srow + s];
     top2_merge(t1, t2, t.x, t.y);
+    if ((c >> 30) & 1) lost = fmaxf(lost, t.z);
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     const float o1 = __shfl_xor_sync(FULL, t1, off), o2 = __shfl_xor_sync(FULL, t2, off);
     top2_merge(t1, t2, o1, o2);
-  }
-  overflow = __any_sync(FULL, overflow);
-  if (overflow) {
-    if (lane == 0) redo_list[atomicAdd(redo_count, 1)] = row;
-    return;
+    lost = fmaxf(lost, __shfl_xor_sync(FULL, lost, off));
   }
   const float thr = (top1 ? t1 : t2) - MARGIN;
+  // a list that overflowed dropped its smallest entries; that only matters if one of them reaches the final threshold
+  // (the same test that discards recorded candidates below)
+  if (lost > -INFINITY && lost >= thr) {
+    float e1, e2;
+    int ei;
+    exact_row_scan(a + (long long)row * dp, b, m, dp, e1, ei, e2);
+    if (lane == 0) {
+      idx[row] = (ei == 0x7fffffff) ? 0 : ei;
+      if (best) best[row] = e1;
+      if (sec) sec[row] = e2;
+    }
+    return;
+  }
   // ---- pass 2
   constexpr int L = 16;
   const int gl = lane & (L - 1), hb = lane & ~(L - 1), h = lane >> 4;
   const int per = dp / (4 * L);   // float4 per lane and row (dp % 64 == 0, dp <= 64 PER_MAX)
   const float4* a4 = reinterpret_cast<const float4*>(a + (long long)row * dp) + gl * per;
   float4 av[PER_MAX];
-#pragma unroll
-  for (int u = 0; u < PER_MAX; ++u)
-    if (u < per) av[u] = __ldg(a4 + u);
+  bool a_loaded = false;
   float b1 = -INFINITY, b2 = -INFINITY;   // per half-warp: exact best / runner-up over the candidates it scored
   int bi = 0x7fffffff;
-  const int entries = slots * CAP;
   for (int e0 = 0; e0 < entries; e0 += 32) {
     const int e = e0 + lane;
     bool keep = false;
     int col = 0;
-    if (e < entries) {
+    if (e0 < 64) {   // prefetched above; the slot of entry e is e / CAP < 4 <= 32 lanes
+      const int cnt = __shfl_sync(FULL, cn_l, (e / CAP) & 31) & 0xFFFF;
+      const float v = e0 ? pv1 : pv0;
+      if (e < entries && (e % CAP) < cnt && v >= thr) {
+        keep = true;
+        col = e0 ? pi1 : pi0;
+      }
+    } else if (e < entries) {
       const int cnt = cand_n[srow + e / CAP] & 0xFFFF;
       if ((e % CAP) < cnt && cand_v[srow * CAP + e] >= thr) {
         keep = true;
@@ -679,6 +755,12 @@ __global__ void __launch_bounds__(256)
       }
     }
     unsigned live = __ballot_sync(FULL, keep);
+    if (live && !a_loaded) {   // warp-uniform
+#pragma unroll
+      for (int u = 0; u < PER_MAX; ++u)
+        if (u < per) av[u] = __ldg(a4 + u);
+      a_loaded = true;
+    }
     while (live) {   // warp-uniform: two survivors per round, one per half-warp
       const int s0 = __ffs(live) - 1;
       live &= live - 1;
@@ -735,67 +817,20 @@ __global__ void __launch_bounds__(256)
       bi = yi;
     }
   }
+  if (bi == 0x7fffffff && !floor_mode) {   // cannot happen for a non-zero row; exact scan as a safety net
+    exact_row_scan(a + (long long)row * dp, b, m, dp, b1, bi, b2);
+    if (bi == 0x7fffffff) bi = 0;
+  }
   if (lane == 0) {
-    if (bi == 0x7fffffff) {
-      if (floor_mode) {   // nothing reaches the caller's gate
-        idx[row] = -1;
-        if (best) best[row] = -INFINITY;
-        if (sec) sec[row] = -INFINITY;
-      } else {
-        redo_list[atomicAdd(redo_count, 1)] = row;   // cannot happen for a non-zero row; exact scan as a safety net
-      }
+    if (bi == 0x7fffffff) {   // floor mode: nothing reaches the caller's gate
+      idx[row] = -1;
+      if (best) best[row] = -INFINITY;
+      if (sec) sec[row] = -INFINITY;
     } else {
       idx[row] = bi;
       if (best) best[row] = b1;
       if (sec) sec[row] = b2;
     }
-  }
-}
-
-// Exact scan of all columns for the (rare) rows whose candidate list overflowed: one CTA per listed row.
-__global__ void __launch_bounds__(256)
-    exact_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, int m, int dp, const int* __restrict__ redo_list,
-                      const int* __restrict__ redo_count, int32_t* __restrict__ idx, float* __restrict__ best,
-                      float* __restrict__ sec) {
-  __shared__ float s1[256], s2[256];
-  __shared__ int si[256];
-  const int count = *redo_count;
-  for (int li = blockIdx.x; li < count; li += gridDim.x) {
-    const int row = redo_list[li];
-    const float* ar = a + (long long)row * dp;
-    float b1 = -INFINITY, b2 = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int j = threadIdx.x; j < m; j += 256) {
-      const float x = canon_dot(ar, b + (long long)j * dp, dp);
-      if (x > b1) {  // j ascending inside a thread: strict '>' keeps the lowest index
-        b2 = b1;
-        b1 = x;
-        bi = j;
-      } else if (x > b2) {
-        b2 = x;
-      }
-    }
-    s1[threadIdx.x] = b1;
-    s2[threadIdx.x] = b2;
-    si[threadIdx.x] = bi;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int t = 1; t < 256; ++t) {
-        const float y1 = s1[t], y2 = s2[t];
-        const int yi = si[t];
-        const bool y_wins = (y1 > b1) || (y1 == b1 && yi < bi);
-        const float lo = y_wins ? b1 : y1;
-        b2 = fmaxf(fmaxf(b2, y2), lo);
-        if (y_wins) {
-          b1 = y1;
-          bi = yi;
-        }
-      }
-      idx[row] = (bi == 0x7fffffff) ? 0 : bi;
-      if (best) best[row] = b1;
-      if (sec) sec[row] = b2;
-    }
-    __syncthreads();
   }
 }
 
@@ -874,34 +909,35 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic = fals
 size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic) {
   const TcPlan p = tc_plan(ctx, n, m, dynamic);
   return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
-         arena_bytes((size_t)n * p.slots, 8) + arena_bytes((size_t)n + 1, 4) + 2048;
+         arena_bytes((size_t)n * p.slots, 16) + 2048;
 }
 
 // a32/b32: renormalised fp32 rows (n x dp), a16/b16: their fp16 copies, nz_a: non-zero flags of the query rows.
 // n_dev (optional, device): the number of query rows actually present; n is then the capacity of a16 / a32 / nz_a / idx.
 // floor (top-1 mode only, NAN = none): the caller drops matches whose score is below this gate, so rows that cannot reach
 // it may report "no match" (index -1, score -inf) -- see the header of this file.
-int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
-             const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev, const float* seed,
-             float floor) {
+//
+// match_tc_begin enqueues the candidate search, match_tc_finish the re-rank.  In batch mode (ctx->match_stream set) the search
+// kernel goes to the batch's high-priority search stream -- the lane stream hands over with an event -- and `pending->done`
+// is recorded behind it; match_tc_finish makes the lane wait for `wait_for` (the batch passes the event behind the LAST
+// search of a group, so that no small kernel runs beside a search) or for `pending->done`.
+int match_tc_begin(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
+                   const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev, const float* seed,
+                   float floor, TcPending* pending) {
   VFM_CHECK_ARG(dp % TBK == 0 && dp <= 1024, "match_tc: padded dim %d must be a multiple of %d and <= 1024 (error bound)", dp, TBK);
   VFM_CHECK_ARG(n > 0 && m > 0 && n < (1LL << 30) && m < (1LL << 30), "match_tc: bad sizes");
   const TcPlan plan = tc_plan(ctx, n, m, n_dev != nullptr);
   float* cand_v = arena_take<float>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_i = arena_take<int>(ctx, (size_t)n * plan.slots * CAP);
-  float2* slot_top2 = arena_take<float2>(ctx, (size_t)n * plan.slots);
-  int* redo_list = arena_take<int>(ctx, (size_t)n);                             // rows for exact_rows_kernel
-  // everything that starts at zero sits in one block: [redo count | cand_n], one memset
-  const size_t z_cn = 256;
-  const size_t z_bytes = z_cn + arena_bytes((size_t)n * plan.slots, 4);
-  char* zero = arena_take<char>(ctx, z_bytes);
-  if (!cand_v || !cand_i || !slot_top2 || !redo_list || !zero) {
+  float4* slot_top2 = arena_take<float4>(ctx, (size_t)n * plan.slots);
+  // slot counts start at zero: a (row, slot) that no span covers stays empty
+  const size_t z_bytes = arena_bytes((size_t)n * plan.slots, 4);
+  int* cand_n = arena_take<int>(ctx, (size_t)n * plan.slots);
+  if (!cand_v || !cand_i || !slot_top2 || !cand_n) {
     set_error("match_tc: scratch arena too small");
     return VFMREG_ERR_ALLOC;
   }
-  int* redo_count = reinterpret_cast<int*>(zero);
-  int* cand_n = reinterpret_cast<int*>(zero + z_cn);
-  VFM_CUDA(cudaMemsetAsync(zero, 0, z_bytes, ctx->stream));
+  VFM_CUDA(cudaMemsetAsync(cand_n, 0, z_bytes, ctx->stream));
   CUtensorMap map_a, map_b;
   VFM_TRY(make_map_f16(&map_a, a16, n, dp, TBM));
   VFM_TRY(make_map_f16(&map_b, b16, m, dp, plan.paired ? TBN / 2 : TBN));
@@ -929,12 +965,9 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
     ctx->tc_attr_set = true;
   }
   const int grp = n_dev ? GROUP_MATCH_PRUNED : GROUP_MATCH;
-  // Batch mode (vfmreg_register_batch with several lanes): the candidate-search kernels of all lanes go to one of two
-  // high-priority streams -- full searches on [0], pruned reverse searches on [1] -- so that they run back to back in pair
-  // order and are scheduled ahead of the lanes' small kernels, which fill the SMs beside them.  The lane stream hands
-  // over with an event and takes the result back with another.
   cudaStream_t lane = ctx->stream;
-  cudaStream_t ks = ctx->match_stream[n_dev ? 1 : 0];
+  cudaStream_t ks = ctx->match_stream;
+  pending->done = nullptr;
   if (ks) {
     cudaEvent_t ev = ctx->match_ev[ctx->match_ev_head];
     ctx->match_ev_head = (ctx->match_ev_head + 1) % vfmreg_ctx::MATCH_EVENTS;
@@ -962,22 +995,59 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
     cudaEvent_t ev = ctx->match_ev[ctx->match_ev_head];
     ctx->match_ev_head = (ctx->match_ev_head + 1) % vfmreg_ctx::MATCH_EVENTS;
     VFM_CUDA(cudaEventRecord(ev, ks));
-    VFM_CUDA(cudaStreamWaitEvent(lane, ev, 0));
+    pending->done = ev;
   }
   VFM_TRY(rc_launch);
-  const int rows_per_cta = 8;
-  if (dp <= 512)
-    rerank_rows_kernel<8><<<ceil_div(n, rows_per_cta), rows_per_cta * 32, 0, ctx->stream>>>(
-        a32, b32, dp, (int)n, n_dev, (int)m, plan.slots, P.top1, floor_mode ? 1 : 0, nz_a, cand_v, cand_i, cand_n, slot_top2, idx, best,
-        sec, redo_list, redo_count);
-  else
-    rerank_rows_kernel<16><<<ceil_div(n, rows_per_cta), rows_per_cta * 32, 0, ctx->stream>>>(
-        a32, b32, dp, (int)n, n_dev, (int)m, plan.slots, P.top1, floor_mode ? 1 : 0, nz_a, cand_v, cand_i, cand_n, slot_top2, idx, best,
-        sec, redo_list, redo_count);
-  VFM_TRY(launch_check(ctx, "rerank_rows_kernel"));
-  exact_rows_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(a32, b32, (int)m, dp, redo_list, redo_count, idx, best, sec);
-  VFM_TRY(launch_check(ctx, "exact_rows_kernel"));
+  pending->a32 = a32;
+  pending->b32 = b32;
+  pending->nz_a = nz_a;
+  pending->n = n;
+  pending->m = m;
+  pending->dp = dp;
+  pending->slots = plan.slots;
+  pending->top1 = P.top1;
+  pending->floor_mode = floor_mode ? 1 : 0;
+  pending->n_dev = n_dev;
+  pending->cand_v = cand_v;
+  pending->cand_i = cand_i;
+  pending->cand_n = cand_n;
+  pending->slot_top2 = slot_top2;
+  pending->idx = idx;
+  pending->best = best;
+  pending->sec = sec;
   return VFMREG_OK;
+}
+
+int match_tc_finish(vfmreg_ctx* ctx, const TcPending& t, cudaEvent_t wait_for) {
+  if (wait_for)
+    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, wait_for, 0));
+  else if (t.done)
+    VFM_CUDA(cudaStreamWaitEvent(ctx->stream, t.done, 0));
+  GroupScope g_rerank(ctx, GROUP_RERANK, 1);
+  const int rows_per_cta = 4;
+  const int n = (int)t.n, dp = t.dp;
+#define VFM_RERANK(PER)                                                                                                      \
+  rerank_rows_kernel<PER><<<ceil_div(n, rows_per_cta), rows_per_cta * 32, 0, ctx->stream>>>(                                 \
+      t.a32, t.b32, dp, n, t.n_dev, (int)t.m, t.slots, t.top1, t.floor_mode, t.nz_a, t.cand_v, t.cand_i, t.cand_n,             \
+      static_cast<const float4*>(t.slot_top2), t.idx, t.best, t.sec)
+  if (dp <= 384)
+    VFM_RERANK(6);
+  else if (dp <= 512)
+    VFM_RERANK(8);
+  else if (dp <= 768)
+    VFM_RERANK(12);
+  else
+    VFM_RERANK(16);
+#undef VFM_RERANK
+  return launch_check(ctx, "rerank_rows_kernel");
+}
+
+int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* nz_a, int64_t n, const float* b32,
+             const void* b16, int64_t m, int dp, int32_t* idx, float* best, float* sec, const int* n_dev, const float* seed,
+             float floor) {
+  TcPending t;
+  VFM_TRY(match_tc_begin(ctx, a32, a16, nz_a, n, b32, b16, m, dp, idx, best, sec, n_dev, seed, floor, &t));
+  return match_tc_finish(ctx, t, nullptr);
 }
 
 }  // namespace vfm

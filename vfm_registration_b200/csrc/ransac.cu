@@ -6,11 +6,11 @@
 // THIS FILE IS COMPILED WITH -fmad=false: every fused multiply-add is an explicit fma().
 //
 // Kernels
-//   gather_pq_kernel   corr (K x 2) + xyz -> pq (K x 6) float64 (p.xyz, q.xyz): 48 B/correspondence, coalesced.
-//   kabsch3_kernel     one thread per hypothesis: 3 samples (given or counter-based RNG) -> R,t (12 doubles).
-//   score_kernel       grid (hyp blocks) x (K splits); 128 hypotheses per CTA, one per thread, R,t in registers;
-//                      correspondences staged through shared memory in 256-row tiles with 128-bit loads and read
-//                      back as warp-wide broadcasts; inlier count and the quantised residual sum
+//   gather_kabsch_kernel  one launch: corr (K x 2) + xyz -> pq (K x 6) float64 (p.xyz, q.xyz), 48 B/correspondence; and one
+//                      thread per hypothesis: 3 samples (given or counter-based RNG) -> R,t (12 doubles).
+//   score_kernel       grid (hyp blocks) x (K slices); 256 hypotheses per CTA, two per thread, R,t in registers;
+//                      correspondences staged through a 3 KB shared-memory tile (the kernel runs beside the candidate
+//                      search of the neighbouring pairs, which leaves ~18 KB per SM); inlier count and the quantised residual sum
 //                      (rint(d^2 2^40/tau^2), order-independent integers) are added with integer atomics.
 //                      Bound: FP64 FMA pipe (16 flop-pairs per hypothesis x correspondence); HBM traffic is the
 //                      48 K bytes of pq per hypothesis block, L2 resident.
@@ -20,10 +20,12 @@
 
 namespace vfm {
 
-constexpr int HYP_PER_CTA = 128;
-constexpr int TILE_K = 256;
+constexpr int SCORE_THREADS = 128;
+constexpr int PREP_THREADS = 128;
+constexpr int SCORE_TILE = 64;   // correspondences per shared-memory tile (3 KB)
+constexpr int HYP_PER_CTA = 2 * SCORE_THREADS;   // two hypotheses per thread
 constexpr int SWEEPS = 6;
-constexpr int FIN_THREADS = 512;
+constexpr int FIN_THREADS = 256;   // 256 x <= 128 registers: the CTA must fit beside a candidate-search CTA of a neighbouring pair
 
 __device__ __forceinline__ uint32_t sample_u32(uint64_t seed, uint64_t ctr, uint32_t k) {
   uint64_t z = seed * 0x9E3779B97F4A7C15ULL + ctr;
@@ -139,27 +141,30 @@ __device__ __forceinline__ long long quant(double d2, double scale) {
   return __double_as_longlong(z) - 0x4330000000000000LL;
 }
 
+// One launch for the two steps that only depend on the correspondence list: blocks [0, gather_blocks) copy the listed points
+// into pq (K x 6 float64, what score_kernel streams); the other blocks fit one hypothesis per thread from its 3 samples,
+// reading the sampled points through corr directly (the same float64 values pq receives, so neither half waits for the other).
 template <typename XYZ>
-__global__ void gather_pq_kernel(const XYZ* __restrict__ src, const XYZ* __restrict__ tgt, const int32_t* __restrict__ corr,
-                                 const int32_t* __restrict__ count, int max_corr, double* __restrict__ pq) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(PREP_THREADS)
+    gather_kabsch_kernel(const XYZ* __restrict__ src, const XYZ* __restrict__ tgt, const int32_t* __restrict__ corr,
+                         const int32_t* __restrict__ count, int max_corr, int gather_blocks, double* __restrict__ pq,
+                         const int32_t* __restrict__ sample_idx, int n_hyp, uint64_t seed, double* __restrict__ rts,
+                         int32_t* __restrict__ counts, unsigned long long* __restrict__ sumq) {
   const int K = min(*count, max_corr);
-  if (k >= K) return;
-  const int i = corr[2 * k], j = corr[2 * k + 1];
-  double* o = pq + (int64_t)k * 6;
+  if ((int)blockIdx.x < gather_blocks) {
+    const int k = blockIdx.x * PREP_THREADS + threadIdx.x;
+    if (k >= K) return;
+    const int i = corr[2 * k], j = corr[2 * k + 1];
+    double* o = pq + (int64_t)k * 6;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    o[c] = (double)src[(int64_t)i * 3 + c];
-    o[3 + c] = (double)tgt[(int64_t)j * 3 + c];
+    for (int c = 0; c < 3; ++c) {
+      o[c] = (double)src[(int64_t)i * 3 + c];
+      o[3 + c] = (double)tgt[(int64_t)j * 3 + c];
+    }
+    return;
   }
-}
-
-__global__ void kabsch3_kernel(const double* __restrict__ pq, const int32_t* __restrict__ count, int max_corr,
-                               const int32_t* __restrict__ sample_idx, int n_hyp, uint64_t seed, double* __restrict__ rts,
-                               int32_t* __restrict__ counts, unsigned long long* __restrict__ sumq) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = (blockIdx.x - gather_blocks) * PREP_THREADS + threadIdx.x;
   if (h >= n_hyp) return;
-  const int K = min(*count, max_corr);
   sumq[h] = 0ULL;
   double* rt = rts + (int64_t)h * 12;
   if (K < 3) {
@@ -171,11 +176,11 @@ __global__ void kabsch3_kernel(const double* __restrict__ pq, const int32_t* __r
   for (int j = 0; j < 3; ++j) {
     int s = sample_idx ? sample_idx[h * 3 + j] : (int)sample_u32(seed, (uint64_t)h * 3 + j, (uint32_t)K);
     s = min(max(s, 0), K - 1);
-    const double* r = pq + (int64_t)s * 6;
+    const int ci = corr[2 * s], cj = corr[2 * s + 1];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      p[j * 3 + c] = r[c];
-      q[j * 3 + c] = r[3 + c];
+      p[j * 3 + c] = (double)src[(int64_t)ci * 3 + c];
+      q[j * 3 + c] = (double)tgt[(int64_t)cj * 3 + c];
     }
   }
   double pm[3], qm[3], S[9], out[12];
@@ -196,49 +201,61 @@ __global__ void kabsch3_kernel(const double* __restrict__ pq, const int32_t* __r
   counts[h] = ok ? 0 : -1;
 }
 
-__global__ void __launch_bounds__(HYP_PER_CTA)
+// Two hypotheses per thread, R,t of both in registers; the CTA's slice of the correspondence list goes through a 3 KB
+// shared-memory tile (64 rows, coalesced 128-bit loads) and is read back as warp-wide broadcasts serving both hypotheses.
+// The tile is that small on purpose: the kernel runs beside the candidate search of the neighbouring pairs, whose CTAs
+// leave about 18 KB of shared memory (and hardly any L1) per SM -- four of these CTAs still fit there.
+// grid = (blocks of 256 hypotheses) x (slices of the correspondence list).
+__global__ void __launch_bounds__(SCORE_THREADS)
     score_kernel(const double* __restrict__ pq, const int32_t* __restrict__ count, int max_corr,
                  const double* __restrict__ rts, int n_hyp, double tau2, double scale, int32_t* __restrict__ counts,
                  unsigned long long* __restrict__ sumq) {
-  __shared__ __align__(16) double tile[TILE_K * 6];
+  __shared__ __align__(16) double tile[SCORE_TILE * 6];
   const int K = min(*count, max_corr);
   if (K < 3) return;
-  const int h = blockIdx.x * HYP_PER_CTA + threadIdx.x;
-  const bool live = (h < n_hyp) && (counts[h] >= 0);  // counts[h] is only ever raised by score CTAs, never below 0
-  // this CTA's slice of the correspondences, in whole tiles
-  const int n_tiles = (K + TILE_K - 1) / TILE_K;
-  const int tiles_per = (n_tiles + gridDim.y - 1) / gridDim.y;
-  const int t0 = blockIdx.y * tiles_per, t1 = min(t0 + tiles_per, n_tiles);
-  if (t0 >= t1) return;
-  double rt[12];
+  const int per = (K + gridDim.y - 1) / gridDim.y;
+  const int k0 = blockIdx.y * per, k1 = min(K, k0 + per);
+  if (k0 >= k1) return;
+  const int ha = blockIdx.x * HYP_PER_CTA + threadIdx.x, hb = ha + SCORE_THREADS;
+  // counts[h] is only ever raised by score CTAs, never below 0: -1 marks a degenerate sample
+  const bool live_a = (ha < n_hyp) && (counts[ha] >= 0), live_b = (hb < n_hyp) && (counts[hb] >= 0);
+  double ra[12], rb[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) rt[i] = (h < n_hyp) ? rts[(int64_t)h * 12 + i] : 0.0;
-  int cnt = 0;
-  long long sum = 0;
-  for (int tl = t0; tl < t1; ++tl) {
-    const int k0 = tl * TILE_K;
-    const int rows = min(TILE_K, K - k0);
+  for (int i = 0; i < 12; ++i) {
+    ra[i] = (ha < n_hyp) ? rts[(int64_t)ha * 12 + i] : 0.0;
+    rb[i] = (hb < n_hyp) ? rts[(int64_t)hb * 12 + i] : 0.0;
+  }
+  int cnt_a = 0, cnt_b = 0;
+  long long sum_a = 0, sum_b = 0;
+  const double2* s2 = reinterpret_cast<const double2*>(tile);
+  for (int t0 = k0; t0 < k1; t0 += SCORE_TILE) {
+    const int rows = min(SCORE_TILE, k1 - t0);
     __syncthreads();
-    // 128-bit coalesced copy of rows*6 doubles
-    const double2* g = reinterpret_cast<const double2*>(pq + (int64_t)k0 * 6);
-    double2* s = reinterpret_cast<double2*>(tile);
-    for (int i = threadIdx.x; i < rows * 3; i += HYP_PER_CTA) s[i] = __ldg(g + i);
+    const double2* g = reinterpret_cast<const double2*>(pq + (int64_t)t0 * 6);
+    for (int i = threadIdx.x; i < rows * 3; i += SCORE_THREADS) reinterpret_cast<double2*>(tile)[i] = __ldg(g + i);
     __syncthreads();
-    if (live) {
-#pragma unroll 4
-      for (int k = 0; k < rows; ++k) {
-        const double2 v0 = s[k * 3 + 0], v1 = s[k * 3 + 1], v2 = s[k * 3 + 2];  // warp-wide broadcasts
-        const double d2 = resid2(rt, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
-        if (d2 < tau2) {
-          ++cnt;
-          sum += quant(d2, scale);
-        }
+#pragma unroll 2
+    for (int k = 0; k < rows; ++k) {
+      const double2 v0 = s2[3 * k], v1 = s2[3 * k + 1], v2 = s2[3 * k + 2];  // warp-wide broadcasts
+      const double da = resid2(ra, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
+      const double db = resid2(rb, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
+      if (da < tau2) {
+        ++cnt_a;
+        sum_a += quant(da, scale);
+      }
+      if (db < tau2) {
+        ++cnt_b;
+        sum_b += quant(db, scale);
       }
     }
   }
-  if (live && cnt > 0) {
-    atomicAdd(&counts[h], cnt);
-    atomicAdd(&sumq[h], (unsigned long long)sum);
+  if (live_a && cnt_a > 0) {
+    atomicAdd(&counts[ha], cnt_a);
+    atomicAdd(&sumq[ha], (unsigned long long)sum_a);
+  }
+  if (live_b && cnt_b > 0) {
+    atomicAdd(&counts[hb], cnt_b);
+    atomicAdd(&sumq[hb], (unsigned long long)sum_b);
   }
 }
 
@@ -255,7 +272,7 @@ __device__ __forceinline__ bool better(const Best& y, const Best& x) {  // is y 
   return y.id < x.id;
 }
 
-__global__ void __launch_bounds__(FIN_THREADS)
+__global__ void __launch_bounds__(FIN_THREADS, 2)
     finalize_kernel(const double* __restrict__ pq, const int32_t* __restrict__ count, int max_corr,
                     const double* __restrict__ rts, int n_hyp, double tau2, int refit, const int32_t* __restrict__ counts,
                     const unsigned long long* __restrict__ sumq, double* __restrict__ T, int32_t* __restrict__ counts_out,
@@ -394,29 +411,31 @@ int ransac_solve(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int 
   }
   const double tau2 = thresh * thresh;
   const double scale = 1099511627776.0 / tau2;
-  if (max_corr > 0) {
+  group_begin(ctx, GROUP_KABSCH);
+  {
+    const int gather_blocks = ceil_div(max_corr, PREP_THREADS), fit_blocks = ceil_div(n_hyp, PREP_THREADS);
     if (xyz_f64)
-      gather_pq_kernel<double><<<ceil_div(max_corr, 256), 256, 0, ctx->stream>>>(
-          (const double*)src_xyz, (const double*)tgt_xyz, corr, count, max_corr, pq);
+      gather_kabsch_kernel<double><<<gather_blocks + fit_blocks, PREP_THREADS, 0, ctx->stream>>>(
+          (const double*)src_xyz, (const double*)tgt_xyz, corr, count, max_corr, gather_blocks, pq, sample_idx, n_hyp, seed, rts, cnt, sq);
     else
-      gather_pq_kernel<float><<<ceil_div(max_corr, 256), 256, 0, ctx->stream>>>(
-          (const float*)src_xyz, (const float*)tgt_xyz, corr, count, max_corr, pq);
-    VFM_TRY(launch_check(ctx, "gather_pq_kernel"));
+      gather_kabsch_kernel<float><<<gather_blocks + fit_blocks, PREP_THREADS, 0, ctx->stream>>>(
+          (const float*)src_xyz, (const float*)tgt_xyz, corr, count, max_corr, gather_blocks, pq, sample_idx, n_hyp, seed, rts, cnt, sq);
+    VFM_TRY(launch_check(ctx, "gather_kabsch_kernel"));
   }
-  kabsch3_kernel<<<ceil_div(n_hyp, 128), 128, 0, ctx->stream>>>(pq, count, max_corr, sample_idx, n_hyp, seed, rts, cnt, sq);
-  VFM_TRY(launch_check(ctx, "kabsch3_kernel"));
+  group_end(ctx, GROUP_KABSCH, 1);
   if (max_corr >= 3) {
     const int hyp_blocks = ceil_div(n_hyp, HYP_PER_CTA);
-    const int max_tiles = ceil_div(max_corr, TILE_K);
-    int splits = ceil_div((int64_t)ctx->sm_count * 8, hyp_blocks);  // ~8 CTAs of 128 threads per SM
+    const int max_splits = ceil_div(max_corr, 64);                  // at least 64 correspondences per slice
+    int splits = ceil_div((int64_t)ctx->sm_count * 4, hyp_blocks);  // ~4 CTAs of 128 threads (x 2 hypotheses) per SM
     if (splits < 1) splits = 1;
-    if (splits > max_tiles) splits = max_tiles;
+    if (splits > max_splits) splits = max_splits;
     group_begin(ctx, GROUP_RANSAC);
-    score_kernel<<<dim3(hyp_blocks, splits), HYP_PER_CTA, 0, ctx->stream>>>(pq, count, max_corr, rts, n_hyp, tau2, scale,
-                                                                           cnt, sq);
+    score_kernel<<<dim3(hyp_blocks, splits), SCORE_THREADS, 0, ctx->stream>>>(pq, count, max_corr, rts, n_hyp, tau2, scale,
+                                                                             cnt, sq);
     VFM_TRY(launch_check(ctx, "score_kernel"));
     group_end(ctx, GROUP_RANSAC, 1);
   }
+  GroupScope g_fin(ctx, GROUP_FINALIZE, 1);
   finalize_kernel<<<1, FIN_THREADS, 0, ctx->stream>>>(pq, count, max_corr, rts, n_hyp, tau2, refit, cnt, sq, T, counts, sumq,
                                               mask, stats);
   return launch_check(ctx, "finalize_kernel");
