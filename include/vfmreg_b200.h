@@ -94,6 +94,18 @@ VFMREG_API int vfmreg_filter_correspondences(vfmreg_ctx* ctx, const int32_t* idx
                                   const int32_t* idx10, int64_t n, float min_cos, float ratio, int mutual,
                                   int32_t* corr, int32_t* count);
 
+/* a8 / a7 remainder.  The reference's brute-force block turns inner products of unit descriptors into L2 distances,
+ * sqrt(2 - 2 a.b + 1e-6), takes the per-row argmin (registration_node.py:191-209) and then keeps the n_points smallest
+ * distances (np.argpartition, :212-214; the non-mutual branch of find_correspondences does the same, :510-518).
+ *   vfmreg_l2_distances   dist[i] = sqrt(2 - 2 sim01[i] + 1e-6) (float32; +inf where idx01[i] < 0; idx01 may be NULL)
+ *   vfmreg_select_smallest  keeps the n_keep queries with the smallest distance (= largest similarity; ties at the
+ *                         boundary towards the lowest query index -- the reference leaves them to introselect) and emits
+ *                         their (query, match) pairs in query order into corr[n][2], their distances into dist (optional,
+ *                         NULL to skip) and their number into *count.  All pointers device. */
+VFMREG_API int vfmreg_l2_distances(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, int64_t n, float* dist);
+VFMREG_API int vfmreg_select_smallest(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, int64_t n, int64_t n_keep,
+                                      int32_t* corr, float* dist, int32_t* count);
+
 /* ---------------------------------------------------------------------------------------------
  * a10  RANSAC on a correspondence list.
  * Replaces o3d.pipelines.registration.registration_ransac_based_on_correspondence(src, tgt, corres, max_dist,
@@ -319,6 +331,32 @@ VFMREG_API int vfmreg_register_frame_vfm(vfmreg_ctx* ctx, const vfmreg_voxel_map
                                          const double* vfm_src, const double* vfm_tgt, int64_t k, const double* T0,
                                          double max_correspondence_distance, double kernel, int32_t max_iterations, double* T_out,
                                          int32_t* vfm_iterations, int32_t* iterations, int32_t* vfm_kept);
+
+/* ---------------------------------------------------------------------------------------------
+ * SURVEY 8f row 4 -- the hypothesis score of Open3D 0.18's registration_ransac_based_on_correspondence, the solver the
+ * reference actually calls (registration_node.py:312-327): every hypothesis (3 sampled correspondences -> rigid fit, as in
+ * vfmreg_ransac) transforms the WHOLE source cloud `src_all` and is scored against the nearest target point of every
+ * transformed point: fitness = #(nearest neighbour closer than max_dist) / n_src, rmse over those; best = larger fitness,
+ * then smaller rmse, then lower hypothesis id; no refit.  With the reference's literal max_dist = 10000 the winner is the
+ * hypothesis with the smallest scan -> map chamfer RMSE.  Open3D's source is not in the reference tree: this follows its
+ * published algorithm as recalled in SURVEY.md A.8 ("parity unpinned").
+ *   vfmreg_kdtree_create   balanced k-d tree over the target cloud (HOST float64 n x 3; built on the host, kept on the device)
+ *   vfmreg_kdtree_nearest  exact nearest neighbour of device queries (n x 3 float64): nn_idx in the caller's order (-1 when
+ *                          nothing is closer than max_dist), nn_d2 (may be NULL) its squared distance
+ *   vfmreg_ransac_nn_all   src_all (n_src x 3 float64 device); src_xyz / tgt_xyz / corr / count / sample_idx / seed as in
+ *                          vfmreg_ransac (the clouds the correspondences index); outputs (device): T[16], inliers[n_hyp] and
+ *                          sum_d2[n_hyp] (optional), stats[4] = {best hypothesis or -1, its inlier count, the bit pattern of
+ *                          its sum of squared distances (a double), unused}.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vfmreg_kdtree vfmreg_kdtree;
+VFMREG_API int vfmreg_kdtree_create(vfmreg_ctx* ctx, const double* xyz_host, int64_t n, vfmreg_kdtree** tree);
+VFMREG_API void vfmreg_kdtree_destroy(vfmreg_kdtree* tree);
+VFMREG_API int vfmreg_kdtree_nearest(vfmreg_ctx* ctx, const vfmreg_kdtree* tree, const double* queries, int64_t n, double max_dist,
+                                     int32_t* nn_idx, double* nn_d2);
+VFMREG_API int vfmreg_ransac_nn_all(vfmreg_ctx* ctx, const vfmreg_kdtree* tree, const double* src_all, int64_t n_src, const void* src_xyz,
+                                    const void* tgt_xyz, int xyz_f64, const int32_t* corr, const int32_t* count, int32_t max_corr,
+                                    const int32_t* sample_idx, int32_t n_hyp, uint64_t seed, double max_dist, double* T,
+                                    int32_t* inliers, double* sum_d2, int64_t* stats);
 
 #ifdef __cplusplus
 }

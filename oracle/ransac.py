@@ -152,3 +152,49 @@ def ransac(src_xyz, tgt_xyz, corr, sample_idx, thresh: float, refit: bool = Fals
     out.update(T=tm, mask=mask, fitness=n_in / k,
                rmse=float(np.sqrt(d2[mask].sum() / n_in)) if n_in else 0.0)
     return out
+
+
+def ransac_nn_all(src_xyz, tgt_xyz, corr, sample_idx, max_dist: float, fit=None):
+    """The hypothesis score of Open3D 0.18's ``registration_ransac_based_on_correspondence`` as recalled in SURVEY.md A.8
+    (call site registration_node.py:312-327; Open3D's source is not in the reference tree -> **parity unpinned**):
+    every hypothesis transforms the whole source cloud; fitness = share of transformed points whose nearest target point
+    (KD-tree query) is closer than ``max_dist``, inlier_rmse over those distances; best = higher fitness, then lower rmse
+    (then lower hypothesis id); the winning 3-point transform is returned as is.
+
+    ``fit(p3, q3) -> (R, t, valid)`` replaces the SVD-based 3-point fit (the tests pass the C restatement's so that the
+    hypotheses are bit-identical to the CUDA path's)."""
+    from scipy.spatial import cKDTree
+    src_xyz = np.asarray(src_xyz, dtype=np.float64)
+    tgt_xyz = np.asarray(tgt_xyz, dtype=np.float64)
+    corr = np.asarray(corr).reshape(-1, 2)
+    h = sample_idx.shape[0]
+    out = dict(T=np.eye(4), best=-1, inliers=np.full(h, -1, dtype=np.int64), sum_d2=np.zeros(h), fitness=0.0, rmse=0.0)
+    if corr.shape[0] < 3 or h == 0:
+        return out
+    src_c, tgt_c = src_xyz[corr[:, 0]], tgt_xyz[corr[:, 1]]
+    if fit is None:
+        r, t, valid = kabsch3_batch(src_c[sample_idx], tgt_c[sample_idx])
+    else:
+        fits = [fit(src_c[s], tgt_c[s]) for s in sample_idx]
+        r, t, valid = np.stack([f[0] for f in fits]), np.stack([f[1] for f in fits]), np.array([f[2] for f in fits])
+    tree = cKDTree(tgt_xyz)
+    cnt = np.full(h, -1, dtype=np.int64)
+    s2 = np.zeros(h)
+    for i in range(h):
+        if not valid[i]:
+            continue
+        x = src_xyz @ r[i].T + t[i]
+        d, _ = tree.query(x, k=1)
+        inl = d < max_dist
+        cnt[i] = int(inl.sum())
+        s2[i] = float((d[inl] ** 2).sum())
+    out.update(inliers=cnt, sum_d2=s2)
+    ok = np.nonzero(cnt > 0)[0]
+    if ok.size == 0:
+        return out
+    order = np.lexsort((ok, s2[ok] / cnt[ok], -cnt[ok]))
+    best = int(ok[order[0]])
+    tm = np.eye(4)
+    tm[:3, :3], tm[:3, 3] = r[best], t[best]
+    out.update(T=tm, best=best, fitness=cnt[best] / src_xyz.shape[0], rmse=float(np.sqrt(s2[best] / cnt[best])))
+    return out

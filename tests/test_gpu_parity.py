@@ -468,3 +468,119 @@ def test_resident_map_match_and_gate_floor(vfm):
         rm.match(a[:, :100])
     with pytest.raises(ValueError, match="Invalid shape"):
         vfm.ResidentMap(s["map_xyz"][:10], s["map_feat"])
+
+
+# ---- a8 / a7 remainder: L2 distances and "keep the n_points smallest" -------------------------------------------------------
+def test_l2_distances_and_select_smallest(vfm):
+    """registration_node.py:191-214 (brute-force L2 block + n_points selection) and :510-518 (non-mutual branch of
+    find_correspondences) against the oracle restatements; the latter is pinned to the reference by find_corr.npz."""
+    import os
+    from vfm_registration_b200 import compat
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "find_corr.npz"))
+    f0 = (g["f0"] / np.linalg.norm(g["f0"], axis=1, keepdims=True)).astype(np.float32)
+    f1 = (g["f1"] / np.linalg.norm(g["f1"], axis=1, keepdims=True)).astype(np.float32)
+    # the reference's own function on these unit vectors (oracle restatement, pinned by the golden fixture on raw features)
+    j0, j1 = match.find_correspondences(f0, f1, n_points=100, mutual_filter=False)
+    o = np.argsort(j0)
+    k0, k1 = compat.find_correspondences(f0, f1, n_points=100, mutual_filter=False)
+    assert np.array_equal(k0, j0[o]) and np.array_equal(k1, j1[o])
+    i0, i1 = match.find_correspondences(f0, f1, mutual_filter=True)
+    m0, m1 = compat.find_correspondences(f0, f1, mutual_filter=True)
+    assert np.array_equal(m0, i0) and np.array_equal(m1, i1)
+    # distances of the brute-force block
+    idx, dis = match.l2_block_argmin(f0, f1)
+    mt = vfm.match_nn(f0, f1)
+    d = vfm.l2_distances(mt).cpu().numpy()
+    assert np.array_equal(mt.idx01.cpu().numpy(), idx) and np.abs(d ** 2 - dis ** 2).max() < 2e-6   # 2 - 2 s: fp32 summation order of s
+    # larger case with ties at the boundary and unmatched queries: the n smallest (distance, index) pairs, in query order
+    rng = np.random.default_rng(5)
+    n = 40_000
+    sim = torch.from_numpy(np.round(rng.uniform(-0.2, 1.0, n), 3).astype(np.float32)).cuda()   # 1201 distinct values -> many ties
+    idx01 = torch.from_numpy(rng.integers(0, 1000, n).astype(np.int32)).cuda()
+    idx01[::97] = -1
+    mt2 = vfm.api.MatchResult(idx01, sim, None)
+    simh, idxh = sim.cpu().numpy(), idx01.cpu().numpy()
+    valid = np.nonzero(idxh >= 0)[0]
+    for keep in (0, 1, 5000, len(valid) - 1, len(valid), n + 5):
+        corr, dist = vfm.select_smallest(mt2, keep, return_distance=True)
+        corr, dist = corr.cpu().numpy(), dist.cpu().numpy()
+        order = valid[np.lexsort((valid, -simh[valid]))][:min(keep, len(valid))]   # largest similarity first, then lowest index
+        want = np.sort(order)
+        assert np.array_equal(corr[:, 0], want) and np.array_equal(corr[:, 1], idxh[want])
+        assert np.allclose(dist, np.sqrt(2 - 2 * simh[want].astype(np.float64) + 1e-6), atol=2e-6)
+
+
+# ---- SURVEY 8f row 4: the Open3D-style hypothesis score (nearest neighbour of every source point) ---------------------------
+def test_kdtree_nearest_exact(vfm):
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(2)
+    for n, nq in ((1, 10), (7, 50), (5000, 4000), (200_000, 20_000)):
+        pts = np.c_[rng.uniform(-50, 50, (n, 2)), rng.uniform(-2, 8, n)]
+        if n > 100:
+            pts[5] = pts[3]                                   # duplicate point
+        q = np.r_[np.c_[rng.uniform(-60, 60, (nq - 3, 2)), rng.uniform(-30, 40, nq - 3)], [[900.0, -700.0, 300.0]], pts[:2] if n > 1 else pts[[0, 0]]]
+        tree = vfm.KdTree(pts)
+        idx, d2 = tree.nearest(q)
+        d, j = cKDTree(pts).query(q)
+        assert np.array_equal(np.sum((pts[idx.cpu().numpy()] - q) ** 2, 1), d2.cpu().numpy())   # the reported point, exactly
+        assert np.allclose(np.sqrt(d2.cpu().numpy()), d, rtol=1e-12, atol=1e-12)                   # ... is the nearest one
+        idx2, _ = tree.nearest(q, max_dist=1.0)
+        assert np.array_equal(idx2.cpu().numpy() >= 0, d < 1.0)
+
+
+@pytest.mark.parametrize("n_map,n_scan,n_hyp,max_dist", [(3000, 700, 512, 1e4), (20_000, 3000, 2048, 1e4), (20_000, 3000, 1024, 0.5),
+                                                         (60_000, 9000, 512, 1e4)])
+def test_ransac_nn_all_vs_oracle(vfm, n_map, n_scan, n_hyp, max_dist):
+    """Winner, per-hypothesis inlier counts and distance sums against the cKDTree restatement (oracle/ransac.py), with the
+    hypotheses of the C restatement so that both sides score bit-identical transforms."""
+    # a scan whose every point lies on the map (the chamfer criterion is about geometry: uniform clutter thrown outside the
+    # map's bounding box by the true pose would dominate it); two thirds of the correspondences are wrong
+    s = synth.make_pair(41, n_map, n_scan, 16, inlier_frac=1.0)
+    rng = np.random.default_rng(3)
+    k = min(600, n_scan // 2)
+    q = np.sort(rng.permutation(n_scan)[:k])
+    j = s["perm"][q].copy()
+    wrong = rng.permutation(k)[: 2 * k // 3]
+    j[wrong] = rng.integers(0, n_map, len(wrong))
+    corr = np.stack([q, j], 1).astype(np.int32)
+    si = ransac.sample_indices(5, n_hyp, len(corr))
+    si[3] = [2, 2, 2]                                        # degenerate sample
+    fit = lambda p, q: cref.kabsch3(p, q)                      # noqa: E731
+    o = ransac.ransac_nn_all(s["scan_xyz"], s["map_xyz"], corr, si, max_dist, fit=fit)
+    g = vfm.ransac_nn_all(s["scan_xyz"], s["map_xyz"], corr, sample_idx=si, max_dist=max_dist)
+    assert np.array_equal(g.inliers.cpu().numpy(), o["inliers"]) and g.inliers[3].item() == -1
+    assert np.allclose(g.sum_d2.cpu().numpy(), o["sum_d2"], rtol=1e-11, atol=1e-9)
+    assert g.best == o["best"] and np.array_equal(g.T, o["T"])
+    assert abs(g.fitness - o["fitness"]) < 1e-12 and abs(g.rmse - o["rmse"]) < 1e-9
+    if max_dist >= 1e4:
+        assert g.fitness == 1.0
+    rte, rre = synth.pose_errors(g.T, s["T_gt"])
+    assert rte < 1.0 and rre < 5.0
+    # device-side sampler, and K < 3 -> identity
+    g2 = vfm.ransac_nn_all(s["scan_xyz"], s["map_xyz"], corr, n_hyp=256, seed=9, max_dist=max_dist)
+    o2 = ransac.ransac_nn_all(s["scan_xyz"], s["map_xyz"], corr, cref.sample_indices(9, 256, len(corr)), max_dist, fit=fit)
+    assert g2.best == o2["best"] and np.array_equal(g2.T, o2["T"])
+    g3 = vfm.ransac_nn_all(s["scan_xyz"], s["map_xyz"], corr[:2], n_hyp=16, max_dist=max_dist)
+    assert g3.best == -1 and np.array_equal(g3.T, np.eye(4)) and g3.fitness == 0.0
+
+
+def test_compat_node_default_score_is_open3d_style(vfm):
+    """At the reference's literal max_correspondence_distance = 10000 the shim scores hypotheses as Open3D does (nearest
+    neighbour of every scan point); checked against the oracle chain, with and without the reference's pre-processing."""
+    from vfm_registration_b200 import compat
+    s = synth.make_pair(9, 5000, 1500, 64, inlier_frac=0.5)
+    vmap_arr = np.c_[s["map_xyz"], s["map_feat"]].astype(np.float32)
+    scan_arr = np.c_[s["scan_xyz"], s["scan_feat"]].astype(np.float32)
+    node = compat.RegistrationNode(ransac_iters=512, preprocess=False)
+    assert node.score == "nn_all" and compat.RegistrationNode(max_correspondence_distance=1.0).score == "corr"
+    pose, _ = node.ransac_registration(vmap_arr, scan_arr, "vfm")
+    m = cref.match_nn(s["scan_feat"], s["map_feat"])
+    corr = match.filter_correspondences(m["idx01"], m["sim01"], min_cos=0.8)
+    o = ransac.ransac_nn_all(s["scan_xyz"], s["map_xyz"], corr, cref.sample_indices(42, 512, len(corr)), 1e4, fit=lambda p, q: cref.kabsch3(p, q))
+    assert np.array_equal(pose, o["T"])
+    rte, rre = synth.pose_errors(pose, s["T_gt"])
+    assert rte < 0.5 and rre < 2.0
+    node2 = compat.RegistrationNode(ransac_iters=512)          # with the voxel pre-processing of registration_node.py:287-291, 396-425
+    pose2, icp = node2.ransac_registration(vmap_arr, scan_arr, "vfm", run_icp=True)
+    rte2, rre2 = synth.pose_errors(icp, s["T_gt"])
+    assert pose2.shape == (4, 4) and rte2 < 0.2 and rre2 < 0.5

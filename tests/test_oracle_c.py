@@ -144,3 +144,23 @@ def test_get_vfm_correspondences_layout():
     # nothing passes a gate of 1.1 -> K = 0, no crash (the reference would hit UB, VoxelHashMap.cpp:547-550)
     e0, e1 = match.get_vfm_correspondences(pts, mp, 1.1)
     assert e0.shape == (0, 3) and e1.shape == (0, 3)
+
+
+def test_nn_all_oracle_known_answer():
+    """The Open3D-style score (oracle/ransac.py:ransac_nn_all): with max_dist = 1e4 every point counts, the planted pose wins,
+    and the score of a hypothesis equals a brute-force chamfer evaluation."""
+    from oracle import ransac
+    from vfm_registration_b200 import synth
+    s = synth.make_pair(5, 1500, 400, 8, inlier_frac=0.6)
+    good = np.nonzero(s["perm"] >= 0)[0][:150]
+    corr = np.stack([good, s["perm"][good]], 1).astype(np.int32)
+    si = ransac.sample_indices(1, 64, len(corr))
+    o = ransac.ransac_nn_all(s["scan_xyz"], s["map_xyz"], corr, si, 1e4)
+    assert o["fitness"] == 1.0 and (o["inliers"][o["inliers"] >= 0] == 400).all()
+    rte, rre = synth.pose_errors(o["T"], s["T_gt"])
+    assert rte < 0.5 and rre < 2.0
+    h = o["best"]
+    x = s["scan_xyz"].astype(np.float64) @ o["T"][:3, :3].T + o["T"][:3, 3]
+    d2 = ((x[:, None, :] - s["map_xyz"].astype(np.float64)[None]) ** 2).sum(-1).min(1)
+    assert abs(d2.sum() - o["sum_d2"][h]) < 1e-9 * max(1.0, d2.sum())
+    assert o["sum_d2"][h] == min(v for v, c in zip(o["sum_d2"], o["inliers"]) if c > 0)

@@ -58,6 +58,8 @@ _SIGS = {
     "vfmreg_group_time_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vfmreg_match_nn": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     "vfmreg_filter_correspondences": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_int, _P, _P]),
+    "vfmreg_l2_distances": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "vfmreg_select_smallest": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "vfmreg_ransac": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int32, _P, C.c_int32, C.c_uint64, C.c_double, C.c_int,
                                 _P, _P, _P, _P, _P]),
     "vfmreg_register": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(RegisterParams), _P, _P,
@@ -89,6 +91,11 @@ _SIGS = {
     "vfmreg_voxel_map_size": (C.c_int64, [_P]),
     "vfmreg_voxel_map_points": (C.c_int, [_P, _P, _P, _P]),
     "vfmreg_voxel_map_nearest": (C.c_int, [_P, _P, _P, C.c_int64, C.c_double, _P, _P]),
+    "vfmreg_kdtree_create": (C.c_int, [_P, _P, C.c_int64, C.POINTER(_P)]),
+    "vfmreg_kdtree_destroy": (None, [_P]),
+    "vfmreg_kdtree_nearest": (C.c_int, [_P, _P, _P, C.c_int64, C.c_double, _P, _P]),
+    "vfmreg_ransac_nn_all": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int, _P, _P, C.c_int32, _P, C.c_int32, C.c_uint64, C.c_double,
+                                       _P, _P, _P, _P]),
     "vfmreg_register_frame": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P,
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vfmreg_register_frame_vfm": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P, C.c_double, C.c_double, C.c_int32, _P,

@@ -26,7 +26,7 @@ from ._lib import VfmRegError
 
 __all__ = ["Context", "get_context", "match_nn", "filter_correspondences", "ransac_kabsch", "register", "RegResult",
            "MatchResult", "RansacResult", "VfmRegError", "CameraSpec", "project_gather", "register_batch", "ResidentMap",
-           "register_scans"]
+           "register_scans", "l2_distances", "select_smallest", "KdTree", "ransac_nn_all", "RansacNNResult"]
 
 _ALGO = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}
 
@@ -152,6 +152,34 @@ def filter_correspondences(match: MatchResult, *, min_cos: Optional[float] = Non
     return corr[: int(count.item())]
 
 
+def l2_distances(match: MatchResult, *, device=None) -> torch.Tensor:
+    """sqrt(2 - 2 s + 1e-6) per query: the L2 distance between unit descriptors in the form the reference's brute-force
+    block computes it (registration_node.py:197-198).  +inf where a query has no match."""
+    ctx = get_context(device)
+    n = match.idx01.shape[0]
+    dist = torch.empty(n, dtype=torch.float32, device=match.idx01.device)
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_l2_distances(ctx.handle, _ptr(match.idx01), _ptr(match.sim01), n, _ptr(dist)), "vfmreg_l2_distances")
+    return dist
+
+
+def select_smallest(match: MatchResult, n_points: int, *, return_distance: bool = False, device=None):
+    """The ``n_points`` nearest-neighbour pairs with the smallest descriptor distance, (K, 2) int32 in query order -- the
+    reference's "keep only top N correspondences (smallest distance)" (registration_node.py:212-214, 510-518; its
+    ``np.argpartition`` leaves boundary ties to chance, here the lowest query index wins)."""
+    ctx = get_context(device)
+    n = match.idx01.shape[0]
+    dev = match.idx01.device
+    corr = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    dist = torch.empty(n, dtype=torch.float32, device=dev) if return_distance else None
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_select_smallest(ctx.handle, _ptr(match.idx01), _ptr(match.sim01), n, int(n_points), _ptr(corr), _ptr(dist),
+                                             _ptr(count)), "vfmreg_select_smallest")
+    k = int(count.item())
+    return (corr[:k], dist[:k]) if return_distance else corr[:k]
+
+
 @dataclass
 class RansacResult:
     T: np.ndarray            # (4, 4) float64
@@ -210,6 +238,109 @@ def ransac_kabsch(src_xyz, tgt_xyz, corr, *, sample_idx=None, n_hyp: Optional[in
     rmse = math.sqrt(float(st[2]) / 2.0 ** 40 * thresh * thresh / n_in) if n_in else 0.0
     return RansacResult(T=t.cpu().numpy().reshape(4, 4), best=int(st[0]), n_inliers=n_in, n_corr=int(st[3]),
                         fitness=(n_in / k if k else 0.0), rmse=rmse, counts=counts, sumq=sumq, mask=mask[:k].bool())
+
+
+class KdTree:
+    """Balanced k-d tree over a point cloud, built on the host and kept on the device (``vfmreg_kdtree_create``): exact
+    nearest neighbours at any distance -- what the Open3D-style hypothesis score needs (``ransac_nn_all``)."""
+
+    def __init__(self, xyz, *, device=None):
+        self.ctx = get_context(device)
+        x = xyz.detach().cpu().numpy() if isinstance(xyz, torch.Tensor) else np.asarray(xyz)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.ndim != 2 or x.shape[1] != 3 or x.shape[0] == 0:
+            raise ValueError(f"Invalid shape for xyz: {x.shape}")
+        self.n = int(x.shape[0])
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.vfmreg_kdtree_create(self.ctx.handle, x.ctypes.data, self.n, C.byref(h)), "vfmreg_kdtree_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.vfmreg_kdtree_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nearest(self, queries, max_dist: float = 1e30):
+        """(index (n,) int32 in the caller's order, -1 when nothing is closer than max_dist; squared distance (n,) float64)."""
+        dev = torch.device("cuda", self.ctx.device)
+        q = queries if isinstance(queries, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(queries))
+        if q.dim() != 2 or q.shape[1] != 3:
+            raise ValueError(f"Invalid shape for queries: {tuple(q.shape)}")
+        q = q.to(device=dev, dtype=torch.float64).contiguous()
+        n = q.shape[0]
+        idx = torch.empty(n, dtype=torch.int32, device=dev)
+        d2 = torch.empty(n, dtype=torch.float64, device=dev)
+        self.ctx.bind_stream()
+        _lib.check(self.ctx.lib.vfmreg_kdtree_nearest(self.ctx.handle, self.handle, _ptr(q), n, float(max_dist), _ptr(idx), _ptr(d2)),
+                   "vfmreg_kdtree_nearest")
+        return idx, d2
+
+
+@dataclass
+class RansacNNResult:
+    T: np.ndarray            # (4, 4) float64
+    best: int
+    n_inliers: int           # source points whose nearest target point is closer than max_dist
+    fitness: float           # n_inliers / number of source points
+    rmse: float              # over those nearest-neighbour distances
+    inliers: torch.Tensor    # (H,) int32 per hypothesis, -1 for degenerate samples
+    sum_d2: torch.Tensor     # (H,) float64
+
+
+def ransac_nn_all(src_xyz, tgt_xyz, corr, *, sample_idx=None, n_hyp: Optional[int] = None, max_dist: float = 1e4, seed: int = 42,
+                  tree: Optional[KdTree] = None, device=None) -> RansacNNResult:
+    """Correspondence RANSAC with the hypothesis score Open3D 0.18 uses (the reference's solver call,
+    registration_node.py:312-327): hypotheses come from 3 sampled correspondences as in ``ransac_kabsch``, but each one is
+    scored by transforming ALL of ``src_xyz`` and looking up every point's nearest neighbour in ``tgt_xyz`` -- fitness =
+    share of points closer than ``max_dist``, rmse over those; best = higher fitness, then lower rmse.  With the
+    reference's ``max_dist = 10000`` that is the hypothesis with the smallest scan -> map chamfer RMSE."""
+    ctx = get_context(device)
+    dev = torch.device("cuda", ctx.device)
+
+    def xyz64(x, name):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if x.dim() != 2 or x.shape[1] != 3:
+            raise ValueError(f"Invalid shape for {name}: {tuple(x.shape)}")
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+
+    src, tgt = xyz64(src_xyz, "src_xyz"), xyz64(tgt_xyz, "tgt_xyz")
+    if src.shape[0] == 0 or tgt.shape[0] == 0:
+        raise ValueError("Invalid shape: empty cloud")
+    if tree is None:
+        tree = KdTree(tgt, device=ctx.device)
+    if isinstance(corr, np.ndarray):
+        corr = torch.from_numpy(np.ascontiguousarray(corr.reshape(-1, 2), dtype=np.int32))
+    corr = corr.to(device=dev, dtype=torch.int32).contiguous()
+    k = corr.shape[0]
+    if sample_idx is not None:
+        if isinstance(sample_idx, np.ndarray):
+            sample_idx = torch.from_numpy(np.ascontiguousarray(sample_idx, dtype=np.int32))
+        sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
+        n_hyp = sample_idx.shape[0]
+    if not n_hyp or n_hyp <= 0:
+        raise ValueError("ransac_nn_all: need sample_idx or a positive n_hyp")
+    count = torch.full((1,), k, dtype=torch.int32, device=dev)
+    t = torch.empty(16, dtype=torch.float64, device=dev)
+    inl = torch.empty(n_hyp, dtype=torch.int32, device=dev)
+    sums = torch.empty(n_hyp, dtype=torch.float64, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    corr_arg = corr if k > 0 else torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_ransac_nn_all(ctx.handle, tree.handle, _ptr(src), src.shape[0], _ptr(src), _ptr(tgt), 1, _ptr(corr_arg),
+                                           _ptr(count), k, _ptr(sample_idx), n_hyp, seed & 0xFFFFFFFFFFFFFFFF, float(max_dist), _ptr(t),
+                                           _ptr(inl), _ptr(sums), _ptr(stats)), "vfmreg_ransac_nn_all")
+    st = stats.cpu()
+    n_in = int(st[1])
+    s2 = float(st[2:3].view(torch.float64)[0])
+    return RansacNNResult(T=t.cpu().numpy().reshape(4, 4), best=int(st[0]), n_inliers=n_in, fitness=n_in / src.shape[0],
+                          rmse=math.sqrt(s2 / n_in) if n_in else 0.0, inliers=inl, sum_d2=sums)
 
 
 @dataclass

@@ -54,6 +54,22 @@ def register_frame(points, voxel_map: "VoxelHashMap", initial_guess, max_corresp
     return _voxel.register_frame_vfm(points[:, :3], core, vfm_src, vfm_tgt, T0, max_correspondance_distance, kernel)
 
 
+def find_correspondences(feats0, feats1, n_points: int = 5000, mutual_filter: bool = True, device=None):
+    """The nested ``find_correspondences`` of compute_correspondences (registration_node.py:482-538, adapted there from
+    TEASER++): nearest neighbours 0 -> 1; with ``mutual_filter`` the pairs that are also nearest neighbours 1 -> 0, else the
+    ``min(n_points, len - 1)`` pairs with the smallest distance.  Returns (idx0, idx1) int64 arrays in query order.
+
+    The search is the inner-product search of L2-renormalised rows, i.e. the reference's L2 nearest neighbour for
+    unit-norm descriptors (which the learned baseline descriptors it is used with are)."""
+    m = api.match_nn(feats0, feats1, normalize=True, mutual=mutual_filter, device=device)
+    if mutual_filter:
+        corr = api.filter_correspondences(m, mutual=True, device=device)
+    else:
+        corr = api.select_smallest(m, min(int(n_points), m.idx01.shape[0] - 1), device=device)
+    corr = corr.cpu().numpy().astype(np.int64)
+    return corr[:, 0], corr[:, 1]
+
+
 class VoxelHashMap:
     """The reference object's two point stores: ``map_`` for (N, 3) clouds and ``map_n_`` for descriptor-carrying clouds,
     each keeping the first ``max_points_per_voxel`` points per voxel; both live on the device."""
@@ -156,10 +172,19 @@ class RegistrationNode:
 
     def __init__(self, ransac_iters: int = 50000, max_correspondence_distance: float = 10000.0, min_cosine: float = 0.8,
                  seed: int = 42, device=None, *, voxel_size: float = 1.0, max_points_per_voxel: int = 20, max_range: float = 100.0,
-                 initial_threshold: float = 2.0, preprocess: bool = True):
+                 initial_threshold: float = 2.0, preprocess: bool = True, score: str = "auto"):
         """``voxel_size`` / ``max_points_per_voxel`` / ``max_range`` / ``initial_threshold`` are the KISS-ICP config values the
         reference reads (config.mapping.voxel_size = max_range / 100, 20, 100 m, config.adaptive_threshold.initial_threshold
-        = 2).  ``preprocess=False`` skips the voxel steps: the clouds are matched at the density they are given."""
+        = 2).  ``preprocess=False`` skips the voxel steps: the clouds are matched at the density they are given.
+
+        ``score``: how a RANSAC hypothesis is scored.  "nn_all" = as Open3D 0.18 does it inside the reference's solver call
+        (registration_node.py:319-327): nearest map point of EVERY transformed scan point, fitness / rmse over
+        those -- with the reference's max_correspondence_distance = 10000 the minimum scan -> map chamfer RMSE wins.
+        "corr" = inlier count and residuals over the correspondence list (BASELINE.json's form).  "auto" (default) = "nn_all"
+        at the reference's literal distance (>= 10000), "corr" for a real inlier threshold."""
+        if score not in ("auto", "nn_all", "corr"):
+            raise ValueError(f"Invalid score: {score}")
+        self.score = ("nn_all" if max_correspondence_distance >= 1e4 else "corr") if score == "auto" else score
         self.ransac_iters, self.max_dist, self.min_cosine, self.seed, self.device = (ransac_iters, max_correspondence_distance,
                                                                                    min_cosine, seed, device)
         self.voxel_size, self.max_points_per_voxel, self.max_range = voxel_size, max_points_per_voxel, max_range
@@ -199,7 +224,10 @@ class RegistrationNode:
             raise ValueError("Invalid shape")
         kw = dict(normalize=True, min_cos=self.min_cosine, ransac_iters=self.ransac_iters, inlier_thresh=self.max_dist,
                   seed=self.seed, device=self.device)
-        if not self.preprocess:
+        if self.score == "nn_all":
+            ransac_pose, scan_xyz = self._ransac_nn_all(voxel_map, raw_scan)
+            r = None
+        elif not self.preprocess:
             r = api.register(raw_scan[:, :3], voxel_map[:, :3], raw_scan[:, 3:], voxel_map[:, 3:], **kw)
             scan_xyz, vmap = raw_scan[:, :3], None
         else:
@@ -215,7 +243,8 @@ class RegistrationNode:
                 r = api.register_scans(res_map, [(np.ascontiguousarray(q[:, :3]), np.ascontiguousarray(q[:, 3:]))], **skw)[0]
                 if len(r.corr) >= 75:
                     break
-        ransac_pose = r.T
+        if r is not None:
+            ransac_pose = r.T
         if not run_icp:
             return ransac_pose, None
         ransac_pose = ransac_pose.copy()
@@ -225,6 +254,31 @@ class RegistrationNode:
         sigma = self.initial_threshold
         pose = register_frame(scan_xyz, icp_map, ransac_pose, 3 * sigma, sigma / 3)  # :337-341
         return ransac_pose, pose
+
+    def _ransac_nn_all(self, voxel_map: np.ndarray, raw_scan: np.ndarray):
+        """Correspondences as above, solved with the Open3D-style hypothesis score: source = the voxelised scan (`voxel_scan`,
+        registration_node.py:287-288), target = the points of the 3-D voxel hash map (`voxel_map_3d`, :290-293), hypotheses
+        from the descriptor correspondences (:312-327).  Returns (pose, voxelised scan xyz)."""
+        dev = api.get_context(self.device).device
+        if not self.preprocess:
+            m = api.match_nn(raw_scan[:, 3:], voxel_map[:, 3:], normalize=True, device=dev)
+            corr = api.filter_correspondences(m, min_cos=self.min_cosine, device=dev)
+            src_xyz, tgt_xyz = raw_scan[:, :3], voxel_map[:, :3]
+        else:
+            vmap = self._new_map()
+            vmap.add_points(voxel_map)
+            voxel_scan = self._voxel_scan(raw_scan)
+            src_xyz, tgt_xyz = voxel_scan[:, :3], vmap._xyzn          # the same thinning as the 3-D map: same kept points
+            corr = None
+            for leaf in (5.0, 1.0):                                   # "Voxelized too sparse, retrying ..." (:420-423)
+                q, qidx = voxel_down_sample(voxel_scan, leaf, return_index=True)
+                m = vmap.resident().match(q[:, 3:], min_cos=self.min_cosine, second=False)
+                corr = api.filter_correspondences(m, min_cos=self.min_cosine, device=dev)
+                corr[:, 0] = torch.from_numpy(np.asarray(qidx)).to(corr.device, torch.int32)[corr[:, 0].long()]   # rows of voxel_scan
+                if corr.shape[0] >= 75:
+                    break
+        r = api.ransac_nn_all(src_xyz, tgt_xyz, corr, n_hyp=self.ransac_iters, max_dist=self.max_dist, seed=self.seed, device=dev)
+        return r.T, src_xyz
 
     def icp_registration(self, voxel_map: np.ndarray, raw_scan: np.ndarray, initial_pose=None, dist: float = 3):
         """registration_node.py:358-394: double-down-sample the scan, thin the map into a voxel hash map, ICP from

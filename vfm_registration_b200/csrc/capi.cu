@@ -922,6 +922,23 @@ int vfmreg_filter_correspondences(vfmreg_ctx* ctx, const int32_t* idx01, const f
   return filter_corr(ctx, idx01, sim01, sec01, idx10, n, min_cos, ratio, mutual, corr, count);
 }
 
+int vfmreg_select_smallest(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, int64_t n, int64_t n_keep, int32_t* corr,
+                           float* dist, int32_t* count) {
+  VFM_CHECK_ARG(ctx && idx01 && sim01 && corr && count, "select_smallest: null pointer");
+  VFM_CHECK_ARG(n >= 0 && n_keep >= 0, "select_smallest: negative size");
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  arena_reset(ctx);
+  VFM_TRY(arena_reserve(ctx, arena_bytes((size_t)n + 1, 4) + 4096));
+  return select_top(ctx, idx01, sim01, n, n_keep, corr, dist, count);
+}
+
+int vfmreg_l2_distances(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, int64_t n, float* dist) {
+  VFM_CHECK_ARG(ctx && sim01 && dist, "l2_distances: null pointer");
+  VFM_CHECK_ARG(n >= 0, "l2_distances: negative n");
+  VFM_CUDA(cudaSetDevice(ctx->device));
+  return l2_from_sim(ctx, idx01, sim01, n, dist);
+}
+
 int vfmreg_ransac(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int xyz_f64, const int32_t* corr,
                   const int32_t* count, int32_t max_corr, const int32_t* sample_idx, int32_t n_hyp, uint64_t seed,
                   double thresh, int refit, double* T, int32_t* counts, int64_t* sumq, uint8_t* mask, int64_t* stats) {

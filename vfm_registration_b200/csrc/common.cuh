@@ -196,6 +196,11 @@ int gather_rows(vfmreg_ctx* ctx, const int32_t* pairs, const int32_t* count, int
 // filter.cu
 int filter_corr(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const float* sec01, const int32_t* idx10,
                 int64_t n, float min_cos, float ratio, int mutual, int32_t* corr, int32_t* count);
+// keep the n_keep queries with the largest similarity (= smallest L2 distance of unit vectors), ties towards the lowest
+// index, pairs in query order; dist (optional) = sqrt(2 - 2 s + 1e-6) of the kept pairs
+int select_top(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, int64_t n, int64_t n_keep, int32_t* corr, float* dist,
+               int32_t* count);
+int l2_from_sim(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, int64_t n, float* dist);
 // second half of the pruned mutual check: keep cand[k] = (i, j) iff back[k] == i (back = nearest query of map row j)
 int filter_mutual_list(vfmreg_ctx* ctx, const int32_t* cand, const int32_t* cand_count, const int32_t* back, int64_t max_rows,
                        int32_t* corr, int32_t* count);

@@ -116,6 +116,117 @@ int filter_corr(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, const
   return launch_check(ctx, "filter_corr");
 }
 
+// ---- "keep the n_points smallest distances" (registration_node.py:212-214 and :510-518) -------------------------------------
+// The reference takes np.argpartition(dists, n)[:n] of the nearest-neighbour distances (an unordered set; ties at the
+// boundary are whatever introselect leaves).  For unit vectors the distance sqrt(2 - 2 s + 1e-6) falls with the similarity s,
+// so the set is the n largest similarities: a 4 x 8-bit radix select over the order-preserving integer image of s finds
+// the n-th largest key, ties at the boundary are broken towards the lowest query index (deterministic), and the kept
+// (query, match) pairs are emitted in query order.  Queries without a match (index < 0) never qualify.  One CTA.
+__device__ __forceinline__ uint32_t order_key(float s) {
+  const uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(FILTER_THREADS) select_top_kernel(const int32_t* __restrict__ idx01, const float* __restrict__ sim01, int n,
+                                                                   int n_keep, int32_t* __restrict__ eq_list,
+                                                                   int32_t* __restrict__ corr, float* __restrict__ dist,
+                                                                   int32_t* __restrict__ count) {
+  __shared__ unsigned hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need, s_valid;
+  const int t = threadIdx.x;
+  // how many queries have a match at all
+  if (t == 0) s_valid = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = t; i < n; i += FILTER_THREADS) mine += idx01[i] >= 0 ? 1 : 0;
+  if (mine) atomicAdd(&s_valid, mine);
+  __syncthreads();
+  const int valid = s_valid;
+  const int want = min(max(n_keep, 0), valid);
+  uint32_t thr_key = 0;   // keep key > thr_key, plus the first `need_eq` (by index) with key == thr_key
+  int need_eq = 0;
+  if (want > 0 && want < valid) {
+    if (t == 0) {
+      s_prefix = 0;
+      s_need = want;
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int bin = t; bin < 256; bin += FILTER_THREADS) hist[bin] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      for (int i = t; i < n; i += FILTER_THREADS) {
+        if (idx01[i] < 0) continue;
+        const uint32_t key = order_key(sim01[i]);
+        if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (t == 0) {   // walk the bins from the largest digit down to the one that holds the s_need-th largest key
+        int need = s_need, bin = 255;
+        for (; bin > 0; --bin) {
+          if ((int)hist[bin] >= need) break;
+          need -= (int)hist[bin];
+        }
+        s_prefix = prefix | ((uint32_t)bin << shift);
+        s_need = need;
+      }
+      __syncthreads();
+    }
+    thr_key = s_prefix;
+    need_eq = s_need;
+  }
+  const bool all = (want == valid);
+  // boundary ties: the indices of the queries whose key equals the threshold, in index order
+  int cut = -1;   // equal keys are kept up to this query index
+  if (!all && want > 0) {
+    ordered_compact(
+        n, [&](int i) { return idx01[i] >= 0 && order_key(sim01[i]) == thr_key; }, [&](int i, int pos) { eq_list[pos] = i; });
+    __syncthreads();
+    cut = eq_list[need_eq - 1];
+  }
+  const int total = ordered_compact(
+      n,
+      [&](int i) {
+        if (idx01[i] < 0 || want == 0) return false;
+        if (all) return true;
+        const uint32_t key = order_key(sim01[i]);
+        return key > thr_key || (key == thr_key && i <= cut);
+      },
+      [&](int i, int pos) {
+        corr[2 * pos] = i;
+        corr[2 * pos + 1] = idx01[i];
+        if (dist) dist[pos] = __fsqrt_rn(__fadd_rn(__fsub_rn(2.0f, __fmul_rn(2.0f, sim01[i])), 1e-6f));
+      });
+  if (t == 0) *count = total;
+}
+
+int select_top(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, int64_t n, int64_t n_keep, int32_t* corr, float* dist,
+               int32_t* count) {
+  VFM_CHECK_ARG(n >= 0 && n < (1LL << 31), "select_smallest: bad n");
+  int32_t* eq_list = arena_take<int32_t>(ctx, (size_t)(n > 0 ? n : 1));
+  if (!eq_list) {
+    set_error("select_smallest: scratch arena too small");
+    return VFMREG_ERR_ALLOC;
+  }
+  select_top_kernel<<<1, FILTER_THREADS, 0, ctx->stream>>>(idx01, sim01, (int)n, (int)(n_keep < n ? n_keep : n), eq_list, corr, dist, count);
+  return launch_check(ctx, "select_top_kernel");
+}
+
+// dist[i] = sqrt(2 - 2 s_i + 1e-6): the L2 distance of unit vectors as the reference's brute-force block writes it
+// (registration_node.py:197-198); queries without a match get +inf
+__global__ void l2_from_sim_kernel(const int32_t* __restrict__ idx01, const float* __restrict__ sim01, int n, float* __restrict__ dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dist[i] = (idx01 && idx01[i] < 0) ? INFINITY : __fsqrt_rn(__fadd_rn(__fsub_rn(2.0f, __fmul_rn(2.0f, sim01[i])), 1e-6f));
+}
+
+int l2_from_sim(vfmreg_ctx* ctx, const int32_t* idx01, const float* sim01, int64_t n, float* dist) {
+  if (n <= 0) return VFMREG_OK;
+  l2_from_sim_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(idx01, sim01, (int)n, dist);
+  return launch_check(ctx, "l2_from_sim_kernel");
+}
+
 // ---- pruned mutual check -------------------------------------------------------------------------------------------
 // idx10[j] is only ever read at j = idx01[i] of the queries that passed the gate, so the reverse search runs over those
 // map rows only (a compacted copy) instead of all m; the answer per row is unchanged because rows are independent.

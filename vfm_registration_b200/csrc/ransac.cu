@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(PREP_THREADS)
   }
   const int h = (blockIdx.x - gather_blocks) * PREP_THREADS + threadIdx.x;
   if (h >= n_hyp) return;
-  sumq[h] = 0ULL;
+  if (sumq) sumq[h] = 0ULL;
   double* rt = rts + (int64_t)h * 12;
   if (K < 3) {
     counts[h] = -1;
@@ -387,6 +387,19 @@ __global__ void __launch_bounds__(FIN_THREADS, 2)
     const int i = t >> 2, j = t & 3;
     T[t] = (i == 3) ? ((j == 3) ? 1.0 : 0.0) : ((j == 3) ? rt_s[9 + i] : rt_s[i * 3 + j]);
   }
+}
+
+// hypotheses only (no pq gather): rts[n_hyp][12], counts[h] = 0 or -1 (degenerate sample)
+int ransac_hypotheses(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int xyz_f64, const int32_t* corr, const int32_t* count,
+                      int32_t max_corr, const int32_t* sample_idx, int32_t n_hyp, uint64_t seed, double* rts, int32_t* counts) {
+  const int fit_blocks = ceil_div(n_hyp, PREP_THREADS);
+  if (xyz_f64)
+    gather_kabsch_kernel<double><<<fit_blocks, PREP_THREADS, 0, ctx->stream>>>((const double*)src_xyz, (const double*)tgt_xyz, corr, count,
+                                                                              max_corr, 0, nullptr, sample_idx, n_hyp, seed, rts, counts, nullptr);
+  else
+    gather_kabsch_kernel<float><<<fit_blocks, PREP_THREADS, 0, ctx->stream>>>((const float*)src_xyz, (const float*)tgt_xyz, corr, count,
+                                                                             max_corr, 0, nullptr, sample_idx, n_hyp, seed, rts, counts, nullptr);
+  return launch_check(ctx, "gather_kabsch_kernel");
 }
 
 size_t ransac_scratch(int32_t max_corr, int32_t n_hyp) {
