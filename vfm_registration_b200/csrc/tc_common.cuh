@@ -91,6 +91,61 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// --- programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization) ---
+// launch_dependents: the next kernel on the stream may be scheduled once every CTA of this grid has executed it (or exited);
+// wait: blocks until the grids this one depends on have completed and their memory is visible.  Code before the wait must
+// not touch global memory that another kernel writes or reads.  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// --- in-situ timeline (tools/vit_trace.py; built only with -DVFM_TRACE into libvfmreg_b200_trace.so) ---
+// Thread 0 of every CTA appends (kind | block << 8 | smid << 40, entry, after griddepcontrol.wait, exit) in globaltimer
+// nanoseconds: the timeline of a CUDA-graph replay with programmatic dependent launches, which no profiler here shows
+// (ncu serialises the launches and flushes the caches between them).  Compiles to nothing in the product build.
+#ifdef VFM_TRACE
+struct TraceBuf {
+  unsigned long long* rec;
+  unsigned int* cursor;
+  unsigned int cap;
+};
+static __device__ TraceBuf g_trace;
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TraceScope {
+  unsigned long long t0, t1;
+  int kind;
+  __device__ __forceinline__ explicit TraceScope(int k) : kind(k) { t0 = t1 = trace_now(); }
+  __device__ __forceinline__ void waited() { t1 = trace_now(); }
+  __device__ __forceinline__ void end() {
+    if (threadIdx.x != 0 || !g_trace.rec) return;
+    const unsigned int i = atomicAdd(g_trace.cursor, 1u);
+    if (i >= g_trace.cap) return;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned long long blk = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+    g_trace.rec[4 * i + 0] = (unsigned long long)kind | (blk << 8) | ((unsigned long long)smid << 40);
+    g_trace.rec[4 * i + 1] = t0;
+    g_trace.rec[4 * i + 2] = t1;
+    g_trace.rec[4 * i + 3] = trace_now();
+  }
+};
+#define VFM_TRACE_ATTACH(fn)                                                                       \
+  extern "C" __attribute__((visibility("default"))) int fn(void* rec, void* cursor, unsigned cap) { \
+    vfm::TraceBuf t{(unsigned long long*)rec, (unsigned int*)cursor, cap};                          \
+    return (int)cudaMemcpyToSymbol(vfm::g_trace, &t, sizeof(t));                                    \
+  }
+#else
+struct TraceScope {
+  __device__ __forceinline__ explicit TraceScope(int) {}
+  __device__ __forceinline__ void waited() {}
+  __device__ __forceinline__ void end() {}
+};
+#define VFM_TRACE_ATTACH(fn)
+#endif
+
 // --- thread-block-cluster variants (CTA pair sharing the streamed operand by TMA multicast) ---
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
   asm volatile(

@@ -4,6 +4,8 @@
 // GEMM operands are bf16 (weights converted once at upload), accumulation and the residual stream are fp32.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <map>
 #include <string>
@@ -20,7 +22,7 @@ namespace {
 struct Layer {
   float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ls1, *ln2_g, *ln2_b, *fc1_b, *fc2_b, *ls2;
   __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
-  WeightMaps m_qkv, m_proj, m_fc1, m_fc2;
+  CUtensorMap m_qkv, m_proj, m_fc1, m_fc2;   // 128-row boxes (vit_weight_map)
 };
 
 }  // namespace
@@ -30,7 +32,7 @@ struct vfmreg_vit {
   vfmreg_vit_config cfg;
   int kp;  // padded patch-embedding K (3 * patch^2 -> multiple of 64)
   __nv_bfloat16* pe_w = nullptr;
-  WeightMaps m_pe;
+  CUtensorMap m_pe;
   float *pe_b = nullptr, *cls = nullptr, *norm_g = nullptr, *norm_b = nullptr, *cn_g = nullptr, *cn_b = nullptr;
   std::vector<Layer> layers;
   std::map<long long, float*> pos;  // (gh << 20 | gw) -> device (1 + gh*gw, W)
@@ -39,7 +41,11 @@ struct vfmreg_vit {
   int cap_rows = 0;
   float* x = nullptr;
   __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hbuf = nullptr, *patches = nullptr;
-  CUtensorMap m_xn, m_ao, m_h, m_patches;
+  // per GEMM of a layer: how it is cut for the current row count (vit_gemm_plan) and the token maps with matching boxes
+  GemmPlan p_pe{}, p_qkv{}, p_proj{}, p_fc1{}, p_fc2{};
+  TokenMaps m_xn_qkv, m_xn_fc1, m_ao, m_h, m_patches;
+  float* ws = nullptr;   // fp32 partial sums of proj / fc2: [split][rows][width]
+  static constexpr int MAX_SPLIT = 4;
   int map_rows = -1, map_prow = -1;
   std::map<std::string, bool> loaded;
   // CUDA-graph replay of the per-forward kernel sequence (launch-bound at small batch): one graph per (b, h, w), captured on
@@ -104,7 +110,7 @@ int ensure_activations(vfmreg_vit* v, int rows, int prows) {
   const int w = v->cfg.width, md = v->cfg.mlp_dim;
   if (rows > v->cap_rows) {
     VFM_CUDA(cudaStreamSynchronize(v->ctx->stream));
-    for (void* p : {(void*)v->x, (void*)v->xn, (void*)v->qkv, (void*)v->ao, (void*)v->hbuf, (void*)v->patches})
+    for (void* p : {(void*)v->x, (void*)v->xn, (void*)v->qkv, (void*)v->ao, (void*)v->hbuf, (void*)v->patches, (void*)v->ws})
       if (p) cudaFree(p);
     for (auto& kv : v->graphs)   // captured graphs hold the old activation pointers
       if (kv.second.exec) {
@@ -118,14 +124,26 @@ int ensure_activations(vfmreg_vit* v, int rows, int prows) {
     VFM_CUDA(cudaMalloc(&v->ao, (size_t)cap * w * 2));
     VFM_CUDA(cudaMalloc(&v->hbuf, (size_t)cap * md * 2));
     VFM_CUDA(cudaMalloc(&v->patches, (size_t)cap * v->kp * 2));
+    VFM_CUDA(cudaMalloc(&v->ws, (size_t)vfmreg_vit::MAX_SPLIT * cap * w * sizeof(float)));
     v->cap_rows = cap;
     v->map_rows = -1;
   }
   if (rows != v->map_rows || prows != v->map_prow) {
-    VFM_TRY(make_tmap_16bit(&v->m_xn, v->xn, rows, w, w, 128, true));
-    VFM_TRY(make_tmap_16bit(&v->m_ao, v->ao, rows, w, w, 128, true));
-    VFM_TRY(make_tmap_16bit(&v->m_h, v->hbuf, rows, md, md, 128, true));
-    VFM_TRY(make_tmap_16bit(&v->m_patches, v->patches, prows, v->kp, v->kp, 128, true));
+    v->p_pe = vit_gemm_plan(v->ctx, prows, w, v->kp, 1, "pe");
+    v->p_qkv = vit_gemm_plan(v->ctx, rows, 3 * w, w, 1, "qkv");
+    v->p_proj = vit_gemm_plan(v->ctx, rows, w, w, vfmreg_vit::MAX_SPLIT, "proj");
+    v->p_fc1 = vit_gemm_plan(v->ctx, rows, md, w, 1, "fc1");
+    v->p_fc2 = vit_gemm_plan(v->ctx, rows, w, md, vfmreg_vit::MAX_SPLIT, "fc2");
+    if (getenv("VFMREG_VIT_VERBOSE"))   // tuning aid: how the cost model cut the five GEMMs for this row count
+      for (const auto& pr : {std::make_pair("pe", v->p_pe), std::make_pair("qkv", v->p_qkv), std::make_pair("proj", v->p_proj),
+                             std::make_pair("fc1", v->p_fc1), std::make_pair("fc2", v->p_fc2)})
+        fprintf(stderr, "vit plan rows=%d %s: nt=%d split=%d tail=%d units=%d\n", rows, pr.first, pr.second.nt, pr.second.split,
+                pr.second.tail_w, pr.second.units);
+    VFM_TRY(vit_token_maps(&v->m_xn_qkv, v->xn, rows, w, v->p_qkv));
+    VFM_TRY(vit_token_maps(&v->m_xn_fc1, v->xn, rows, w, v->p_fc1));
+    VFM_TRY(vit_token_maps(&v->m_ao, v->ao, rows, w, v->p_proj));
+    VFM_TRY(vit_token_maps(&v->m_h, v->hbuf, rows, md, v->p_fc2));
+    VFM_TRY(vit_token_maps(&v->m_patches, v->patches, prows, v->kp, v->p_pe));
     v->map_rows = rows;
     v->map_prow = prows;
   }
@@ -140,8 +158,7 @@ int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit*
   VFM_CHECK_ARG(ctx && cfg && out, "vit_create: null pointer");
   VFM_CHECK_ARG(cfg->depth > 0 && cfg->heads > 0 && cfg->width == cfg->heads * 64, "vit_create: width must be heads * 64");
   VFM_CHECK_ARG(cfg->width % 128 == 0 && cfg->width <= 1024 && cfg->mlp_dim % 64 == 0, "vit_create: unsupported width/mlp_dim");
-  VFM_CHECK_ARG(vit_gemm_tile_n(cfg->width) && vit_gemm_tile_n(3 * cfg->width) && vit_gemm_tile_n(cfg->mlp_dim),
-                "vit_create: width, 3*width and mlp_dim must be multiples of 128, 192 or 256");
+  VFM_CHECK_ARG(cfg->mlp_dim % 128 == 0, "vit_create: mlp_dim must be a multiple of 128");
   VFM_CHECK_ARG(cfg->patch > 0 && cfg->patch_h > 0, "vit_create: bad patch geometry");
   VFM_CUDA(cudaSetDevice(ctx->device));
   vfmreg_vit* v = new vfmreg_vit();
@@ -159,13 +176,13 @@ int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit*
     A(&l.ln2_g, w); A(&l.ln2_b, w); A(&l.fc1_b, md); A(&l.fc2_b, w); A(&l.ls2, w);
     A(&l.qkv_w, (size_t)3 * w * w); A(&l.proj_w, (size_t)w * w); A(&l.fc1_w, (size_t)md * w); A(&l.fc2_w, (size_t)w * md);
   }
-  if (rc == VFMREG_OK) rc = vit_weight_maps(&v->m_pe, v->pe_w, w, v->kp);
+  if (rc == VFMREG_OK) rc = vit_weight_map(&v->m_pe, v->pe_w, w, v->kp);
   for (Layer& l : v->layers) {
     if (rc != VFMREG_OK) break;
-    rc = vit_weight_maps(&l.m_qkv, l.qkv_w, 3 * w, w);
-    if (rc == VFMREG_OK) rc = vit_weight_maps(&l.m_proj, l.proj_w, w, w);
-    if (rc == VFMREG_OK) rc = vit_weight_maps(&l.m_fc1, l.fc1_w, md, w);
-    if (rc == VFMREG_OK) rc = vit_weight_maps(&l.m_fc2, l.fc2_w, w, md);
+    rc = vit_weight_map(&l.m_qkv, l.qkv_w, 3 * w, w);
+    if (rc == VFMREG_OK) rc = vit_weight_map(&l.m_proj, l.proj_w, w, w);
+    if (rc == VFMREG_OK) rc = vit_weight_map(&l.m_fc1, l.fc1_w, md, w);
+    if (rc == VFMREG_OK) rc = vit_weight_map(&l.m_fc2, l.fc2_w, w, md);
   }
   if (rc != VFMREG_OK) {
     vfmreg_vit_destroy(v);
@@ -190,7 +207,7 @@ void vfmreg_vit_destroy(vfmreg_vit* v) {
   if (v->img_stage) cudaFree(v->img_stage);
   if (v->tok_stage) cudaFree(v->tok_stage);
   if (v->cap_stream) cudaStreamDestroy(v->cap_stream);
-  for (void* p : {(void*)v->x, (void*)v->xn, (void*)v->qkv, (void*)v->ao, (void*)v->hbuf, (void*)v->patches})
+  for (void* p : {(void*)v->x, (void*)v->xn, (void*)v->qkv, (void*)v->ao, (void*)v->hbuf, (void*)v->patches, (void*)v->ws})
     if (p) cudaFree(p);
   delete v;
 }
@@ -284,22 +301,29 @@ static int vit_enqueue(vfmreg_vit* v, const uint8_t* images, int b, int img_h, i
   const float ms[6] = {v->cfg.mean[0], v->cfg.mean[1], v->cfg.mean[2], v->cfg.std[0], v->cfg.std[1], v->cfg.std[2]};
   VFM_TRY(vit_preprocess(ctx, images, b, img_h, img_w, gh, gw, v->cfg.patch, ms, v->patches, v->kp, v->x, v->cls, pos, w));
   GemmEpilogue ep{};
-  ep = GemmEpilogue{prows, w, v->kp, np, w, v->pe_b, nullptr, pos, v->x, nullptr};
-  VFM_TRY(vit_gemm(ctx, EPI_F32_PATCH, v->m_patches, v->m_pe, ep));
+  ep.m = prows; ep.n = w; ep.k = v->kp; ep.np = np; ep.ldo = w; ep.bias = v->pe_b; ep.pos = pos; ep.x = v->x;
+  VFM_TRY(vit_gemm(ctx, EPI_F32_PATCH, v->m_pe, v->m_patches, v->p_pe, ep));
+  Residual pending{};   // the residual branch of the last proj / fc2 GEMM, folded into the next normalisation kernel
   for (Layer& l : v->layers) {
-    VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, l.ln1_g, l.ln1_b, v->cfg.ln_eps, v->xn));
-    ep = GemmEpilogue{rows, 3 * w, w, 0, 3LL * w, l.qkv_b, nullptr, nullptr, nullptr, v->qkv};
-    VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS, v->m_xn, l.m_qkv, ep));
+    VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, pending, l.ln1_g, l.ln1_b, v->cfg.ln_eps, v->xn));
+    ep = GemmEpilogue{};
+    ep.m = rows; ep.n = 3 * w; ep.k = w; ep.ldo = 3LL * w; ep.bias = l.qkv_b; ep.out_bf16 = v->qkv;
+    VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS, l.m_qkv, v->m_xn_qkv, v->p_qkv, ep));
     VFM_TRY(vit_attention(ctx, v->qkv, b, t, v->cfg.heads, w, v->ao));
-    ep = GemmEpilogue{rows, w, w, 0, w, l.proj_b, l.ls1, nullptr, v->x, nullptr};
-    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_ao, l.m_proj, ep));
-    VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, l.ln2_g, l.ln2_b, v->cfg.ln_eps, v->xn));
-    ep = GemmEpilogue{rows, md, w, 0, md, l.fc1_b, nullptr, nullptr, nullptr, v->hbuf};
-    VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS_GELU, v->m_xn, l.m_fc1, ep));
-    ep = GemmEpilogue{rows, w, md, 0, w, l.fc2_b, l.ls2, nullptr, v->x, nullptr};
-    VFM_TRY(vit_gemm(ctx, EPI_F32_RESID, v->m_h, l.m_fc2, ep));
+    ep = GemmEpilogue{};
+    ep.m = rows; ep.n = w; ep.k = w; ep.ldo = w; ep.x = v->ws;
+    VFM_TRY(vit_gemm(ctx, EPI_F32_PARTIAL, l.m_proj, v->m_ao, v->p_proj, ep));
+    pending = Residual{v->ws, v->p_proj.split, l.proj_b, l.ls1};
+    VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, pending, l.ln2_g, l.ln2_b, v->cfg.ln_eps, v->xn));
+    ep = GemmEpilogue{};
+    ep.m = rows; ep.n = md; ep.k = w; ep.ldo = md; ep.bias = l.fc1_b; ep.out_bf16 = v->hbuf;
+    VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS_GELU, l.m_fc1, v->m_xn_fc1, v->p_fc1, ep));
+    ep = GemmEpilogue{};
+    ep.m = rows; ep.n = w; ep.k = md; ep.ldo = w; ep.x = v->ws;
+    VFM_TRY(vit_gemm(ctx, EPI_F32_PARTIAL, l.m_fc2, v->m_h, v->p_fc2, ep));
+    pending = Residual{v->ws, v->p_fc2.split, l.fc2_b, l.ls2};
   }
-  return vit_final_norm(ctx, v->x, b, t, w, v->norm_g, v->norm_b, v->cfg.ln_eps, v->cn_g, v->cn_b, v->cfg.cn_eps, v->cfg.channel_norm,
+  return vit_final_norm(ctx, v->x, b, t, w, pending, v->norm_g, v->norm_b, v->cfg.ln_eps, v->cn_g, v->cn_b, v->cfg.cn_eps, v->cfg.channel_norm,
                         tokens);
 }
 

@@ -1,22 +1,37 @@
 // bf16 x bf16 -> fp32 GEMM on tcgen05 for the DINOv2 forward (reference: the ViT behind image_features.py:95-101),
-// C[M, N] = A[M, K] W[N, K]^T with the layer's element-wise tail fused into the epilogue so that no intermediate is
-// re-read from HBM:
+// out[token, feature] = X[token, :] . W[feature, :] with the layer's element-wise tail fused into the epilogue so that no
+// intermediate is re-read from HBM:
 //   EPI_BF16_BIAS       out_bf16 = acc + bias                       (QKV projection)
 //   EPI_BF16_BIAS_GELU  out_bf16 = gelu(acc + bias), exact erf      (MLP fc1)
-//   EPI_F32_RESID       x += gamma * (acc + bias), fp32 in place    (attention proj / MLP fc2 + LayerScale + residual)
+//   EPI_F32_PARTIAL     ws[split][token][feature] = acc, fp32       (attention proj / MLP fc2: the K range may be split over
+//                       several clusters; bias, LayerScale, residual add and the reduction over the splits are done by the
+//                       LayerNorm kernel that follows, vit_ops.cu, in a fixed order -- deterministic, and the GEMM's
+//                       epilogue is a plain coalesced store)
 //   EPI_F32_PATCH       x[token row] = acc + bias + pos_embed       (patch embedding; skips the CLS row of each image)
 //
-// Persistent kernel, one CTA per SM, static round-robin over 128 x BN output tiles (BN = 256 when N % 256 == 0, else 192:
-// every DINOv2 width is a multiple of one of them; wide N keeps the MMA off the shared-memory read limit, which a
-// 128-wide tile hits).  Every weight carries a TMA box per width it divides into (256 / 192 / 128), and each
-// launch picks the width with the fewest waves x tile time for its M: large batches use 256, BASELINE config 3 (6 images x
-// 257 tokens = 13 row blocks) uses 192 for QKV and 128 for proj / fc1 / fc2.  Warp 0 = TMA producer (128B-swizzled 64-wide K chunks, 4-stage mbarrier ring), warp 1 = TMEM
-// allocator + elected-lane tcgen05.mma issuer (kind::f16, bf16 operands, M128 N{192,256} K16), accumulators double-buffered in
-// TMEM (2 x 256 columns) so the epilogue of tile i (warps 2-5: tcgen05.ld 32x32b, one output row per thread) overlaps
-// the MMAs of tile i+1.  Bound: tensor pipe for the large layers; at BASELINE config 3 (6 images, 1542 tokens) most layers
-// are below one wave of tiles and are latency bound.
+// Layout of the work ("swap-AB"): the WEIGHTS are the M operand of the MMA and the TOKENS the N operand.  A CTA pair
+// (thread-block cluster of two, one tcgen05.mma.cta_group::2 issued by the leader drives the tensor cores of both SMs)
+// owns 256 output features -- 128 per CTA, accumulator rows in that CTA's TMEM lanes -- times a token tile whose width is a
+// run-time value (any multiple of 16 up to 256: the N field of the instruction descriptor).  Why this way round:
+//   * the token count of a ViT batch is never a multiple of 128 (B x 257 with the CLS rows: 1542 at BASELINE config 3), the
+//     feature counts always are.  Token tiles of a width chosen per launch plus one narrow tail tile (16-wide for the 6 rows
+//     past 6 x 256) fill the 74 CTA pairs in one or two even waves instead of 13 row blocks x N tiles with a 6-row block;
+//   * an epilogue thread owns one FEATURE (its TMEM lane) and walks the tokens: bias / LayerScale are one register each, and the
+//     32 lanes of a warp write 32 consecutive features of one token -- coalesced 64 B (bf16) / 128 B (fp32) rows;
+//   * each CTA loads only half of the token tile (the pair's MMA reads both halves), so the shared-memory operand traffic
+//     per MMA is 4 KB + N/2 x 32 B per SM, under the 128 B/clk limit down to N = 96.
+// Persistent clusters walk the tile list (full token tiles first, the narrow tail tiles last) round-robin.  Warp 0 = TMA
+// producer (128B-swizzled 64-wide K chunks, 6-stage mbarrier ring; both CTAs' loads credit the leader's barrier), warp 1 =
+// TMEM allocator and, in the leader, the elected-lane MMA issuer (multicast tcgen05.commit frees the stage / publishes the
+// accumulator in both CTAs), warps 2-9 = epilogue (tcgen05.ld 32x32b.x32; warps w and w+4 share a TMEM lane quarter and
+// take alternate 32-token chunks), accumulators double-buffered in TMEM (2 x 256 columns).
+// Every kernel of the forward is launched with programmatic stream serialisation (PDL): barrier init, TMEM allocation and
+// tensor-map prefetch of launch i+1 overlap the tail of launch i; griddepcontrol.wait precedes the first global access.
+// Bound: tensor pipe for large batches; at BASELINE config 3 (6 images) one or two waves per layer.
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -24,240 +39,354 @@
 
 namespace vfm {
 
-constexpr int GBM = 128, GBK = 64, GSTAGES = 4;
-constexpr uint32_t GA_BYTES = GBM * GBK * 2;
-constexpr uint32_t GB_BYTES_MAX = 256 * GBK * 2;
-constexpr uint32_t GSMEM_BARS = GSTAGES * (GA_BYTES + GB_BYTES_MAX);
-constexpr uint32_t GSMEM_TOTAL = GSMEM_BARS + 256 + 1024;
+constexpr int G_FM = 128;            // features per CTA (256 per pair)
+constexpr int G_BK = 64, G_STAGES = 6;
+constexpr int G_EPI_WARPS = 8, G_THREADS = 64 + G_EPI_WARPS * 32;
+constexpr uint32_t G_A_BYTES = G_FM * G_BK * 2;        // 16 KB: this CTA's 128 weight rows x 64 k
+constexpr uint32_t G_B_BYTES = 128 * G_BK * 2;         // up to 128 token rows (half of a 256-wide tile) x 64 k
+constexpr uint32_t G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr uint32_t G_SMEM_BARS = G_STAGES * G_STAGE_BYTES;
+constexpr uint32_t G_SMEM_TOTAL = G_SMEM_BARS + 256 + 1024;
+static_assert(G_SMEM_TOTAL <= 232448, "shared memory budget of one SM");
 
-// exact-erf GELU.  (An Abramowitz-Stegun erf -- reciprocal + ex2 + 6 fma -- was measured SLOWER than libm's erff here:
-// 17.98 vs 16.24 ms for ViT-L/14 B=48 on the same box; erff's polynomial fast path has no reciprocal.)
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU, 0.5 x (1 + erf(x / sqrt 2)).  libm's erff costs ~25 instructions per element and made the fc1 epilogue the
+// limiter of the whole GEMM (ncu: tensor pipe 37 % active at 48 images against 82 % for the QKV projection).  Here
+// 1 + erf(z) = erfc(-z) and erfc(a) = 2^(-a q(a)) for a >= 0 with q a degree-4 polynomial (weighted least squares on
+// [0, 4], |erf error| < 7.2e-7 in fp32 arithmetic, tools/fit_erf.py; erfc(4) = 1.5e-8 is below half an ulp of 1):
+// one MUFU.EX2 and ~11 FMA-pipe instructions, no branch, and full relative accuracy in the negative tail.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float a = fminf(fabsf(z), 4.0f);
+  float q = 0.002966806525364518f;
+  q = fmaf(q, a, -0.02966925874352455f);
+  q = fmaf(q, a, 0.148755744099617f);
+  q = fmaf(q, a, 0.9184716939926147f);
+  q = fmaf(q, a, 1.6278934478759766f);
+  float e;                                  // erfc(|z|); the exponent is >= -27: no denormal handling needed
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * q));
+  const float h = 0.5f * x;
+  return h * (z >= 0.f ? 2.0f - e : e);     // 1 + erf(z)
+}
 
-template <int EPI, int BN>
-__global__ void __launch_bounds__(192, 1)
-    vit_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmEpilogue ep) {
-  constexpr uint32_t GB_BYTES = BN * GBK * 2;
-  constexpr uint32_t IDESC = umma_idesc_f16(GBM, BN, 1);  // bf16 operands
+// tile t of the launch: full token tiles first (token-tile major, feature block minor), then the tail tiles
+struct GemmTile {
+  int fb, tok0, w, split, kb0, kb1;
+};
+__device__ __forceinline__ GemmTile gemm_tile(const GemmEpilogue& ep, int u) {
+  GemmTile g;
+  const int t = u / ep.split;
+  g.split = u - t * ep.split;
+  const int kbs = ep.k / G_BK;
+  g.kb0 = (kbs * g.split) / ep.split;
+  g.kb1 = (kbs * (g.split + 1)) / ep.split;
+  const int full = ep.fb_count * ep.n_full;
+  if (t < full) {
+    g.fb = t % ep.fb_count;
+    g.tok0 = (t / ep.fb_count) * ep.nt;
+    g.w = ep.nt;
+  } else {
+    g.fb = t - full;
+    g.tok0 = ep.n_full * ep.nt;
+    g.w = ep.tail_w;
+  }
+  return g;
+}
+
+// One 32-token chunk of one feature (r[j] = accumulator of token tok_c + j): the epilogue's element-wise tail and store.
+template <int EPI, bool FULL>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t* r, int tok_c, int f, float bias, int split,
+                                               int valid) {
+  if (EPI == EPI_BF16_BIAS || EPI == EPI_BF16_BIAS_GELU) {
+    __nv_bfloat16* o = ep.out_bf16 + (long long)tok_c * ep.ldo + f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (FULL || j < valid) {
+        float v = __uint_as_float(r[j]) + bias;
+        if (EPI == EPI_BF16_BIAS_GELU) v = gelu_erf(v);
+        *o = __float2bfloat16(v);
+      }
+      o += ep.ldo;
+    }
+  } else if (EPI == EPI_F32_PARTIAL) {
+    float* o = ep.x + ((long long)split * ep.m + tok_c) * ep.ldo + f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (FULL || j < valid) *o = __uint_as_float(r[j]);
+      o += ep.ldo;
+    }
+  } else {
+    // patch row tok = img * np + p  ->  residual-stream row img * (np + 1) + 1 + p, position row 1 + p
+    int img = tok_c / ep.np, p = tok_c - img * ep.np;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (FULL || j < valid) {
+        const long long out_row = (long long)img * (ep.np + 1) + 1 + p;
+        ep.x[out_row * ep.ldo + f] = __uint_as_float(r[j]) + bias + __ldg(ep.pos + (long long)(1 + p) * ep.n + f);
+        if (++p == ep.np) { p = 0; ++img; }
+      }
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
+    vit_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                    const __grid_constant__ CUtensorMap map_x_tail, const GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t sA = base, sB = base + GSTAGES * GA_BYTES;
-  const uint32_t bars = base + GSMEM_BARS;
-  const uint32_t full0 = bars, empty0 = bars + 8 * GSTAGES, tfull0 = bars + 16 * GSTAGES, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GSMEM_BARS + 16 * GSTAGES + 32);
+  const uint32_t bars = base + G_SMEM_BARS;
+  const uint32_t full0 = bars, empty0 = bars + 8 * G_STAGES, tfull0 = bars + 16 * G_STAGES, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + G_SMEM_BARS + 16 * G_STAGES + 32);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kb_count = ep.k / GBK;
-  const int n_tiles = ep.n / BN;
-  const int total = ((ep.m + GBM - 1) / GBM) * n_tiles;
+  const uint32_t rank = cluster_cta_rank();
+  const int clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int total = ep.fb_count * (ep.n_full + (ep.tail_w > 0 ? 1 : 0)) * ep.split;   // units of (tile, K split)
 
+  TraceScope trace(EPI);
+  pdl_launch_dependents();   // the next kernel may start its own prologue; its global accesses wait for this grid to finish
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < GSTAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    if (ep.tail_w > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x_tail) : "memory");
+    for (int s = 0; s < G_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);    // leader: one arrive.expect_tx per phase, bytes from both CTAs' loads
+      mbar_init(empty0 + 8 * s, 1);   // both CTAs: multicast commit from the leader's MMA warp
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, 4);
+      mbar_init(tfull0 + 8 * b, 1);                  // both CTAs: multicast commit
+      mbar_init(tempty0 + 8 * b, 2 * G_EPI_WARPS);   // leader: epilogue warps of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512u);
+  __syncthreads();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit / 2-SM load
+  if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
+  trace.waited();
 
   if (warp == 0) {
+    // ===== TMA producer: this CTA's 128 weight rows and its half of the token tile =====
     uint32_t stage = 0, phase = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int rb = t / n_tiles, nb = t % n_tiles;   // consecutive CTAs share the activation row block (L2 reuse)
+    for (int t = cid; t < total; t += clusters) {
+      const GemmTile g = gemm_tile(ep, t);
+      const int w_row = g.fb * 2 * G_FM + (int)rank * G_FM;
+      const int x_row = g.tok0 + (int)rank * (g.w / 2);
+      const bool tail = g.w != ep.nt;   // the tail tile has its own token map: a box of tail_w / 2 rows
+      const CUtensorMap* mx = tail ? &map_x_tail : &map_x;
+      const uint32_t b_bytes = (uint32_t)(g.w / 2) * (G_BK * 2);
 #pragma unroll 1
-      for (int kb = 0; kb < kb_count; ++kb) {
+      for (int kb = g.kb0; kb < g.kb1; ++kb) {
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(full0 + 8 * stage, GA_BYTES + GB_BYTES);
-          tma_load_2d(sA + stage * GA_BYTES, &map_a, full0 + 8 * stage, kb * GBK, rb * GBM);
-          tma_load_2d(sB + stage * GB_BYTES_MAX, &map_w, full0 + 8 * stage, kb * GBK, nb * BN);
+          const uint32_t full_leader = mapa_cluster(full0 + 8 * stage, 0);
+          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2u * (G_A_BYTES + b_bytes));
+          tma_load_2d_2sm(base + stage * G_STAGE_BYTES, &map_w, full_leader, kb * G_BK, w_row);
+          tma_load_2d_2sm(base + stage * G_STAGE_BYTES + G_A_BYTES, mx, full_leader, kb * G_BK, x_row);
         }
         __syncwarp();
-        if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    uint32_t stage = 0, phase = 0;
-    int it = 0;
-    const uint64_t da0 = umma_desc_k_sw128(sA), db0 = umma_desc_k_sw128(sB);
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const uint32_t buf = (uint32_t)(it & 1);
-      mbar_wait(tempty0 + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * 256;
-#pragma unroll 1
-      for (int kb = 0; kb < kb_count; ++kb) {
-        mbar_wait(full0 + 8 * stage, phase);
+    // ===== MMA issuer: the leader CTA only =====
+    if (rank == 0) {
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      const uint64_t da0 = umma_desc_k_sw128(base), db0 = umma_desc_k_sw128(base + G_A_BYTES);
+      for (int t = cid; t < total; t += clusters, ++it) {
+        const GemmTile g = gemm_tile(ep, t);
+        const uint32_t idesc = umma_idesc_f16(2 * G_FM, g.w, 1);   // bf16 operands, M = 256 (pair), N = token tile width
+        const uint32_t buf = (uint32_t)(it & 1);
+        mbar_wait(tempty0 + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t da = da0 + (uint64_t)(stage * (GA_BYTES >> 4));
-          const uint64_t db = db0 + (uint64_t)(stage * (GB_BYTES_MAX >> 4));
+        const uint32_t d_tmem = tmem_base + buf * 256;
+#pragma unroll 1
+        for (int kb = g.kb0; kb < g.kb1; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = da0 + (uint64_t)(stage * (G_STAGE_BYTES >> 4));
+            const uint64_t db = db0 + (uint64_t)(stage * (G_STAGE_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < GBK / 16; ++k)
-            tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(empty0 + 8 * stage);
-          if (kb == kb_count - 1) tc_commit(tfull0 + 8 * buf);
+            for (int k = 0; k < G_BK / 16; ++k)
+              tc_mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb != g.kb0 || k != 0) ? 1u : 0u);
+            tc_commit_2sm(empty0 + 8 * stage, (uint16_t)3);   // stage free in both CTAs once these MMAs have read it
+            if (kb == g.kb1 - 1) tc_commit_2sm(tfull0 + 8 * buf, (uint16_t)3);   // accumulator halves complete
+          }
+          __syncwarp();
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    const int q = warp & 3;
+    // ===== epilogue: this CTA's 128 features x the tile's tokens; thread = feature (TMEM lane), chunks of 32 tokens =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
     int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int rb = t / n_tiles, nb = t % n_tiles;
+    const uint32_t tempty_leader0 = mapa_cluster(tempty0, 0);
+    for (int t = cid; t < total; t += clusters, ++it) {
+      const GemmTile g = gemm_tile(ep, t);
+      const int f = g.fb * 2 * G_FM + (int)rank * G_FM + q * 32 + lane;
+      const bool f_live = f < ep.n;
+      float bias = 0.f;
+      if (EPI != EPI_F32_PARTIAL && f_live) bias = __ldg(ep.bias + f);
       const uint32_t buf = (uint32_t)(it & 1);
-      const int row = rb * GBM + q * 32 + lane;
-      const bool live = row < ep.m;
-      long long out_row = row;
-      const float* pos_row = nullptr;
-      if (EPI == EPI_F32_PATCH && live) {
-        const int img = row / ep.np, p = row - img * ep.np;
-        out_row = (long long)img * (ep.np + 1) + 1 + p;
-        pos_row = ep.pos + (long long)(1 + p) * ep.n;
-      }
       mbar_wait(tfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+      const int n_chunks = (g.w + 31) >> 5;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < n_chunks; c += 2) {
         uint32_t r[32];
         tc_ld32(t_addr + c * 32, r);
         tc_wait_ld();
-        if (!live) continue;
-        const int col0 = nb * BN + c * 32;
-        if (EPI == EPI_BF16_BIAS || EPI == EPI_BF16_BIAS_GELU) {
-          __nv_bfloat16* o = ep.out_bf16 + out_row * ep.ldo + col0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint32_t pk[4];
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float v0 = __uint_as_float(r[i + 2 * j]) + bb[2 * j];
-              float v1 = __uint_as_float(r[i + 2 * j + 1]) + bb[2 * j + 1];
-              if (EPI == EPI_BF16_BIAS_GELU) {
-                v0 = gelu_erf(v0);
-                v1 = gelu_erf(v1);
-              }
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(o + i) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        } else {
-          float* o = ep.x + out_row * ep.ldo + col0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            float* pv = reinterpret_cast<float*>(&v);
-            if (EPI == EPI_F32_RESID) v = *reinterpret_cast<const float4*>(o + i);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            float gg[4] = {0.f, 0.f, 0.f, 0.f};
-            if (EPI == EPI_F32_RESID) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + col0 + i));
-              gg[0] = g4.x; gg[1] = g4.y; gg[2] = g4.z; gg[3] = g4.w;
-            } else {
-              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos_row + col0 + i));
-              gg[0] = p4.x; gg[1] = p4.y; gg[2] = p4.z; gg[3] = p4.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float a = __uint_as_float(r[i + j]) + bb[j];
-              pv[j] = (EPI == EPI_F32_RESID) ? fmaf(gg[j], a, pv[j]) : a + gg[j];
-            }
-            *reinterpret_cast<float4*>(o + i) = v;
-          }
-        }
+        const int tok_c = g.tok0 + c * 32;
+        const int valid = min(32, min(g.w - c * 32, ep.m - tok_c));   // warp-uniform
+        if (!f_live || valid <= 0) continue;
+        // full chunks run straight-line code (32 independent elements in flight); only the last chunk of a tail tile /
+        // of the token range takes the predicated path
+        if (valid == 32)
+          epilogue_chunk<EPI, true>(ep, r, tok_c, f, bias, g.split, 32);
+        else
+          epilogue_chunk<EPI, false>(ep, r, tok_c, f, bias, g.split, valid);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
     }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // both CTAs are done with the pair's TMEM and with each other's barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512u);
+    tmem_dealloc_2sm(tmem_base, 512u);
   }
+  trace.end();
 }
 
-template <int EPI, int BN>
-static int launch_gemm(vfmreg_ctx* ctx, const CUtensorMap& a, const CUtensorMap& w, const GemmEpilogue& ep) {
-  const uint64_t bit = 1ull << (EPI * 3 + (BN == 256 ? 0 : (BN == 192 ? 1 : 2)));   // per device (= per context), not per process
+// ---- host side --------------------------------------------------------------------------------------------------------
+// Cost model of one launch (SM cycles): the units (tile x K split) are dealt round-robin to the clusters; a unit costs its
+// MMAs -- (k-blocks) x 4 x w/2 cycles for a w-token tile -- or the time its operand bytes need to reach the pair's shared
+// memory, whichever is larger, plus a fixed fill / drain; the launch can also not be faster than its total operand bytes
+// through the L2 (the chip-wide L2 -> SM rate, ~6300 B/clk, is what bounds 256 x 256 x 64 bf16 tiles: 64 KB per 512 MMA
+// cycles per pair = 64 B/clk per SM against ~42 B/clk per SM when all 148 SMs stream).
+static long long gemm_cost(int m, int n, int k, int nt, int split, int clusters, GemmPlan* plan) {
+  const int fb_count = ceil_div(n, 2 * G_FM);
+  const int n_full = m / nt;
+  const int rest = m - n_full * nt;
+  const int tail = (rest + 15) / 16 * 16;
+  const int kbs = k / G_BK;
+  auto unit_cost = [&](int w, int s, long long* bytes) {
+    const int kb = (kbs * (s + 1)) / split - (kbs * s) / split;
+    const long long b = (long long)kb * 2 * (G_A_BYTES + (long long)(w / 2) * (G_BK * 2));
+    *bytes = b;
+    const long long mma = (long long)kb * 4 * (w / 2), ingest = b / 110;
+    return (mma > ingest ? mma : ingest) + 600 + (long long)(w / 64 + 1) * 250;
+  };
+  const int tiles_full = fb_count * n_full, tiles = tiles_full + (tail ? fb_count : 0);
+  const int units = tiles * split;
+  long long worst = 0, total_bytes = 0;
+  for (int c = 0; c < clusters && c < units; ++c) {
+    long long sum = 0;
+    for (int u = c; u < units; u += clusters) {
+      long long b;
+      sum += unit_cost(u / split < tiles_full ? nt : tail, u % split, &b);
+      total_bytes += b;
+    }
+    if (sum > worst) worst = sum;
+  }
+  long long l2 = total_bytes / 5500;
+  if (split > 1) l2 += (long long)split * m * n * 8 / 5500;   // the partial sums are written here and read back by the next kernel
+  if (plan) {
+    plan->nt = nt;
+    plan->split = split;
+    plan->tail_w = tail;
+    plan->n_full = n_full;
+    plan->fb_count = fb_count;
+    plan->units = units;
+  }
+  return worst > l2 ? worst : l2;
+}
+
+// VFMREG_VIT_PLAN="qkv:256:1,proj:256:3,fc1:192:1,fc2:256:3,pe:128:1" overrides (tile width : K splits) per GEMM of the forward --
+// a tuning aid for tools/bench_kernels.py; unset = the cost model above
+static bool plan_override(const char* which, int* nt, int* split) {
+  const char* e = getenv("VFMREG_VIT_PLAN");
+  if (!e || !which) return false;
+  const char* p = strstr(e, which);
+  if (!p || p[strlen(which)] != ':') return false;
+  return sscanf(p + strlen(which) + 1, "%d:%d", nt, split) == 2;
+}
+
+GemmPlan vit_gemm_plan(vfmreg_ctx* ctx, int m, int n, int k, int max_split, const char* which) {
+  const int clusters = ctx->sm_count / 2;
+  GemmPlan best{};
+  long long best_cost = -1;
+  int fnt = 0, fsplit = 0;
+  if (plan_override(which, &fnt, &fsplit) && fnt >= 32 && fnt <= 256 && fnt % 32 == 0 && fsplit >= 1 && fsplit <= max_split) {
+    gemm_cost(m, n, k, fnt, fsplit, clusters, &best);
+    return best;
+  }
+  for (int split = 1; split <= max_split && split <= k / G_BK; ++split)
+    for (int nt = 256; nt >= 64; nt -= 32) {   // multiples of 32: the epilogue's chunks never straddle the end of a full tile
+      GemmPlan p{};
+      const long long c = gemm_cost(m, n, k, nt, split, clusters, &p);
+      if (best_cost < 0 || c < best_cost) {
+        best = p;
+        best_cost = c;
+      }
+    }
+  return best;
+}
+
+template <int EPI>
+static int launch_gemm(vfmreg_ctx* ctx, const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& x_tail, const GemmEpilogue& ep,
+                       int grid) {
+  const uint64_t bit = 1ull << EPI;   // per device (= per context), not per process
   if (!(ctx->gemm_attr_mask & bit)) {
-    VFM_CUDA(cudaFuncSetAttribute(vit_gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSMEM_TOTAL));
+    VFM_CUDA(cudaFuncSetAttribute(vit_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_TOTAL));
     ctx->gemm_attr_mask |= bit;
   }
-  const int total = ceil_div(ep.m, GBM) * (ep.n / BN);
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-  vit_gemm_kernel<EPI, BN><<<grid, 192, GSMEM_TOTAL, ctx->stream>>>(a, w, ep);
+  VFM_CUDA(launch_pdl(vit_gemm_kernel<EPI>, dim3(grid), dim3(G_THREADS), G_SMEM_TOTAL, ctx->stream, w, x, x_tail, ep));
   return launch_check(ctx, "vit_gemm_kernel");
 }
 
-int vit_gemm_tile_n(int n) { return (n % 256 == 0) ? 256 : ((n % 192 == 0) ? 192 : ((n % 128 == 0) ? 128 : 0)); }
+int vit_weight_map(CUtensorMap* map, const void* ptr, int n, int k) { return make_tmap_16bit(map, ptr, n, k, k, G_FM, true); }
 
-int vit_weight_maps(WeightMaps* w, const void* ptr, int n, int k) {
-  const int widths[3] = {256, 192, 128};
-  for (int i = 0; i < 3; ++i) {
-    w->ok[i] = (n % widths[i] == 0);
-    if (w->ok[i]) VFM_TRY(make_tmap_16bit(&w->map[i], ptr, n, k, k, widths[i], true));
-  }
+int vit_token_maps(TokenMaps* t, const void* ptr, int rows, int k, const GemmPlan& plan) {
+  VFM_TRY(make_tmap_16bit(&t->full, ptr, rows, k, k, plan.nt / 2, true));
+  if (plan.tail_w > 0 && plan.tail_w != plan.nt) return make_tmap_16bit(&t->tail, ptr, rows, k, k, plan.tail_w / 2, true);
+  t->tail = t->full;
   return VFMREG_OK;
 }
 
-int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& a, const WeightMaps& w, const GemmEpilogue& ep) {
-  VFM_CHECK_ARG(ep.k % GBK == 0 && ep.m > 0 && (w.ok[0] || w.ok[1] || w.ok[2]), "vit_gemm: unsupported shape m=%d n=%d k=%d", ep.m,
-                ep.n, ep.k);
-  // Tile width: the persistent CTAs take ceil(tiles / SMs) tiles each; a tile's MMA time is proportional to its width,
-  // except that 128-wide tiles run into the shared-memory operand limit (x 1.25).  Small batches (6 images = 13 row blocks)
-  // pick narrower tiles than the 256 that large batches use.  VFMREG_VIT_TILE=256|192|128 forces a width (tuning aid).
-  static const int forced = [] { const char* e = getenv("VFMREG_VIT_TILE"); return e ? atoi(e) : 0; }();
-  const int widths[3] = {256, 192, 128}, cost[3] = {256, 192, 160};
-  int best = -1;
-  long long best_cost = 0;
-  for (int i = 0; i < 3; ++i) {
-    if (!w.ok[i]) continue;
-    const long long tiles = (long long)ceil_div(ep.m, GBM) * (ep.n / widths[i]);
-    const long long c = ((tiles + ctx->sm_count - 1) / ctx->sm_count) * cost[i];
-    if (forced == widths[i]) {
-      best = i;
-      break;
-    }
-    if (best < 0 || c < best_cost) {
-      best = i;
-      best_cost = c;
-    }
-  }
-#define VFM_GEMM_CASE(E)                                                                              \
-  case E:                                                                                             \
-    return best == 0 ? launch_gemm<E, 256>(ctx, a, w.map[0], ep)                                      \
-                     : (best == 1 ? launch_gemm<E, 192>(ctx, a, w.map[1], ep) : launch_gemm<E, 128>(ctx, a, w.map[2], ep));
+int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& w, const TokenMaps& x, const GemmPlan& plan, GemmEpilogue ep) {
+  VFM_CHECK_ARG(ep.k % G_BK == 0 && ep.m > 0 && ep.n % 128 == 0 && plan.nt >= 32 && plan.nt <= 256 && plan.nt % 32 == 0 &&
+                    plan.split >= 1 && (plan.split == 1 || epi == EPI_F32_PARTIAL),
+                "vit_gemm: unsupported shape m=%d n=%d k=%d nt=%d split=%d", ep.m, ep.n, ep.k, plan.nt, plan.split);
+  const int clusters = ctx->sm_count / 2;
+  ep.nt = plan.nt;
+  ep.split = plan.split;
+  ep.fb_count = plan.fb_count;
+  ep.n_full = plan.n_full;
+  ep.tail_w = plan.tail_w;
+  const int grid = 2 * (plan.units < clusters ? plan.units : clusters);
   switch (epi) {
-    VFM_GEMM_CASE(EPI_BF16_BIAS)
-    VFM_GEMM_CASE(EPI_BF16_BIAS_GELU)
-    VFM_GEMM_CASE(EPI_F32_RESID)
-    VFM_GEMM_CASE(EPI_F32_PATCH)
+    case EPI_BF16_BIAS: return launch_gemm<EPI_BF16_BIAS>(ctx, w, x.full, x.tail, ep, grid);
+    case EPI_BF16_BIAS_GELU: return launch_gemm<EPI_BF16_BIAS_GELU>(ctx, w, x.full, x.tail, ep, grid);
+    case EPI_F32_PARTIAL: return launch_gemm<EPI_F32_PARTIAL>(ctx, w, x.full, x.tail, ep, grid);
+    case EPI_F32_PATCH: return launch_gemm<EPI_F32_PATCH>(ctx, w, x.full, x.tail, ep, grid);
   }
-#undef VFM_GEMM_CASE
   set_error("vit_gemm: bad epilogue %d", epi);
   return VFMREG_ERR_ARG;
 }
 
 }  // namespace vfm
+
+VFM_TRACE_ATTACH(vfmreg_trace_attach_gemm)

@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "vit.cuh"
 
 namespace vfm {
@@ -18,6 +19,7 @@ namespace vfm {
 __global__ void __launch_bounds__(256)
     preprocess_kernel(const uint8_t* __restrict__ images, int b, int h, int w, int gh, int gw, int patch, float m0, float m1,
                       float m2, float s0, float s1, float s2, __nv_bfloat16* __restrict__ patches, int kp) {
+  pdl_launch_dependents();
   const long long total = (long long)b * gh * gw * kp;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void cls_rows_kernel(float* __restrict__ x, int b, int t, int width, const float* __restrict__ cls,
                                 const float* __restrict__ pos) {
+  pdl_launch_dependents();
+  pdl_wait();   // keeps the chain of programmatic dependencies transitive (this kernel itself depends on nothing)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b * width) return;
   const int img = i / width, c = i % width;
@@ -63,7 +67,8 @@ int vit_preprocess(vfmreg_ctx* ctx, const uint8_t* images, int b, int h, int w, 
   preprocess_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(images, b, h, w, gh, gw, patch, ms[0], ms[1], ms[2], ms[3],
                                                                   ms[4], ms[5], patches, kp);
   VFM_TRY(launch_check(ctx, "preprocess_kernel"));
-  cls_rows_kernel<<<ceil_div((long long)b * width, 256), 256, 0, ctx->stream>>>(x, b, gh * gw + 1, width, cls, pos);
+  VFM_CUDA(launch_pdl(cls_rows_kernel, dim3(ceil_div((long long)b * width, 256)), dim3(256), 0, ctx->stream, x, b, gh * gw + 1, width,
+                      cls, pos));
   return launch_check(ctx, "cls_rows_kernel");
 }
 
@@ -94,18 +99,69 @@ __device__ __forceinline__ RowStats warp_row_stats(const float4* v, int nv, int 
   return {mean, rsqrtf(q / (float)width + eps)};
 }
 
-__global__ void __launch_bounds__(256)
-    layernorm_bf16_kernel(const float* __restrict__ x, int rows, int width, const float* __restrict__ g, const float* __restrict__ b,
-                          float eps, __nv_bfloat16* __restrict__ out) {
+// v += scale * (ws[0] + ws[1] + ... + bias) for one row held by a warp (the pending residual branch of the previous GEMM).
+// SPLIT is a template parameter so that every load of the row is in flight before the first add (a run-time loop over the
+// splits serialised 8 x SPLIT dependent L2 round trips per row: 8 us per LayerNorm at 6 images).
+template <int SPLIT>
+__device__ __forceinline__ void add_residual_n(float4* v, int nv, const Residual& res, long long row, int rows, int width, int lane) {
+  float4 a[LN_MAX_V4];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) a[i] = *reinterpret_cast<const float4*>(res.ws + row * width + i * 128 + lane * 4);
+#pragma unroll
+  for (int s = 1; s < SPLIT; ++s) {
+    float4 p[LN_MAX_V4];
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i)
+      if (i < nv) p[i] = *reinterpret_cast<const float4*>(res.ws + ((long long)s * rows + row) * width + i * 128 + lane * 4);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i)
+      if (i < nv) {
+        a[i].x += p[i].x; a[i].y += p[i].y; a[i].z += p[i].z; a[i].w += p[i].w;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) {
+      const int k = i * 128 + lane * 4;
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(res.bias + k)), sc = __ldg(reinterpret_cast<const float4*>(res.scale + k));
+      v[i].x = fmaf(sc.x, a[i].x + bb.x, v[i].x);
+      v[i].y = fmaf(sc.y, a[i].y + bb.y, v[i].y);
+      v[i].z = fmaf(sc.z, a[i].z + bb.z, v[i].z);
+      v[i].w = fmaf(sc.w, a[i].w + bb.w, v[i].w);
+    }
+}
+__device__ __forceinline__ void add_residual(float4* v, int nv, const Residual& res, long long row, int rows, int width, int lane) {
+  switch (res.split) {   // warp-uniform
+    case 1: add_residual_n<1>(v, nv, res, row, rows, width, lane); break;
+    case 2: add_residual_n<2>(v, nv, res, row, rows, width, lane); break;
+    case 3: add_residual_n<3>(v, nv, res, row, rows, width, lane); break;
+    default: add_residual_n<4>(v, nv, res, row, rows, width, lane); break;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+    layernorm_bf16_kernel(float* __restrict__ x, int rows, int width, const Residual res, const float* __restrict__ g,
+                          const float* __restrict__ b, float eps, __nv_bfloat16* __restrict__ out) {
+  TraceScope trace(10);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.waited();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nv = width / 128;
-  const float* xr = x + (long long)row * width;
+  float* xr = x + (long long)row * width;
   float4 v[LN_MAX_V4];
 #pragma unroll
   for (int i = 0; i < LN_MAX_V4; ++i)
     if (i < nv) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  if (res.ws) {
+    add_residual(v, nv, res, row, rows, width, lane);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i)
+      if (i < nv) *reinterpret_cast<float4*>(xr + i * 128 + lane * 4) = v[i];
+  }
   const RowStats st = warp_row_stats(v, nv, width, eps);
 #pragma unroll
   for (int i = 0; i < LN_MAX_V4; ++i)
@@ -119,31 +175,36 @@ __global__ void __launch_bounds__(256)
       pk.y = *reinterpret_cast<uint32_t*>(&h1);
       *reinterpret_cast<uint2*>(out + (long long)row * width + k) = pk;
     }
+  trace.end();
 }
 
-int vit_layernorm_bf16(vfmreg_ctx* ctx, const float* x, int rows, int width, const float* g, const float* b, float eps,
+int vit_layernorm_bf16(vfmreg_ctx* ctx, float* x, int rows, int width, const Residual& res, const float* g, const float* b, float eps,
                        __nv_bfloat16* out) {
   VFM_CHECK_ARG(width % 128 == 0 && width <= 128 * LN_MAX_V4, "layernorm: width %d unsupported", width);
-  layernorm_bf16_kernel<<<ceil_div(rows, 8), 256, 0, ctx->stream>>>(x, rows, width, g, b, eps, out);
+  VFM_CUDA(launch_pdl(layernorm_bf16_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, ctx->stream, x, rows, width, res, g, b, eps, out));
   return launch_check(ctx, "layernorm_bf16_kernel");
 }
 
 // final LayerNorm -> drop CLS -> ChannelNorm (LayerNorm over C), fp32 out (B, gh*gw, C)
 __global__ void __launch_bounds__(256)
-    final_norm_kernel(const float* __restrict__ x, int b, int t, int width, const float* __restrict__ g1, const float* __restrict__ b1,
+    final_norm_kernel(const float* __restrict__ x, int b, int t, int width, const Residual res, const float* __restrict__ g1, const float* __restrict__ b1,
                       float eps1, const float* __restrict__ g2, const float* __restrict__ b2, float eps2, int channel_norm,
                       float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int np = t - 1;
   if (tok >= b * np) return;
   const int img = tok / np, p = tok % np;
   const int nv = width / 128;
-  const float* xr = x + ((long long)img * t + 1 + p) * width;
+  const long long row = (long long)img * t + 1 + p;
+  const float* xr = x + row * width;
   float4 v[LN_MAX_V4];
 #pragma unroll
   for (int i = 0; i < LN_MAX_V4; ++i)
     if (i < nv) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  if (res.ws) add_residual(v, nv, res, row, b * t, width, lane);   // the last layer's MLP branch
   RowStats st = warp_row_stats(v, nv, width, eps1);
 #pragma unroll
   for (int i = 0; i < LN_MAX_V4; ++i)
@@ -173,11 +234,11 @@ __global__ void __launch_bounds__(256)
     if (i < nv) *reinterpret_cast<float4*>(out + (long long)tok * width + i * 128 + lane * 4) = v[i];
 }
 
-int vit_final_norm(vfmreg_ctx* ctx, const float* x, int b, int t, int width, const float* g1, const float* b1, float eps1,
+int vit_final_norm(vfmreg_ctx* ctx, const float* x, int b, int t, int width, const Residual& res, const float* g1, const float* b1, float eps1,
                    const float* g2, const float* b2, float eps2, int channel_norm, float* out) {
   VFM_CHECK_ARG(width % 128 == 0 && width <= 128 * LN_MAX_V4, "final_norm: width %d unsupported", width);
-  final_norm_kernel<<<ceil_div((long long)b * (t - 1), 8), 256, 0, ctx->stream>>>(x, b, t, width, g1, b1, eps1, g2, b2, eps2,
-                                                                                 channel_norm, out);
+  VFM_CUDA(launch_pdl(final_norm_kernel, dim3(ceil_div((long long)b * (t - 1), 8)), dim3(256), 0, ctx->stream, x, b, t, width, res, g1, b1,
+                      eps1, g2, b2, eps2, channel_norm, out));
   return launch_check(ctx, "final_norm_kernel");
 }
 
@@ -218,6 +279,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
   const long long ld = 3LL * width;
   const __nv_bfloat16* base = qkv + (long long)img * t * ld + head * ATT_DH;
   const uint4 z4 = make_uint4(0, 0, 0, 0);
+  TraceScope trace(11);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.waited();
   for (int i = tid; i < tp * 8; i += ATT_WARPS * 32) {
     const int r = i >> 3, ch = i & 7;
     uint4 kv = z4, vv = z4;
@@ -339,6 +404,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
       if (r1 < t) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * width + c) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
     }
   }
+  trace.end();
 }
 
 int vit_attention(vfmreg_ctx* ctx, const __nv_bfloat16* qkv, int b, int t, int heads, int width, __nv_bfloat16* out) {
@@ -355,8 +421,10 @@ int vit_attention(vfmreg_ctx* ctx, const __nv_bfloat16* qkv, int b, int t, int h
   int splits = ceil_div(2 * ctx->sm_count, heads * b);
   const int max_splits = (n_tiles + ATT_WARPS - 1) / ATT_WARPS;
   splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
-  attention_kernel<<<dim3(heads, b, splits), ATT_WARPS * 32, smem, ctx->stream>>>(qkv, t, width, tp, out);
+  VFM_CUDA(launch_pdl(attention_kernel, dim3(heads, b, splits), dim3(ATT_WARPS * 32), smem, ctx->stream, qkv, t, width, tp, out));
   return launch_check(ctx, "attention_kernel");
 }
 
 }  // namespace vfm
+
+VFM_TRACE_ATTACH(vfmreg_trace_attach_ops)
