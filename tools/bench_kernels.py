@@ -112,11 +112,11 @@ def vit_flops(depth, w, t, tp, b):
     return b * (depth * (24.0 * t * w * w + 4.0 * t * t * w) + 2.0 * tp * 588 * w)
 
 
-def bench_vit(batches=(6, 48)):
+def bench_vit(batches=(6, 48), models=("vits14", "vitb14", "vitl14")):
     from vfm_registration_b200 import features
     ctx = v.get_context(0)
     rng = np.random.default_rng(0)
-    for model in ("vits14", "vitb14", "vitl14"):
+    for model in models:
         depth, w, heads = features.PRESETS[model]
         f = v.ViTFeaturizer(model, seed=1, random_init=True)
         for b in batches:
@@ -195,5 +195,7 @@ if __name__ == "__main__":
         bench_project()
     elif what == "vit":
         bench_vit()
+    elif what == "vitl":   # one model, one batch size: python tools/bench_kernels.py vitl 6
+        bench_vit(batches=(int(sys.argv[2]) if len(sys.argv) > 2 else 6,), models=("vitl14",))
     elif what == "extract":
         bench_extract()

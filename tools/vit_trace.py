@@ -22,7 +22,7 @@ lib = _lib.load()
 cap = 1 << 18
 rec = torch.zeros(cap * 4, dtype=torch.int64, device="cuda")
 cur = torch.zeros(1, dtype=torch.int32, device="cuda")
-for fn in ("vfmreg_trace_attach_gemm", "vfmreg_trace_attach_ops"):
+for fn in ("vfmreg_trace_attach_gemm", "vfmreg_trace_attach_ops", "vfmreg_trace_attach_attn"):
     f = getattr(lib, fn)
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
     assert f(rec.data_ptr(), cur.data_ptr(), cap) == 0
@@ -39,6 +39,8 @@ e1.record()
 torch.cuda.synchronize()
 n = int(cur.item())
 r = rec[: 4 * min(n, cap)].cpu().numpy().reshape(-1, 4)
+marks = r[(r[:, 0] & 0xFF) >= 100]
+r = r[(r[:, 0] & 0xFF) < 100]
 kind = r[:, 0] & 0xFF
 t0, t1, t2 = r[:, 1], r[:, 2], r[:, 3]
 base = t0.min()
@@ -51,7 +53,9 @@ for i in order:
         L = launches[-1]
         L["entry"], L["start"], L["end"], L["ctas"] = min(L["entry"], t0[i]), min(L["start"], t1[i]), max(L["end"], t2[i]), L["ctas"] + 1
     else:
-        launches.append({"kind": int(kind[i]), "entry": t0[i], "start": t1[i], "end": t2[i], "ctas": 1})
+        launches.append({"kind": int(kind[i]), "entry": t0[i], "start": t1[i], "end": t2[i], "ctas": 1, "cta_us": 0.0, "last_start": t1[i]})
+    launches[-1]["cta_us"] += (t2[i] - t1[i]) / 1e3
+    launches[-1]["last_start"] = max(launches[-1]["last_start"], t1[i])
 print(f"# {model} B={b}: forward {e0.elapsed_time(e1) * 1e3:.1f} us by CUDA events (trace build), {n} CTA records, {len(launches)} launches seen")
 print(f"# {'kernel':16s} {'CTAs':>5s} {'entry':>9s} {'start':>9s} {'end':>9s} {'busy':>7s} {'gap':>6s}   (us; entry = first CTA running, start = past griddepcontrol.wait, gap = start - previous end)")
 prev_end = None
@@ -72,14 +76,22 @@ for k, L in enumerate(launches):
         name += " (proj)" if k and launches[k - 1]["kind"] == 11 else " (fc2)"
     busy = (L["end"] - L["start"]) / 1e3
     gap = (L["start"] - prev_end) / 1e3 if prev_end is not None else 0.0
-    s = seq.setdefault(name, [0, 0.0, 0.0])
+    s = seq.setdefault(name, [0, 0.0, 0.0, 0.0, 0.0])
     s[0] += 1
     s[1] += busy
     s[2] += gap
+    s[3] += L["cta_us"] / L["ctas"]
+    s[4] += (L["last_start"] - L["start"]) / 1e3
     prev_end = L["end"]
 print("# per kernel type: launches, mean busy us (first start -> last exit), mean gap before it")
 tot = 0.0
-for name, (c, bs, gp) in seq.items():
-    print(f"  {name:22s} n={c:3d} busy {bs / c:7.2f}  gap {gp / c:6.2f}   total {bs + gp:8.1f}")
+for name, (c, bs, gp, cu, ls) in seq.items():
+    print(f"  {name:22s} n={c:3d} busy {bs / c:7.2f}  gap {gp / c:6.2f}   total {bs + gp:8.1f}   mean CTA time {cu / c:6.2f}  last CTA starts +{ls / c:5.2f}")
     tot += bs + gp
+if len(marks):   # trace_mark() timestamps of CTA 0 (kernel-internal phases), first 40, relative to the first
+    m = marks[np.argsort(marks[:, 1])]
+    first = [x for x in m if x[0] == 100]
+    if first:
+        sel = m[(m[:, 1] >= first[0][1])][:40]
+        print("# marks of CTA 0 (kind: us since the first):", " ".join(f"{int(k)}:{(tt - sel[0][1]) / 1e3:.2f}" for k, tt in zip(sel[:, 0], sel[:, 1])))
 print(f"# sum {tot:.1f} us (final norm / preprocess / cls rows are not traced)")

@@ -112,6 +112,7 @@ struct vfmreg_ctx {
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per context, not per process
   bool tc_attr_set = false;
   uint64_t gemm_attr_mask = 0;     // vit_gemm_kernel<EPI, BN> instantiations already opted in
+  size_t attention_tc_smem_attr = 0;   // same for attention_tc_kernel
   size_t attention_smem_attr = 0;  // largest dynamic shared memory size attention_kernel was opted in for
   // events that order the pairs of a batch after the preparation of the map they share (grown on demand)
   cudaEvent_t* map_ev = nullptr;

@@ -98,6 +98,19 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// L2 prefetch of this CTA's slice (part `idx` of `parts`) of a byte range another kernel will stream soon (the weights of the
+// next GEMM: at a few images per batch every GEMM would otherwise start by pulling its weights out of HBM); one thread
+__device__ __forceinline__ void l2_prefetch_slice(const char* ptr, unsigned long long bytes, unsigned idx, unsigned parts) {
+  if (!ptr || bytes == 0) return;
+  const unsigned long long chunk = 16384ull;
+  const unsigned long long n_chunks = (bytes + chunk - 1) / chunk;
+  for (unsigned long long c = idx; c < n_chunks; c += parts) {
+    const unsigned long long off = c * chunk;
+    const unsigned sz = (unsigned)((bytes - off < chunk ? bytes - off : chunk) & ~15ull);
+    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + off), "r"(sz) : "memory");
+  }
+}
+
 // --- in-situ timeline (tools/vit_trace.py; built only with -DVFM_TRACE into libvfmreg_b200_trace.so) ---
 // Thread 0 of every CTA appends (kind | block << 8 | smid << 40, entry, after griddepcontrol.wait, exit) in globaltimer
 // nanoseconds: the timeline of a CUDA-graph replay with programmatic dependent launches, which no profiler here shows
@@ -132,6 +145,29 @@ struct TraceScope {
     g_trace.rec[4 * i + 3] = trace_now();
   }
 };
+// timestamps of one thread of CTA 0 (kinds >= 100), kept in local memory while the kernel runs (a store does not stall the
+// thread) and appended to the trace when the thread is done: where the time inside a kernel goes
+struct TraceMarks {
+  unsigned long long t[64];
+  int k[64];
+  int n = 0;
+  __device__ __forceinline__ void mark(int kind) {
+    if (n < 64) {
+      t[n] = trace_now();
+      k[n] = kind;
+      ++n;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if (blockIdx.x != 0 || blockIdx.y != 0 || !g_trace.rec || n == 0) return;
+    const unsigned int i0 = atomicAdd(g_trace.cursor, (unsigned int)n);
+    for (int j = 0; j < n; ++j) {
+      if (i0 + j >= g_trace.cap) break;
+      g_trace.rec[4 * (i0 + j) + 0] = (unsigned long long)k[j];
+      g_trace.rec[4 * (i0 + j) + 1] = g_trace.rec[4 * (i0 + j) + 2] = g_trace.rec[4 * (i0 + j) + 3] = t[j];
+    }
+  }
+};
 #define VFM_TRACE_ATTACH(fn)                                                                       \
   extern "C" __attribute__((visibility("default"))) int fn(void* rec, void* cursor, unsigned cap) { \
     vfm::TraceBuf t{(unsigned long long*)rec, (unsigned int*)cursor, cap};                          \
@@ -142,6 +178,10 @@ struct TraceScope {
   __device__ __forceinline__ explicit TraceScope(int) {}
   __device__ __forceinline__ void waited() {}
   __device__ __forceinline__ void end() {}
+};
+struct TraceMarks {
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void flush() {}
 };
 #define VFM_TRACE_ATTACH(fn)
 #endif

@@ -44,6 +44,7 @@ struct vfmreg_vit {
   // per GEMM of a layer: how it is cut for the current row count (vit_gemm_plan) and the token maps with matching boxes
   GemmPlan p_pe{}, p_qkv{}, p_proj{}, p_fc1{}, p_fc2{};
   TokenMaps m_xn_qkv, m_xn_fc1, m_ao, m_h, m_patches;
+  CUtensorMap m_qkv_attn;   // the QKV matrix for the attention kernel: boxes of 64 rows x 64 columns
   float* ws = nullptr;   // fp32 partial sums of proj / fc2: [split][rows][width]
   static constexpr int MAX_SPLIT = 4;
   int map_rows = -1, map_prow = -1;
@@ -144,6 +145,7 @@ int ensure_activations(vfmreg_vit* v, int rows, int prows) {
     VFM_TRY(vit_token_maps(&v->m_ao, v->ao, rows, w, v->p_proj));
     VFM_TRY(vit_token_maps(&v->m_h, v->hbuf, rows, md, v->p_fc2));
     VFM_TRY(vit_token_maps(&v->m_patches, v->patches, prows, v->kp, v->p_pe));
+    VFM_TRY(make_tmap_16bit(&v->m_qkv_attn, v->qkv, rows, 3 * w, 3 * w, 64, true));
     v->map_rows = rows;
     v->map_prow = prows;
   }
@@ -304,12 +306,22 @@ static int vit_enqueue(vfmreg_vit* v, const uint8_t* images, int b, int img_h, i
   ep.m = prows; ep.n = w; ep.k = v->kp; ep.np = np; ep.ldo = w; ep.bias = v->pe_b; ep.pos = pos; ep.x = v->x;
   VFM_TRY(vit_gemm(ctx, EPI_F32_PATCH, v->m_pe, v->m_patches, v->p_pe, ep));
   Residual pending{};   // the residual branch of the last proj / fc2 GEMM, folded into the next normalisation kernel
-  for (Layer& l : v->layers) {
+  for (size_t li = 0; li < v->layers.size(); ++li) {
+    Layer& l = v->layers[li];
+    // every GEMM / attention kernel pulls the weights of a GEMM further down the chain into L2 while it runs
+    // (small batches only: with thousands of tokens a GEMM runs for tens of microseconds and its weights are a small share
+    // of its traffic)
+    const bool pf = rows <= 4096;
+    const Layer* nxt = pf && li + 1 < v->layers.size() ? &v->layers[li + 1] : nullptr;
     VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, pending, l.ln1_g, l.ln1_b, v->cfg.ln_eps, v->xn));
     ep = GemmEpilogue{};
     ep.m = rows; ep.n = 3 * w; ep.k = w; ep.ldo = 3LL * w; ep.bias = l.qkv_b; ep.out_bf16 = v->qkv;
+    if (pf) { ep.pf_ptr = (const char*)l.proj_w; ep.pf_bytes = (size_t)w * w * 2; }
     VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS, l.m_qkv, v->m_xn_qkv, v->p_qkv, ep));
-    VFM_TRY(vit_attention(ctx, v->qkv, b, t, v->cfg.heads, w, v->ao));
+    if (vit_attention_tc_supported(t))
+      VFM_TRY(vit_attention_tc(ctx, v->m_qkv_attn, b, t, v->cfg.heads, w, v->ao, pf ? l.fc1_w : nullptr, (size_t)md * w * 2));
+    else
+      VFM_TRY(vit_attention(ctx, v->qkv, b, t, v->cfg.heads, w, v->ao));
     ep = GemmEpilogue{};
     ep.m = rows; ep.n = w; ep.k = w; ep.ldo = w; ep.x = v->ws;
     VFM_TRY(vit_gemm(ctx, EPI_F32_PARTIAL, l.m_proj, v->m_ao, v->p_proj, ep));
@@ -317,9 +329,11 @@ static int vit_enqueue(vfmreg_vit* v, const uint8_t* images, int b, int img_h, i
     VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, pending, l.ln2_g, l.ln2_b, v->cfg.ln_eps, v->xn));
     ep = GemmEpilogue{};
     ep.m = rows; ep.n = md; ep.k = w; ep.ldo = md; ep.bias = l.fc1_b; ep.out_bf16 = v->hbuf;
+    if (pf) { ep.pf_ptr = (const char*)l.fc2_w; ep.pf_bytes = (size_t)w * md * 2; }
     VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS_GELU, l.m_fc1, v->m_xn_fc1, v->p_fc1, ep));
     ep = GemmEpilogue{};
     ep.m = rows; ep.n = w; ep.k = md; ep.ldo = w; ep.x = v->ws;
+    if (nxt) { ep.pf_ptr = (const char*)nxt->qkv_w; ep.pf_bytes = (size_t)3 * w * w * 2; }
     VFM_TRY(vit_gemm(ctx, EPI_F32_PARTIAL, l.m_fc2, v->m_h, v->p_fc2, ep));
     pending = Residual{v->ws, v->p_fc2.split, l.fc2_b, l.ls2};
   }

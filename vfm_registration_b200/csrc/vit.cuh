@@ -19,6 +19,8 @@ struct GemmEpilogue {
   const float* pos;         // [(1 + np), n] position embedding (EPI_F32_PATCH)
   float* x;                 // EPI_F32_PATCH: fp32 residual stream; EPI_F32_PARTIAL: workspace [split][m][ldo]
   __nv_bfloat16* out_bf16;  // bf16 output (EPI_BF16_*)
+  const char* pf_ptr;       // optional: byte range prefetched into L2 while this GEMM runs (the weights of a later GEMM)
+  unsigned long long pf_bytes;
 };
 
 // TMA map of one weight matrix (N x K, K-major bf16): box = 128 rows (one CTA's features) x 64 k
@@ -66,6 +68,11 @@ struct Residual {
 // x (+= pending residual, written back) -> LayerNorm -> bf16
 int vit_layernorm_bf16(vfmreg_ctx* ctx, float* x, int rows, int width, const Residual& res, const float* g, const float* b, float eps,
                        __nv_bfloat16* out);
+// tcgen05 attention (vit_attn.cu) for t <= 320 tokens per image; map_qkv: the (rows, 3 width) QKV matrix with 64 x 64 boxes
+bool vit_attention_tc_supported(int t);
+// pf_ptr / pf_bytes: a byte range (the next GEMM's weights) the kernel prefetches into L2 while it runs (may be null)
+int vit_attention_tc(vfmreg_ctx* ctx, const CUtensorMap& map_qkv, int b, int t, int heads, int width, __nv_bfloat16* out,
+                     const void* pf_ptr, size_t pf_bytes);
 int vit_attention(vfmreg_ctx* ctx, const __nv_bfloat16* qkv, int b, int t, int heads, int width, __nv_bfloat16* out);
 int vit_final_norm(vfmreg_ctx* ctx, const float* x, int b, int t, int width, const Residual& res, const float* g1, const float* b1, float eps1,
                    const float* g2, const float* b2, float eps2, int channel_norm, float* out);

@@ -1,0 +1,380 @@
+// Multi-head self-attention of the DINOv2 forward on tcgen05 (reference: the attention inside the ViT behind
+// image_features.py:95-101; xformers memory_efficient_attention there = plain softmax(Q K^T / sqrt(64)) V).
+//
+// One CTA per (head, image).  K and V of the head (t <= 320 tokens x 64 channels, bf16) are loaded once by TMA straight out
+// of the QKV projection's output (row pitch 3 W) into 128B-swizzled shared-memory tiles; the queries are walked in blocks of
+// 128 rows:
+//   S = Q K^T      tcgen05.mma kind::f16, M128 x N(keys, <= 256 + rest) x K64, both operands K-major, accumulator in TMEM
+//                  (columns 0 .. keys)
+//   softmax        8 warps, two per TMEM lane quarter: a thread owns one query row (its TMEM lane) and half of the keys:
+//                  tcgen05.ld 32x32b.x32 chunks (the next one in flight while one is processed), max pass, maxima of the two
+//                  halves exchanged through shared memory, then p = exp2((s - max) / sqrt(64) * log2 e) summed in fp32 and
+//                  written as bf16 into a 128B-swizzled K-major tile P in shared memory (generic -> async proxy fence
+//                  before the MMA reads it)
+//   O = P V        tcgen05.mma M128 x N64 x K(keys): A = P from shared memory, B = the V tile exactly as TMA wrote it
+//                  (key rows of 128 B) described as an MN-major operand -- no transpose anywhere; accumulator in TMEM
+//                  columns 448 .. 511
+//   epilogue       the same warps read O (32 channels each), multiply by 1 / (sum of the two halves) and store 64
+//                  contiguous bytes per thread.
+// Thread 0 issues the TMA loads and the MMAs between its own softmax work (the stages of a query block run one after the
+// other anyway: S and P of two blocks do not fit TMEM / shared memory at 257 keys); the S MMAs of block i + 1 are queued
+// right behind the P V MMAs of block i and overlap its epilogue; Q blocks are double buffered.  The bounds of this kernel are
+// the TMEM read of S (~64 B/clk per SM) and the exponentials (MUFU, 16 per clk per SM), about 2200 cycles each per block.  Masked: keys >= t (scores), queries >= t (never
+// stored).  Token counts above 320 use attention_kernel (vit_ops.cu, mma.sync).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "vit.cuh"
+
+namespace vfm {
+
+constexpr int AT_DH = 64, AT_QB = 128;
+constexpr int AT_MAX_CH = 5;                  // 32-key chunks per softmax warp (two warps share a row)
+constexpr int AT_MAX_T = AT_MAX_CH * 2 * 32;   // 320 tokens per image
+constexpr int AT_FEW = 4;                     // query blocks with at most this many real rows take the shared-row path
+constexpr uint32_t AT_O_COL = 448;   // TMEM column of the O accumulator (S uses columns 0 .. 319)
+
+__device__ __forceinline__ void tc_mma_f16_1sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  tc_mma_f16(tmem_d, desc_a, desc_b, idesc, accum);
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// shared memory: [K tile | V tile | Q block x 2 | P tile | barriers]; tiles are 1024-byte aligned (swizzle atoms)
+struct AttnSmem {
+  uint32_t k, v, q, p, bars;
+  uint32_t total;
+};
+__host__ __device__ inline AttnSmem attn_smem(int t) {
+  const uint32_t rows64 = (uint32_t)(t + 63) / 64 * 64;     // K / V rows loaded (boxes of 64 rows)
+  const uint32_t kblocks = (uint32_t)(t + 63) / 64;          // P: 64-key blocks of 128 rows x 128 B
+  AttnSmem s;
+  s.k = 0;
+  s.v = s.k + rows64 * 128;
+  s.q = s.v + rows64 * 128;
+  s.p = s.q + 2 * AT_QB * 128;
+  s.bars = s.p + kblocks * AT_QB * 128;
+  s.total = s.bars + 128 + 4 * AT_QB * 4 + AT_FEW * AT_MAX_T * 4 + 64 + 1024;   // barriers, row max / sum exchange, shared rows, slack
+  return s;
+}
+
+__global__ void __launch_bounds__(256, 1)
+    attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, int t, int width, __nv_bfloat16* __restrict__ out,
+                        const char* pf_ptr, unsigned long long pf_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const AttnSmem L = attn_smem(t);
+  const uint32_t sK = base + L.k, sV = base + L.v, sQ = base + L.q, sP = base + L.p, bars = base + L.bars;
+  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool leader = threadIdx.x == 0;             // issues every TMA load and MMA of the CTA
+  const int head = blockIdx.x, img = blockIdx.y;
+  const int kp = (t + 15) / 16 * 16;                // keys covered by the MMAs (scores of keys >= t are masked, their P is 0)
+  const int n_qb = (t + AT_QB - 1) / AT_QB;
+  const int row0 = img * t;                         // first token row of this image in the QKV matrix
+  const int rows64 = (t + 63) / 64 * 64;
+
+  TraceScope trace(11);
+  TraceMarks marks;   // phases of CTA 0, thread 0
+  pdl_launch_dependents();
+  if (leader) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_q0, 1);
+    mbar_init(bar_q0 + 8, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 8);
+    mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  trace.waited();
+
+  if (leader) l2_prefetch_slice(pf_ptr, pf_bytes, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
+  const int n_lo = kp < 256 ? kp : 256, n_hi = kp - n_lo;
+  const uint32_t idesc_lo = umma_idesc_f16(AT_QB, n_lo, 1), idesc_hi = umma_idesc_f16(AT_QB, n_hi > 0 ? n_hi : 16, 1);
+  const uint32_t idesc_pv = umma_idesc_f16(AT_QB, AT_DH, 1) | (1u << 16);   // B (= V) is MN-major: channels contiguous
+  const uint64_t dK = umma_desc_k_sw128(sK), dV = umma_desc_k_sw128(sV), dP = umma_desc_k_sw128(sP);
+  auto load_q = [&](int qb) {   // leader: query block qb -> buffer qb & 1
+    const uint32_t nb = (uint32_t)(qb & 1);
+    mbar_expect_tx(bar_q0 + 8 * nb, AT_QB * 128u);
+    tma_load_2d(sQ + nb * (AT_QB * 128), &map_qkv, bar_q0 + 8 * nb, head * AT_DH, row0 + qb * AT_QB);
+    tma_load_2d(sQ + nb * (AT_QB * 128) + 64 * 128, &map_qkv, bar_q0 + 8 * nb, head * AT_DH, row0 + qb * AT_QB + 64);
+  };
+  auto issue_s = [&](int qb) {   // leader: S = Q(qb) K^T into TMEM columns 0 .. kp
+    const uint32_t qbuf = (uint32_t)(qb & 1);
+    mbar_wait(bar_q0 + 8 * qbuf, (uint32_t)((qb >> 1) & 1));
+    tc_fence_after();
+    const uint64_t dQ = umma_desc_k_sw128(sQ + qbuf * (AT_QB * 128));
+#pragma unroll
+    for (int k = 0; k < AT_DH / 16; ++k) {
+      tc_mma_f16(tmem_base, dQ + (uint64_t)(k * 2), dK + (uint64_t)(k * 2), idesc_lo, k != 0 ? 1u : 0u);
+      if (n_hi > 0)   // keys 256 ..: rows 256.. of the K tile = +32 KB
+        tc_mma_f16(tmem_base + 256, dQ + (uint64_t)(k * 2), dK + (uint64_t)((256 * 128) >> 4) + (uint64_t)(k * 2), idesc_hi,
+                   k != 0 ? 1u : 0u);
+    }
+    tc_commit(bar_s);
+  };
+  if (leader) {
+    mbar_expect_tx(bar_kv, 2u * (uint32_t)rows64 * 128u);
+    load_q(0);   // Q first: the S MMAs need Q and K
+    for (int r = 0; r < rows64; r += 64) tma_load_2d(sK + r * 128, &map_qkv, bar_kv, width + head * AT_DH, row0 + r);
+    for (int r = 0; r < rows64; r += 64) tma_load_2d(sV + r * 128, &map_qkv, bar_kv, 2 * width + head * AT_DH, row0 + r);
+    if (n_qb > 1) load_q(1);
+    mbar_wait(bar_kv, 0);
+    marks.mark(100);
+    issue_s(0);
+    marks.mark(101);
+  }
+  __syncwarp();
+
+  // ===== softmax + epilogue: all 8 warps.  TMEM lane quarter = warp % 4 (a hardware rule); the two warps of a quarter
+  // (warp, warp + 4) own the same 32 query rows and split the keys in 32-wide chunks (the first takes the larger half) and the
+  // 64 output channels; row maximum and row sum are exchanged through shared memory. =====
+  const int q4 = warp & 3, half = warp >> 2;
+  const int r = q4 * 32 + lane;                    // row inside the query block = TMEM lane
+  const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+  const float sc = 0.125f * 1.4426950408889634f;   // 1 / sqrt(64) * log2(e)
+  const uint32_t p_row = sP + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+  float* xmax = reinterpret_cast<float*>(smem + L.bars + 128);   // [2][128]
+  float* xsum = xmax + 2 * AT_QB;                                  // [2][128]
+  const int n_chunks = (kp + 31) >> 5, c_split = (n_chunks + 1) >> 1;
+  const int c_begin = half ? c_split : 0, c_end = half ? n_chunks : c_split;
+  const int pair_bar = 1 + q4;   // named barrier of the two warps of this quarter (0 is __syncthreads)
+  for (int qb = 0; qb < n_qb; ++qb) {
+    const int q_row = qb * AT_QB + r;
+    const bool warp_live = qb * AT_QB + q4 * 32 < t;   // warp-uniform: some row of this warp is a real query
+    mbar_wait(bar_s, (uint32_t)(qb & 1));
+    if (leader) marks.mark(110);
+    tc_fence_after();
+    const int live_rows = t - qb * AT_QB;   // real query rows of this block (>= 128: all)
+    // the scores of this thread's keys are read from TMEM ONCE (TMEM reads run at ~64 B/clk per SM: a second pass over the
+    // 128 x keys fp32 tile would cost as much as all the exponentials) and stay in registers: up to AT_MAX_CH chunks
+    uint32_t v[AT_MAX_CH][32];
+    if (warp_live) {
+#pragma unroll
+      for (int i = 0; i < AT_MAX_CH; ++i)
+        if (c_begin + i < c_end) tc_ld32(t_lane + (c_begin + i) * 32, v[i]);
+      tc_wait_ld();
+    }
+    if (live_rows <= AT_FEW) {
+      // ---- a block with a handful of real rows (the 257th token of a 16 x 16 patch grid): one thread per row would spend a
+      // full block's worth of MUFU issue slots on them (an exp2 costs the warp 8 cycles however few lanes are active).  The
+      // rows' scores go through shared memory instead and all 256 threads share each row: thread j takes keys j and j + 256.
+      float* srow = xsum + 2 * AT_QB;   // [AT_FEW][AT_MAX_T] scores, then [8] per-warp partials
+      float* wpart = srow + AT_FEW * AT_MAX_T;
+      if (q4 == 0) {
+        if (lane < live_rows) {
+#pragma unroll
+          for (int i = 0; i < AT_MAX_CH; ++i)
+            if (c_begin + i < c_end) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) srow[lane * AT_MAX_T + (c_begin + i) * 32 + j] = __uint_as_float(v[i][j]);
+            }
+        }
+      }
+      asm volatile("bar.sync 9, 256;" ::: "memory");
+      const int tid = threadIdx.x;
+      for (int row = 0; row < live_rows; ++row) {
+        const float s0 = tid < t ? srow[row * AT_MAX_T + tid] : -INFINITY;
+        const float s1 = tid + 256 < t ? srow[row * AT_MAX_T + tid + 256] : -INFINITY;
+        float mx = fmaxf(s0, s1);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (lane == 0) wpart[warp] = mx;
+        asm volatile("bar.sync 9, 256;" ::: "memory");
+        mx = wpart[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, wpart[w]);
+        const float mb = -mx * sc;
+        const float p0 = tid < t ? ex2_approx(fmaf(s0, sc, mb)) : 0.f;
+        const float p1 = tid + 256 < t ? ex2_approx(fmaf(s1, sc, mb)) : 0.f;
+        float sum = p0 + p1;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        asm volatile("bar.sync 9, 256;" ::: "memory");   // every thread has read the maxima
+        if (lane == 0) wpart[warp] = sum;
+        // P[row][key] (bf16) at its swizzled place: key block key / 64, 16-byte chunk (key % 64) / 8 XOR row % 8
+        const uint32_t prow = sP + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+        auto put = [&](int key, float p) {
+          if (key < kp) {
+            const uint32_t addr = prow + (uint32_t)(key >> 6) * (AT_QB * 128) + (uint32_t)(((((key & 63) >> 3) ^ (row & 7)) << 4) + (key & 7) * 2);
+            const __nv_bfloat16 h = __float2bfloat16(p);
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
+          }
+        };
+        put(tid, p0);
+        put(tid + 256, p1);
+        asm volatile("bar.sync 9, 256;" ::: "memory");
+        if (tid == 0) {
+          float tot = wpart[0];
+          for (int w = 1; w < 8; ++w) tot += wpart[w];   // fixed order: deterministic
+          xsum[row] = tot;
+          xsum[AT_QB + row] = 0.f;
+        }
+      }
+      asm volatile("bar.sync 9, 256;" ::: "memory");   // the row sums are visible to the epilogue's threads
+    } else
+    if (warp_live) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < AT_MAX_CH; ++i)
+        if (c_begin + i < c_end) {
+          const int valid = t - (c_begin + i) * 32;   // keys of the chunk are real iff index < valid
+          if (valid >= 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[i][j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < valid) mx = fmaxf(mx, __uint_as_float(v[i][j]));
+          }
+        }
+      xmax[half * AT_QB + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(xmax[r], xmax[AT_QB + r]);
+      if (leader) marks.mark(111);
+      const float mb = -mx * sc;
+      // ---- p = exp2((s - max) * sc) -> row sum (fp32) and bf16 P tile
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < AT_MAX_CH; ++i)
+        if (c_begin + i < c_end) {
+          const int c = c_begin + i;
+          const int valid = t - c * 32;
+          uint32_t pk[16];
+          if (valid >= 32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[i][j]), sc, mb));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[i][j + 1]), sc, mb));
+              sum += p0 + p1;
+              pk[j >> 1] = pack_bf16x2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float p0 = j < valid ? ex2_approx(fmaf(__uint_as_float(v[i][j]), sc, mb)) : 0.f;
+              const float p1 = j + 1 < valid ? ex2_approx(fmaf(__uint_as_float(v[i][j + 1]), sc, mb)) : 0.f;
+              sum += p0 + p1;
+              pk[j >> 1] = pack_bf16x2(p0, p1);
+            }
+          }
+          // 32 keys = four 16-byte chunks of this row in key block c / 2, XOR-swizzled with the row index (SWIZZLE_128B)
+          const uint32_t blk = p_row + (uint32_t)(c >> 1) * (AT_QB * 128);
+          const int ch0 = (c & 1) << 2;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            if (c * 32 + 8 * k4 < kp) {
+              const uint32_t addr = blk + (uint32_t)(((ch0 + k4) ^ (r & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * k4]), "r"(pk[4 * k4 + 1]),
+                           "r"(pk[4 * k4 + 2]), "r"(pk[4 * k4 + 3])
+                           : "memory");
+            }
+          }
+        }
+      xsum[half * AT_QB + r] = sum;
+    }
+    if (leader) marks.mark(112);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P (generic-proxy stores) -> visible to the MMA
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
+    if (leader) {
+      // every warp is done with S(qb) and has written its part of P(qb): O = P V, then S of the next block right behind it
+      // (it overlaps the epilogue below; its Q block has been loaded while this block ran)
+      mbar_wait(bar_p, (uint32_t)(qb & 1));
+      marks.mark(102);
+      tc_fence_after();
+      for (int kk = 0; kk < kp / 16; ++kk) {
+        // A: 16 keys of P = 32 B inside the 128 B swizzle row of key block kk / 4; B: 16 key rows of V = 2 x 1024 B
+        const uint64_t da = dP + (uint64_t)(((kk >> 2) * (AT_QB * 128)) >> 4) + (uint64_t)((kk & 3) * 2);
+        const uint64_t db = dV + (uint64_t)((kk * 2048) >> 4);
+        tc_mma_f16(tmem_base + AT_O_COL, da, db, idesc_pv, kk != 0 ? 1u : 0u);
+      }
+      tc_commit(bar_o);
+      if (qb + 1 < n_qb) {
+        issue_s(qb + 1);
+        if (qb + 2 < n_qb) load_q(qb + 2);   // into the buffer S(qb) read; those MMAs completed before bar_s(qb)
+      }
+      marks.mark(103);
+    }
+    __syncwarp();
+    mbar_wait(bar_o, (uint32_t)(qb & 1));
+    if (leader) marks.mark(113);
+    tc_fence_after();
+    if (warp_live) {
+      uint32_t o[32];
+      tc_ld32(t_lane + AT_O_COL + half * 32, o);
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // both partial sums of the row are in shared memory
+      const float inv_sum = 1.f / (xsum[r] + xsum[AT_QB + r]);
+      tc_wait_ld();
+      if (q_row < t) {
+        __nv_bfloat16* dst = out + (long long)(row0 + q_row) * width + head * AT_DH + half * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * i]) * inv_sum, __uint_as_float(o[8 * i + 1]) * inv_sum);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_sum, __uint_as_float(o[8 * i + 3]) * inv_sum);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_sum, __uint_as_float(o[8 * i + 5]) * inv_sum);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_sum, __uint_as_float(o[8 * i + 7]) * inv_sum);
+          *reinterpret_cast<uint4*>(dst + 8 * i) = w;
+        }
+      }
+    }
+    if (leader) marks.mark(114);
+    // O(qb) has been read by this warp before it takes part in P(qb + 1): PV(qb + 1) is issued after all 8 warps arrived
+    tc_fence_before();
+  }
+  if (leader) marks.flush();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+  trace.end();
+}
+
+bool vit_attention_tc_supported(int t) { return t >= 16 && t <= AT_MAX_T; }
+
+int vit_attention_tc(vfmreg_ctx* ctx, const CUtensorMap& map_qkv, int b, int t, int heads, int width, __nv_bfloat16* out,
+                     const void* pf_ptr, size_t pf_bytes) {
+  VFM_CHECK_ARG(width == heads * AT_DH && vit_attention_tc_supported(t), "attention_tc: unsupported shape (t %d, width %d, heads %d)", t,
+                width, heads);
+  const size_t smem = attn_smem(t).total;
+  if (smem > ctx->attention_tc_smem_attr) {   // per device (= per context)
+    VFM_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->attention_tc_smem_attr = smem;
+  }
+  VFM_CUDA(launch_pdl(attention_tc_kernel, dim3(heads, b), dim3(256), smem, ctx->stream, map_qkv, t, width, out, (const char*)pf_ptr,
+                      (unsigned long long)pf_bytes));
+  return launch_check(ctx, "attention_tc_kernel");
+}
+
+}  // namespace vfm
+
+VFM_TRACE_ATTACH(vfmreg_trace_attach_attn)

@@ -173,6 +173,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
   if (warp == 0) {
     // ===== TMA producer: this CTA's 128 weight rows and its half of the token tile =====
     uint32_t stage = 0, phase = 0;
+    if (elect_one()) l2_prefetch_slice(ep.pf_ptr, ep.pf_bytes, blockIdx.x, gridDim.x);
+    __syncwarp();
     for (int t = cid; t < total; t += clusters) {
       const GemmTile g = gemm_tile(ep, t);
       const int w_row = g.fb * 2 * G_FM + (int)rank * G_FM;
@@ -286,7 +288,7 @@ static long long gemm_cost(int m, int n, int k, int nt, int split, int clusters,
     const int kb = (kbs * (s + 1)) / split - (kbs * s) / split;
     const long long b = (long long)kb * 2 * (G_A_BYTES + (long long)(w / 2) * (G_BK * 2));
     *bytes = b;
-    const long long mma = (long long)kb * 4 * (w / 2), ingest = b / 110;
+    const long long mma = (long long)kb * 4 * (w / 2), ingest = b / 100;
     return (mma > ingest ? mma : ingest) + 600 + (long long)(w / 64 + 1) * 250;
   };
   const int tiles_full = fb_count * n_full, tiles = tiles_full + (tail ? fb_count : 0);
@@ -301,8 +303,8 @@ static long long gemm_cost(int m, int n, int k, int nt, int split, int clusters,
     }
     if (sum > worst) worst = sum;
   }
-  long long l2 = total_bytes / 5500;
-  if (split > 1) l2 += (long long)split * m * n * 8 / 5500;   // the partial sums are written here and read back by the next kernel
+  long long l2 = total_bytes / 7500;   // calibrated on the plan sweep (tools/vit_plan_sweep.sh, profiles/r2_vit_plan_sweep_b6.txt)
+  if (split > 1) l2 += (long long)split * m * n * 8 / 7500;   // the partial sums are written here and read back by the next kernel
   if (plan) {
     plan->nt = nt;
     plan->split = split;
