@@ -122,3 +122,28 @@ def test_project_gather_rot90_matches_reference_nclt_branch(vfm, golden):
     z0[np.all(g["images"] == 0, axis=-1)] = 0
     d0, _, _ = vfm.project_gather(pts, cams0, [z0[i] for i in range(3)], [g["images"][i] for i in range(3)])
     assert np.abs(d0.cpu().numpy() - g["out"]).max() < 1e-6
+
+
+def test_nclt_dataset_camera_spec_on_the_kernel(vfm, golden, tmp_path):
+    """datasets.NCLT.camera_spec drives the fused kernel to the visible set and pixels of the reference's
+    project_pcl_to_image on the synthetic NCLT tree (fixture from oracle/gen_golden_datasets.py)."""
+    import os
+    import sys
+    pytest.importorskip("cv2")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import synth_dataset
+    from vfm_registration_b200 import datasets
+    g = golden("datasets_nclt.npz")
+    synth_dataset.build(tmp_path, cameras=("Cam1",), distinct_maps=1)
+    for sub in (1, 2):
+        seq = datasets.NCLT(synth_dataset.SEQ, tmp_path, image_subsample=sub, cameras=("Cam1",))
+        img = seq.read_images(frame_id=0)["Cam1"]
+        pcl = seq.read_pcl(frame_id=0)
+        spec = seq.camera_spec("Cam1", img.shape[:2])
+        spec.grid_hw = (4, 5)
+        tok = np.random.default_rng(0).standard_normal((4, 5, 8)).astype(np.float32)
+        _, cam_of, uv = vfm.project_gather(pcl, [spec], [tok], [img])
+        sel = np.nonzero(cam_of.cpu().numpy() == 0)[0]
+        assert np.array_equal(sel, g[f"proj{sub}_Cam1_idx"])
+        assert np.array_equal(uv.cpu().numpy()[sel, 0], g[f"proj{sub}_Cam1_x"])
+        assert np.array_equal(uv.cpu().numpy()[sel, 1], g[f"proj{sub}_Cam1_y"])

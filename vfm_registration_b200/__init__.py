@@ -6,4 +6,4 @@ from .api import (CameraSpec, Context, MatchResult, RansacResult, RegResult, Vfm
 __version__ = "0.1.0"
 from .features import ImageFeatureGenerator, ViTFeaturizer, create_descriptors, extract_features  # noqa: E402,F401
 from .voxel import VoxelMap, register_frame, register_frame_vfm, voxel_down_sample  # noqa: E402,F401
-from . import scenes  # noqa: E402,F401
+from . import datasets, scenes  # noqa: E402,F401
