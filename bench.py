@@ -172,6 +172,33 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_other_workload(args, v, ctx, dev, rank, local_rank):
+    """`--workload configs[0|2|3]` / `reference_shape`: one of the measurement legs of tools/bench_extras.py as a bench line of its
+    own (rank 0, one GPU): value = device-resident, e2e = host buffers, roofline of the leg's dominant kernel, parity and the CPU
+    arm of that configuration where the leg has them."""
+    if rank != 0:
+        return
+    from tools import bench_extras
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.kernel_launches
+    leg = bench_extras.LEGS[args.workload](v, ctx, dev, load_peaks())
+    launches = ctx.kernel_launches - l0
+    clocks = sampler.stop()
+    unit = "searches/s" if args.workload == "reference_shape" else UNIT
+    value = leg.get("value", leg.get("searches_per_sec"))
+    line = {"metric": METRIC if unit == UNIT else "map_searches_per_sec", "value": value, "unit": unit, "n_gpus": 1, "steps": 10, "warmup": 3,
+            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": leg.get("dtype", "f32 match"), "data": "synthetic", "config": {"workload": leg["workload"], "l2": leg.get("l2")},
+            "roofline": leg.get("roofline"), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": leg.get("e2e"), "unit": unit, "h2d_bytes_per_step": leg.get("h2d_bytes"), "d2h_bytes_per_step": None},
+            "parity": leg.get("parity"), "cpu_baseline": leg.get("cpu_baseline")}
+    for k in ("hyps_per_sec", "recall_at_1m_5deg", "vit_forward_ms", "images_per_sec", "n_corr", "rte_m", "rre_deg"):
+        if k in leg:
+            line[k] = leg[k]
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -185,6 +212,9 @@ def main():
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--workload", default="configs[1]", choices=["configs[0]", "configs[1]", "configs[2]", "configs[3]", "reference_shape"],
+                    help="configs[1] = the headline (BASELINE.json's metric is quoted on it); the others print the same JSON line "
+                         "for one of the other BASELINE configurations (N = 1 only; they are parity-test cases first)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -213,6 +243,11 @@ def main():
     import vfm_registration_b200 as v
     from vfm_registration_b200 import synth
     ctx = v.get_context(local_rank)
+    if args.workload != "configs[1]":
+        run_other_workload(args, v, ctx, dev, rank, local_rank)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     lanes = args.lanes or 5   # the library default
     ctx.set_lanes(lanes)
     S, C = args.scenes_per_step, args.scans_per_map

@@ -150,3 +150,46 @@ def test_vit_graph_replay_matches_eager(vfm):
     e_big = f.forward(big).clone()
     g_big = f.forward(big).clone()
     assert torch.equal(e_big, g_big) and torch.equal(f.forward(a), ea)
+
+
+def test_nn_indices_survive_the_bf16_forward(vfm):
+    """What the registration consumes is not the tokens but the nearest-neighbour indices computed from them.  Descriptors
+    gathered from the GPU forward (bf16 GEMM operands) and from the fp32 oracle forward of the same seeded ViT-S/14 are
+    matched (scan vs map, cosine gate 0.8 as VoxelHashMap.cpp:486-511): at least 99 % of the gated queries pick the same map
+    row, and the two gated sets agree to within 1 %."""
+    cfg = ovit.CONFIGS["vits14"]
+    sd = ovit.make_weights(cfg, seed=21)
+    rng = np.random.default_rng(9)
+    imgs = _images(rng, 3, 224, 224)
+    f = vfm.ViTFeaturizer("vits14", sd)
+    tok_gpu = f.forward(imgs).cpu().numpy()                                     # (3, 16, 16, 384)
+    tok_ref = ovit.forward(sd, cfg, torch.stack([ovit.preprocess(im) for im in imgs])).numpy()
+
+    def sample(tok, cam, gy, gx):   # bilinear sample of the token grid at continuous grid coordinates (SURVEY A.6)
+        y0, x0 = np.floor(gy).astype(int), np.floor(gx).astype(int)
+        y1, x1 = np.minimum(y0 + 1, 15), np.minimum(x0 + 1, 15)
+        wy, wx = (gy - y0)[:, None], (gx - x0)[:, None]
+        t = tok[cam]
+        return ((1 - wy) * ((1 - wx) * t[y0, x0] + wx * t[y0, x1]) + wy * ((1 - wx) * t[y1, x0] + wx * t[y1, x1])).astype(np.float32)
+
+    m, n = 6000, 2000
+    cam_m, gy_m, gx_m = rng.integers(0, 3, m), rng.uniform(0, 15, m), rng.uniform(0, 15, m)
+    pick = rng.choice(m, n, replace=False)           # every scan point sits near one map point (a few hundredths of a cell)
+    cam_s, gy_s, gx_s = cam_m[pick], np.clip(gy_m[pick] + rng.normal(0, 0.03, n), 0, 15), np.clip(gx_m[pick] + rng.normal(0, 0.03, n), 0, 15)
+    res = {}
+    for name, tok in (("gpu", tok_gpu), ("ref", tok_ref)):
+        mp = np.concatenate([sample(tok, c, gy_m[cam_m == c], gx_m[cam_m == c]) for c in range(3)])
+        order = np.concatenate([np.nonzero(cam_m == c)[0] for c in range(3)])
+        map_feat = np.empty_like(mp)
+        map_feat[order] = mp
+        sc = np.empty((n, mp.shape[1]), dtype=np.float32)
+        for c in range(3):
+            sc[cam_s == c] = sample(tok, c, gy_s[cam_s == c], gx_s[cam_s == c])
+        r = vfm.match_nn(sc, map_feat)
+        res[name] = (r.idx01.cpu().numpy(), r.sim01.cpu().numpy())
+    gated_gpu, gated_ref = res["gpu"][1] >= 0.8, res["ref"][1] >= 0.8
+    both = gated_gpu & gated_ref
+    assert both.sum() > 0.9 * n, int(both.sum())                                   # the planted neighbours clear the gate
+    assert (gated_gpu != gated_ref).mean() < 0.01
+    agree = (res["gpu"][0][both] == res["ref"][0][both]).mean()
+    assert agree >= 0.99, float(agree)

@@ -47,10 +47,11 @@ def test_voxel_down_sample_errors(vfm):
         vfm.voxel_down_sample(np.zeros((10, 2)), 1.0)
     bad = np.zeros((4, 3))
     bad[2, 0] = np.inf
-    with pytest.raises(vfm.VfmRegError):
-        vfm.voxel_down_sample(bad, 1.0)
-    with pytest.raises(vfm.VfmRegError):
-        vfm.voxel_down_sample(np.full((4, 3), 3e7), 1.0)   # |index| >= 2^20
+    with pytest.warns(RuntimeWarning, match="1 of 4"):   # dropped by the host wrapper (the library alone rejects the cloud)
+        out, idx = vfm.voxel_down_sample(bad, 1.0, return_index=True)
+    assert out.shape == (1, 3) and idx.tolist() == [0]
+    with pytest.warns(RuntimeWarning, match="4 of 4"):
+        assert vfm.voxel_down_sample(np.full((4, 3), 3e7), 1.0).shape == (0, 3)   # |index| >= 2^20
     assert vfm.voxel_down_sample(np.zeros((0, 3)), 1.0).shape == (0, 3)
 
 
@@ -292,3 +293,27 @@ def test_voxel_operations_full_size(vfm):
     sure = d < 0.99                                    # the true neighbour then lies inside the 27 voxels
     assert sure.mean() > 0.9 and valid.cpu().numpy()[sure].all()
     assert np.array_equal(tgt.cpu().numpy()[sure], kept[j[sure]]) and np.allclose(np.sqrt(d2.cpu().numpy()[sure]), d[sure], rtol=0, atol=1e-12)
+
+
+def test_non_finite_points_are_dropped_not_fatal(vfm):
+    """Raw scans carry NaN / inf returns: voxel_down_sample and VoxelMap.build drop them (with a warning) and keep reporting
+    row numbers of the caller's array (the library alone rejects such a cloud: VFMREG_ERR_ARG)."""
+    rng = np.random.default_rng(12)
+    pts = rng.uniform(-20, 20, (5000, 3))
+    bad = rng.choice(5000, 37, replace=False)
+    dirty = pts.copy()
+    dirty[bad[:20]] = np.nan
+    dirty[bad[20:30], 1] = np.inf
+    dirty[bad[30:]] = 1e9   # beyond +-2^20 voxels of 0.5 m
+    with pytest.warns(RuntimeWarning, match="37 of 5000"):
+        out, idx = vfm.voxel_down_sample(dirty, 0.5, return_index=True)
+    good = np.setdiff1d(np.arange(5000), bad)
+    ref, ref_idx = vfm.voxel_down_sample(pts[good], 0.5, return_index=True)
+    assert np.array_equal(idx, good[ref_idx]) and np.array_equal(out, ref)
+    m = vfm.VoxelMap(0.5, 20)
+    with pytest.warns(RuntimeWarning):
+        m.build(dirty)
+    xyz, src = m.points()
+    assert np.isfinite(xyz.cpu().numpy()).all() and np.isin(src.cpu().numpy(), good).all()
+    assert np.array_equal(xyz.cpu().numpy(), dirty[src.cpu().numpy()])
+    m.close()

@@ -78,6 +78,7 @@ def config0(v, ctx, dev, peaks):
     rte, rre = synth.pose_errors(r.T, s["T_gt"])
     return {"workload": "configs[0]: 4096 x 4096 pts, 384-d, cos >= 0.8 gate, 1024 RANSAC hyps (tau = 1 m)",
             "value": 1e3 / ms_d, "e2e": 1e3 / ms_h, "unit": "pairs/s", "ms_per_pair": ms_d, "l2": "flushed between iterations",
+            "h2d_bytes": 2 * 4096 * (384 + 3) * 4, "dtype": "f32 match / f64 solve",
             "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "pairs/s", "cores": cref.num_threads(), "kind": "port"},
             "parity": {"corr_equal": bool(np.array_equal(r.corr, corr)), "mask_equal": bool(np.array_equal(r.inlier_mask, c["mask"])),
                        "best_equal": r.best_hyp == c["best"], "T_frob": float(np.linalg.norm(r.T - c["T"]))},
@@ -112,7 +113,7 @@ def config3(v, ctx, dev, peaks):
     rte, rre = synth.pose_errors(r.T, s["T_gt"])
     return {"workload": "configs[3]: 200k map x 20k scan pts, 768-d, ratio test 0.9, 65536 RANSAC hyps (tau = 1 m)",
             "value": 1e3 / ms_d, "e2e": 1e3 / ms_h, "unit": "pairs/s", "ms_per_pair": ms_d, "hyps_per_sec": h * 1e3 / ms_d,
-            "l2": "inputs (676 MB) larger than L2",
+            "l2": "inputs (676 MB) larger than L2", "h2d_bytes": (n + m) * (d + 3) * 4, "dtype": "f32 match / f64 solve",
             "roofline": {"bound": "tensor", "kernel": "match_tc3_kernel<streamed A>, top-2 mode", "achieved": flops / (k_avg * 1e-3) / 1e12,
                          "peak": peaks["tf"], "unit": "TFLOP/s", "frac": flops / (k_avg * 1e-3) / 1e12 / peaks["tf"], "avg_launch_ms": k_avg,
                          "ransac_score_avg_ms": r_ms / max(r_n, 1),
@@ -174,7 +175,8 @@ def config2(v, ctx, dev, peaks):
     out = {"workload": "configs[2]: 6 x (224 x 224) images -> DINOv2 ViT-L/14 -> projection gather (10k pts) -> mutual match vs a "
                        "resident 50k-pt map -> 8192-hyp RANSAC; random-init weights (none available offline)",
            "value": 1e3 / ms_d, "e2e": 1e3 / ms_h, "unit": "pairs/s", "ms_per_pair": ms_d, "l2": "flushed between iterations",
-           "vit_forward_ms": ms_vit, "images_per_sec": b * 1e3 / ms_vit,
+           "vit_forward_ms": ms_vit, "images_per_sec": b * 1e3 / ms_vit, "h2d_bytes": b * hh * ww * 3 + 2 * n_scan * 12,
+           "dtype": "bf16 GEMM operands, f32 accumulate / residual (ViT); f32 match / f64 solve",
            "roofline": {"bound": "tensor", "kernel": "vit_gemm_kernel (all GEMMs of one forward)", "achieved": b * flops_img / (ms_vit * 1e-3) / 1e12,
                         "peak": peaks["tf"], "unit": "TFLOP/s", "frac": b * flops_img / (ms_vit * 1e-3) / 1e12 / peaks["tf"],
                         "note": "whole forward (GEMMs + attention + norms) over the model's algorithmic flop",

@@ -20,6 +20,20 @@ from . import _lib
 from .api import _ptr, get_context
 
 MAX_NUM_ITERATIONS = 1000   # Registration.cpp:92
+VOXEL_RANGE = float(1 << 20)   # the 3 x 21-bit voxel key of csrc/voxel.cu
+
+
+def _usable_rows(t: torch.Tensor, voxel_size: float) -> Optional[torch.Tensor]:
+    """Raw LiDAR returns contain NaN / inf rows, and a point 2^20 voxels from the origin has no key: the reference keeps
+    such rows alive as undefined behaviour (`cast<int>` of a non-finite double); the library rejects the whole call.  Here
+    they are dropped (with a warning) before the call.  Returns the kept row indices, or None when every row is usable."""
+    xyz = t[:, :3]
+    ok = torch.isfinite(xyz).all(dim=1) & ((xyz.abs().to(torch.float64) / float(voxel_size)) < VOXEL_RANGE - 1).all(dim=1)
+    if bool(ok.all()):
+        return None
+    import warnings
+    warnings.warn(f"{int((~ok).sum())} of {t.shape[0]} points are not finite or outside +-2^20 voxels: dropped", RuntimeWarning, stacklevel=3)
+    return torch.nonzero(ok).squeeze(1)
 
 
 def voxel_down_sample(points, voxel_size: float, *, return_index: bool = False, device=None):
@@ -35,6 +49,9 @@ def voxel_down_sample(points, voxel_size: float, *, return_index: bool = False, 
     if t.dtype not in (torch.float32, torch.float64):
         t = t.to(torch.float64)
     t = t.to(dev).contiguous()
+    rows = _usable_rows(t, voxel_size)   # indices into the caller's array, or None
+    if rows is not None:
+        t = t[rows].contiguous()
     n, cols = t.shape
     if n == 0:
         out = t.cpu().numpy() if is_np else t
@@ -50,6 +67,8 @@ def voxel_down_sample(points, voxel_size: float, *, return_index: bool = False, 
         _lib.check(ctx.lib.vfmreg_gather_rows(ctx.handle, _ptr(t), cols * t.element_size(), _ptr(keep), _ptr(count), k, _ptr(out)),
                    "vfmreg_gather_rows")
     idx = keep[:k]
+    if rows is not None:
+        idx = rows[idx.long()].to(torch.int32)   # row numbers of the caller's array
     if is_np:
         out = out.cpu().numpy()
         idx = idx.cpu().numpy().astype(np.int64)
@@ -87,6 +106,9 @@ class VoxelMap:
     def build(self, xyz) -> None:
         """Replace the content by the thinned points of ``xyz`` (N, 3)."""
         t = self._f64(xyz)
+        self._rows = _usable_rows(t, self.voxel_size)   # non-finite / out-of-range rows are dropped; src_idx stays the caller's
+        if self._rows is not None:
+            t = t[self._rows].contiguous()
         self.ctx.bind_stream()
         _lib.check(self.ctx.lib.vfmreg_voxel_map_build(self.ctx.handle, self.handle, _ptr(t), t.shape[0]), "vfmreg_voxel_map_build")
 
@@ -104,6 +126,8 @@ class VoxelMap:
             _lib.check(self.ctx.lib.vfmreg_voxel_map_points(self.ctx.handle, self.handle, _ptr(xyz), _ptr(idx)), "vfmreg_voxel_map_points")
             order = torch.argsort(idx)
             xyz, idx = xyz[order], idx[order]
+            if getattr(self, "_rows", None) is not None:
+                idx = self._rows[idx.long()].to(torch.int32)
         return xyz, idx
 
     def nearest(self, query, max_dist: float):
