@@ -167,14 +167,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
-  trace.waited();
-
   if (warp == 0) {
     // ===== TMA producer: this CTA's 128 weight rows and its half of the token tile =====
+    // The weights do not depend on the previous kernel: their loads for the first ring of stages (and the L2 prefetch of a
+    // later GEMM's weights) are issued BEFORE griddepcontrol.wait, while the previous kernel is still running -- after a
+    // LayerNorm (no shared memory) this CTA is resident microseconds early.  Only the token loads wait.
     uint32_t stage = 0, phase = 0;
-    if (elect_one()) l2_prefetch_slice(ep.pf_ptr, ep.pf_bytes, blockIdx.x, gridDim.x);
-    __syncwarp();
+    int pre = 0;
+    if (cid < total) {
+      const GemmTile g0 = gemm_tile(ep, cid);
+      pre = min(G_STAGES, g0.kb1 - g0.kb0);
+      if (elect_one()) {
+        const int w_row = g0.fb * 2 * G_FM + (int)rank * G_FM;
+        const uint32_t b_bytes = (uint32_t)(g0.w / 2) * (G_BK * 2);
+        for (int s = 0; s < pre; ++s) {
+          const uint32_t full_leader = mapa_cluster(full0 + 8 * s, 0);
+          if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2u * (G_A_BYTES + b_bytes));
+          tma_load_2d_2sm(base + s * G_STAGE_BYTES, &map_w, full_leader, (g0.kb0 + s) * G_BK, w_row);
+        }
+        l2_prefetch_slice(ep.pf_ptr, ep.pf_bytes, blockIdx.x, gridDim.x);
+      }
+      __syncwarp();
+    }
+    pdl_wait();   // the previous kernel's results (the token matrix) are visible from here on
+    trace.waited();
     for (int t = cid; t < total; t += clusters) {
       const GemmTile g = gemm_tile(ep, t);
       const int w_row = g.fb * 2 * G_FM + (int)rank * G_FM;
@@ -184,11 +200,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
       const uint32_t b_bytes = (uint32_t)(g.w / 2) * (G_BK * 2);
 #pragma unroll 1
       for (int kb = g.kb0; kb < g.kb1; ++kb) {
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const bool early = t == cid && kb - g.kb0 < pre;   // barrier armed and weights already on their way
+        if (!early) mbar_wait(empty0 + 8 * stage, phase ^ 1);
         if (elect_one()) {
           const uint32_t full_leader = mapa_cluster(full0 + 8 * stage, 0);
-          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2u * (G_A_BYTES + b_bytes));
-          tma_load_2d_2sm(base + stage * G_STAGE_BYTES, &map_w, full_leader, kb * G_BK, w_row);
+          if (!early) {
+            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2u * (G_A_BYTES + b_bytes));
+            tma_load_2d_2sm(base + stage * G_STAGE_BYTES, &map_w, full_leader, kb * G_BK, w_row);
+          }
           tma_load_2d_2sm(base + stage * G_STAGE_BYTES + G_A_BYTES, mx, full_leader, kb * G_BK, x_row);
         }
         __syncwarp();
@@ -197,6 +216,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the leader CTA only =====
+    pdl_wait();
     if (rank == 0) {
       uint32_t stage = 0, phase = 0;
       int it = 0;
@@ -228,6 +248,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     }
   } else {
     // ===== epilogue: this CTA's 128 features x the tile's tokens; thread = feature (TMEM lane), chunks of 32 tokens =====
+    pdl_wait();   // the epilogue writes what the previous kernels may still be reading
     const int q = warp & 3, half = (warp - 2) >> 2;
     int it = 0;
     const uint32_t tempty_leader0 = mapa_cluster(tempty0, 0);
