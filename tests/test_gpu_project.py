@@ -147,3 +147,31 @@ def test_nclt_dataset_camera_spec_on_the_kernel(vfm, golden, tmp_path):
         assert np.array_equal(sel, g[f"proj{sub}_Cam1_idx"])
         assert np.array_equal(uv.cpu().numpy()[sel, 0], g[f"proj{sub}_Cam1_x"])
         assert np.array_equal(uv.cpu().numpy()[sel, 1], g[f"proj{sub}_Cam1_y"])
+
+
+def test_binned_path_equals_one_kernel_path(vfm):
+    """Clouds of >= 65536 points are binned by (camera, token cell) before the gather (project.cu); the result must be the
+    one-kernel path's bit for bit -- the same cloud in chunks below the threshold runs that path -- including the rot90 frame,
+    black pixels that hide (mode 1) or claim (mode 2) a point, and points no camera sees."""
+    rng = np.random.default_rng(21)
+    n, d, hw, grid = 200_000, 384, (96, 128), (7, 9)
+    pts = np.c_[rng.uniform(-30, 30, (n, 2)), rng.uniform(-3, 6, n)].astype(np.float32)
+    kmat = np.array([[60.0, 0, 64.0], [0, 60.0, 48.0], [0, 0, 1.0]])
+    cams, toks, imgs = [], [], []
+    from scipy.spatial.transform import Rotation as R
+    for c in range(4):
+        t = np.eye(4)
+        t[:3, :3] = (R.from_euler("z", 90.0 * c, degrees=True) * R.from_euler("yx", [90, -90], degrees=True)).as_matrix().T
+        rot = c == 1
+        img = rng.integers(1, 255, ((hw[1], hw[0]) if rot else hw) + (3,), dtype=np.uint8)
+        img[10:30, 20:50] = 0
+        cams.append(vfm.CameraSpec(P=kmat @ t[:3], img_hw=hw, grid_hw=grid if not rot else (grid[1], grid[0]), black_mode=(1, 1, 2, 0)[c], rot90=rot))
+        toks.append(rng.standard_normal(((grid[1], grid[0]) if rot else grid) + (d,)).astype(np.float32))
+        imgs.append(img)
+    desc, cam_of, uv = vfm.project_gather(pts, cams, toks, imgs)
+    desc, cam_of, uv = desc.cpu().numpy(), cam_of.cpu().numpy(), uv.cpu().numpy()
+    assert (cam_of >= 0).mean() > 0.3 and (cam_of < 0).mean() > 0.01 and len(np.unique(cam_of)) == 5
+    for lo in range(0, n, 50_000):
+        d2, c2, u2 = vfm.project_gather(pts[lo:lo + 50_000], cams, toks, imgs)
+        assert np.array_equal(cam_of[lo:lo + 50_000], c2.cpu().numpy()) and np.array_equal(uv[lo:lo + 50_000], u2.cpu().numpy())
+        assert np.array_equal(desc[lo:lo + 50_000], d2.cpu().numpy())

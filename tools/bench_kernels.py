@@ -101,9 +101,9 @@ def bench_project(n=2_000_000, d=384):
     ms = time_fn(lambda: v.project_gather(pts, cams, toks, imgs), iters=10)
     gms, gl = ctx.group_time_ms(2)
     ctx.enable_timing(False)
-    k = gms / max(gl, 1)
+    k = gms / 13   # device time of one call (3 warm-up + 10 timed calls; a call is one launch, or four on the binned path)
     by = n * (12 + 4 * d + 12) + 6 * 256 * d * 4
-    print(f"project_gather N={n} D={d}: call {ms:.3f} ms, kernel {k:.3f} ms = {by / k / 1e6:.0f} GB/s algorithmic "
+    print(f"project_gather N={n} D={d}: call {ms:.3f} ms, kernels {k:.3f} ms ({gl // 13} launches) = {by / k / 1e6:.0f} GB/s algorithmic "
           f"(12 B read + {4 * d} B desc + 12 B index written per point)", flush=True)
 
 
