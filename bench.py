@@ -412,15 +412,19 @@ def main():
             pass
         cores = cref.use_all_cores()   # torchrun exports OMP_NUM_THREADS=1; the baseline uses every core it may
         t_cpu, cres = cpu_scene(scenes[-1])
-        gres = res[-C:]
+        n_par = C
+        if world == 1 and S >= 2:   # a second scene: parity and recall-vs-CPU on 2 x C >= 8 pairs (N = 1 only: 3 s of host time)
+            _, cres0 = cpu_scene(scenes[-2])
+            cres, n_par = cres0 + cres, 2 * C
+        gres = res[-n_par:]
         t_frob = max(float(np.linalg.norm(g.T - c["T"])) for g, c in zip(gres, cres))
-        line["parity"] = {"against": "oracle/c on the last scene of the step (same inputs, same seed)", "pairs": C,
+        line["parity"] = {"against": "oracle/c on the last scene(s) of the step (same inputs, same seed)", "pairs": n_par,
                           "corr_equal": all(np.array_equal(g.corr.cpu().numpy(), c["corr"]) for g, c in zip(gres, cres)),
                           "mask_equal": all(np.array_equal(g.inlier_mask.cpu().numpy(), c["mask"]) for g, c in zip(gres, cres)),
                           "best_equal": all(g.best_hyp == c["best"] for g, c in zip(gres, cres)),
                           "T_frob": t_frob}
-        cpu_errs = [synth.pose_errors(c["T"], t) for c, t in zip(cres, truth[-C:])]
-        line["parity"]["recall_equal"] = recall_table(cpu_errs) == recall_table(errs[-C:])
+        cpu_errs = [synth.pose_errors(c["T"], t) for c, t in zip(cres, truth[-n_par:])]
+        line["parity"]["recall_equal"] = recall_table(cpu_errs) == recall_table(errs[-n_par:])
         if world == 1:
             line["cpu_baseline"] = {"value": C / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"1 full scene: map renormalised once + {C} scans x (10k x 50k x 384 search in both "
