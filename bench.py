@@ -400,7 +400,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / e2e_steps, "host_memory": "pinned",
                     "pageable": {"value": world * P * page_steps / (ms_page / 1e3), "unit": UNIT,
-                                 "note": "plain NumPy arrays: the driver stages every copy through its own pinned buffer"}},
+                                 "note": "plain NumPy arrays (what a reference user passes): staged through pinned memory by the library's copy threads (csrc/hostcopy.cu)"}},
             "distinct": distinct,
             "gpu_launches": int(launches)}
     # ---- parity against the oracle + the CPU baseline, on the LAST scene of this rank (one full scene on the host cores)

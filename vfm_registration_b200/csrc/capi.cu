@@ -596,15 +596,15 @@ static int batch_run(vfmreg_ctx* ctx, const BatchView& b, const vfmreg_register_
         if ((slot_lanes[slot] >> l) & 1u) VFM_CUDA(cudaStreamWaitEvent(cs, ev[1 + l], 0));
       slot_lanes[slot] = 0;
       char* mem = ctx->hbuf + (size_t)slot * hslot;
-      VFM_CUDA(cudaMemcpyAsync(mem, b.tgt_feats[j], (size_t)b.m[j] * d * 4, cudaMemcpyHostToDevice, cs));
-      VFM_CUDA(cudaMemcpyAsync(mem + raw_stage, b.tgt_xyz[j], (size_t)b.m[j] * 3 * 4, cudaMemcpyHostToDevice, cs));
+      VFM_TRY(h2d_copy(ctx, mem, b.tgt_feats[j], (size_t)b.m[j] * d * 4, cs));
+      VFM_TRY(h2d_copy(ctx, mem + raw_stage, b.tgt_xyz[j], (size_t)b.m[j] * 3 * 4, cs));
     }
     cudaEvent_t* sev = ctx->map_ev + stage_ev + 2 * (j % stages);
     if (j >= stages) VFM_CUDA(cudaStreamWaitEvent(cs, sev[1], 0));   // stage free again (pair j - stages is done with it)
     const Staged s = scan_ptrs(j);
-    VFM_CUDA(cudaMemcpyAsync(s.sx, b.src_xyz[j], (size_t)b.n[j] * 3 * 4, cudaMemcpyHostToDevice, cs));
-    VFM_CUDA(cudaMemcpyAsync(s.sf, b.src_feats[j], (size_t)b.n[j] * d * 4, cudaMemcpyHostToDevice, cs));
-    if (s.si) VFM_CUDA(cudaMemcpyAsync(s.si, b.sample_idx[j], (size_t)params->n_hyp * 3 * 4, cudaMemcpyHostToDevice, cs));
+    VFM_TRY(h2d_copy(ctx, s.sx, b.src_xyz[j], (size_t)b.n[j] * 3 * 4, cs));
+    VFM_TRY(h2d_copy(ctx, s.sf, b.src_feats[j], (size_t)b.n[j] * d * 4, cs));
+    if (s.si) VFM_TRY(h2d_copy(ctx, s.si, b.sample_idx[j], (size_t)params->n_hyp * 3 * 4, cs));
     VFM_CUDA(cudaEventRecord(sev[0], cs));
     return VFMREG_OK;
   };
@@ -816,6 +816,7 @@ void vfmreg_destroy(vfmreg_ctx* ctx) {
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->hbuf) cudaFree(ctx->hbuf);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  hostcopy_destroy(ctx);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -1013,12 +1014,9 @@ int vfmreg_map_create(vfmreg_ctx* ctx, const float* tgt_xyz, const float* tgt_fe
       arena_reset(ctx);
       if ((rc = arena_reserve(ctx, arena_bytes((size_t)m * d, 4))) != VFMREG_OK) break;
       float* raw = arena_take<float>(ctx, (size_t)m * d);
-      if (cudaMemcpyAsync(raw, tgt_feats, (size_t)m * d * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-          cudaMemcpyAsync(map->xyz, tgt_xyz, (size_t)m * 3 * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
-        set_error("map_create: host -> device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-        rc = VFMREG_ERR_CUDA;
+      if ((rc = h2d_copy(ctx, raw, tgt_feats, (size_t)m * d * 4, ctx->stream)) != VFMREG_OK ||
+          (rc = h2d_copy(ctx, map->xyz, tgt_xyz, (size_t)m * 3 * 4, ctx->stream)) != VFMREG_OK)
         break;
-      }
       feats_dev = raw;
     } else if (cudaMemcpyAsync(map->xyz, tgt_xyz, (size_t)m * 3 * 4, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
       set_error("map_create: device copy failed: %s", cudaGetErrorString(cudaGetLastError()));

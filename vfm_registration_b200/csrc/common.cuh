@@ -73,8 +73,13 @@ struct Prepared {
 
 }  // namespace vfm
 
+namespace vfm {
+struct HostCopy;   // hostcopy.cu: staging ring + copy threads for pageable host sources
+}
+
 struct vfmreg_ctx {
   int device = 0;
+  vfm::HostCopy* hostcopy = nullptr;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   vfm::Arena arena;
@@ -121,6 +126,10 @@ struct vfmreg_ctx {
 
 namespace vfm {
 
+// hostcopy.cu: host -> device copy of a caller-owned buffer on `stream`; pageable sources are staged through pinned memory by a
+// pool of copy threads (the source may be reused when the call returns)
+int h2d_copy(vfmreg_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream);
+void hostcopy_destroy(vfmreg_ctx* ctx);
 int arena_reserve(vfmreg_ctx* ctx, size_t bytes);  // make sure the slab holds `bytes` in total (call before carving)
 inline void arena_reset(vfmreg_ctx* ctx) { ctx->arena.off = 0; }
 template <typename T>

@@ -41,7 +41,10 @@ namespace vfm {
 
 constexpr int G_FM = 128;            // features per CTA (256 per pair)
 constexpr int G_BK = 64, G_STAGES = 6;
-constexpr int G_EPI_WARPS = 8, G_THREADS = 64 + G_EPI_WARPS * 32;
+#ifndef VFM_GEMM_EPI_WARPS
+#define VFM_GEMM_EPI_WARPS 8
+#endif
+constexpr int G_EPI_WARPS = VFM_GEMM_EPI_WARPS, G_THREADS = 64 + G_EPI_WARPS * 32;   // warps sharing a TMEM lane quarter take chunks round-robin
 constexpr uint32_t G_A_BYTES = G_FM * G_BK * 2;        // 16 KB: this CTA's 128 weight rows x 64 k
 constexpr uint32_t G_B_BYTES = 128 * G_BK * 2;         // up to 128 token rows (half of a 256-wide tile) x 64 k
 constexpr uint32_t G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
@@ -264,7 +267,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
       const int n_chunks = (g.w + 31) >> 5;
 #pragma unroll 1
-      for (int c = half; c < n_chunks; c += 2) {
+      for (int c = half; c < n_chunks; c += G_EPI_WARPS / 4) {
         uint32_t r[32];
         tc_ld32(t_addr + c * 32, r);
         tc_wait_ld();
