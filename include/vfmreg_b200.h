@@ -358,6 +358,31 @@ VFMREG_API int vfmreg_ransac_nn_all(vfmreg_ctx* ctx, const vfmreg_kdtree* tree, 
                                     const int32_t* sample_idx, int32_t n_hyp, uint64_t seed, double max_dist, double* T,
                                     int32_t* inliers, double* sum_d2, int64_t* stats);
 
+/* ---------------------------------------------------------------------------------------------
+ * SURVEY 8f row 4, second half -- the TEASER++ solve of registration_node.py:91-131 (teaserpp_python.RobustRegistrationSolver
+ * with the parameters set there: cbar2 = 1, noise_bound = 0.2, no scale estimation, PMC_EXACT inlier selection, CHAIN TIM graph,
+ * GNC-TLS rotation with factor 1.4 / 10000 iterations / cost threshold 1e-16).  TEASER++ is not in the reference tree: this is
+ * its published algorithm ("parity unpinned"): compatibility graph of the translation-invariant measurements (GPU), exact
+ * maximum clique (host branch and bound, `max_clique_nodes` search nodes at most: 0 = 20 M), GNC-TLS rotation on the clique's
+ * chain of TIMs, component-wise TLS translation by adaptive voting.
+ *   src_xyz / tgt_xyz  HOST float64 (k x 3): the correspondences' source and target points (solver.solve(src, tgt))
+ *   T                  HOST double[16], row-major 4 x 4 (identity when k < 2 or the clique has fewer than 2 vertices)
+ *   clique             HOST int32[k] (optional): the clique's correspondence indices, ascending
+ *   stats              HOST int32[5] (optional): clique size, 1 if the clique search finished (exact), GNC iterations,
+ *                      rotation inliers (TIMs with weight >= 0.5), translation inliers (minimum over the three axes)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  double noise_bound;       /* solver_params.noise_bound (0.2: "should be similar to the voxel size") */
+  double cbar2;             /* solver_params.cbar2 (1.0) */
+  double gnc_factor;        /* rotation_gnc_factor (1.4) */
+  double cost_threshold;    /* rotation_cost_threshold (1e-16) */
+  int32_t max_iterations;   /* rotation_max_iterations (10000) */
+  int32_t reserved;
+  int64_t max_clique_nodes; /* 0 = default */
+} vfmreg_teaser_params;
+VFMREG_API int vfmreg_teaser_solve(vfmreg_ctx* ctx, const double* src_xyz, const double* tgt_xyz, int64_t k, const vfmreg_teaser_params* p,
+                                   double* T, int32_t* clique, int32_t* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -584,3 +584,66 @@ def test_compat_node_default_score_is_open3d_style(vfm):
     pose2, icp = node2.ransac_registration(vmap_arr, scan_arr, "vfm", run_icp=True)
     rte2, rre2 = synth.pose_errors(icp, s["T_gt"])
     assert pose2.shape == (4, 4) and rte2 < 0.2 and rre2 < 0.5
+
+
+# ---- SURVEY 8f row 4, second half: the TEASER++-style solve (csrc/teaser.cu) against oracle/teaser.py ---------------------
+def _teaser_problem(seed, n_in, n_out, noise=0.02):
+    rng = np.random.default_rng(seed)
+    from scipy.spatial.transform import Rotation as R
+    rot = R.from_euler("zyx", rng.uniform(-180, 180, 3) * [1, 0.05, 0.05], degrees=True).as_matrix()
+    t = rng.normal(0, 10, 3)
+    src = rng.uniform(-40, 40, (n_in + n_out, 3))
+    tgt = src @ rot.T + t + rng.normal(0, noise, (n_in + n_out, 3))
+    tgt[n_in:] = rng.uniform(-40, 40, (n_out, 3))
+    perm = rng.permutation(n_in + n_out)
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = rot, t
+    return src[perm], tgt[perm], T
+
+
+@pytest.mark.parametrize("seed,n_in,n_out", [(1, 40, 110), (2, 25, 175), (3, 120, 60)])
+def test_teaser_solve_vs_oracle(vfm, seed, n_in, n_out):
+    """Compatibility graph (GPU), exact maximum clique, GNC-TLS rotation and TLS translation against the NumPy restatement
+    (an unrelated clique algorithm and np.linalg.svd): same clique, pose within 1e-9 (float64, different summation order)."""
+    from oracle import teaser as ot
+    src, tgt, T_gt = _teaser_problem(seed, n_in, n_out)
+    r = vfm.teaser_solve(src, tgt)
+    T_o, cl_o = ot.teaser_solve(src, tgt)
+    assert r.exact and len(r.clique) == len(cl_o)
+    if not np.array_equal(r.clique, cl_o):            # maximum cliques of equal size: solve the oracle on the product's clique
+        T_o, _ = ot.teaser_solve(src, tgt, clique=r.clique)
+    assert np.abs(r.T - T_o).max() < 1e-9, float(np.abs(r.T - T_o).max())
+    assert np.linalg.norm(r.T[:3, 3] - T_gt[:3, 3]) < 0.05
+    assert np.degrees(np.arccos(np.clip((np.trace(r.T[:3, :3].T @ T_gt[:3, :3]) - 1) / 2, -1, 1))) < 0.2
+    # the graph itself, through the clique: every pair of clique members is compatible in the oracle's graph
+    g = ot.tim_graph(src, tgt, 0.2)
+    assert g[np.ix_(r.clique, r.clique)].sum() == len(r.clique) * (len(r.clique) - 1)
+
+
+def test_teaser_solve_edge_cases_and_size(vfm):
+    r = vfm.teaser_solve(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert np.array_equal(r.T, np.eye(4)) and len(r.clique) == 0
+    r = vfm.teaser_solve(np.ones((1, 3)), np.ones((1, 3)))
+    assert np.array_equal(r.T, np.eye(4))
+    with pytest.raises(ValueError, match="Invalid shape"):
+        vfm.teaser_solve(np.zeros((4, 3)), np.zeros((5, 3)))
+    # the size the reference feeds it (a few thousand correspondences of the 1 m-voxelised scan), 60 % outliers
+    src, tgt, T_gt = _teaser_problem(7, 1200, 1800)
+    r = vfm.teaser_solve(src, tgt)
+    assert r.exact and 1200 <= len(r.clique) <= 1210
+    assert np.linalg.norm(r.T[:3, 3] - T_gt[:3, 3]) < 0.02
+
+
+def test_compat_teaser_registration(vfm):
+    """compat.RegistrationNode.teaser_registration (registration_node.py:91-160) on a synthetic descriptor-carrying pair."""
+    from vfm_registration_b200 import compat, synth
+    s = synth.make_pair(5, 6000, 3000, 64, inlier_frac=0.5)
+    node = compat.RegistrationNode(preprocess=False)
+    vmap = np.c_[s["map_xyz"], s["map_feat"]]
+    scan = np.c_[s["scan_xyz"], s["scan_feat"]]
+    pose, icp = node.teaser_registration(vmap, scan, "vfm")
+    assert icp is None
+    rte, rre = synth.pose_errors(pose, s["T_gt"])
+    assert rte < 0.2 and rre < 0.5, (rte, rre)
+    with pytest.raises(ValueError, match="Invalid method"):
+        node.teaser_registration(vmap, scan, "fpfh")

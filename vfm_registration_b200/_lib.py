@@ -43,8 +43,14 @@ class VitConfig(C.Structure):
                 ("mean", C.c_float * 3), ("std", C.c_float * 3)]
 
 
+class TeaserParams(C.Structure):
+    _fields_ = [("noise_bound", C.c_double), ("cbar2", C.c_double), ("gnc_factor", C.c_double), ("cost_threshold", C.c_double),
+                ("max_iterations", C.c_int32), ("reserved", C.c_int32), ("max_clique_nodes", C.c_int64)]
+
+
 _P = C.c_void_p
 _SIGS = {
+    "vfmreg_teaser_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(TeaserParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "vfmreg_version": (C.c_int, []),
     "vfmreg_last_error": (C.c_char_p, []),
     "vfmreg_device_count": (C.c_int, []),

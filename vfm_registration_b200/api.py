@@ -644,6 +644,41 @@ def register_scans(resident: ResidentMap, scans, *, min_cos: Optional[float] = 0
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# 8f row 4: the TEASER++-style solve of registration_node.py:91-131
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class TeaserResult:
+    T: np.ndarray              # (4, 4) float64
+    clique: np.ndarray         # correspondence indices of the maximum clique, ascending
+    exact: bool                # the clique search ran to completion
+    iterations: int            # GNC-TLS iterations
+    rotation_inliers: int
+    translation_inliers: int
+
+
+def teaser_solve(src_xyz, tgt_xyz, *, noise_bound: float = 0.2, cbar2: float = 1.0, gnc_factor: float = 1.4,
+                 max_iterations: int = 10000, cost_threshold: float = 1e-16, max_clique_nodes: int = 0, device=None) -> TeaserResult:
+    """``teaserpp_python.RobustRegistrationSolver(params).solve(src, tgt)`` with the reference's parameters
+    (registration_node.py:109-121): src_xyz / tgt_xyz are the (K, 3) points of K putative correspondences.  Compatibility
+    graph on the GPU, exact maximum clique, GNC-TLS rotation, TLS translation (csrc/teaser.cu; "parity unpinned")."""
+    ctx = get_context(device)
+    s = np.ascontiguousarray(np.asarray(src_xyz.detach().cpu() if isinstance(src_xyz, torch.Tensor) else src_xyz, dtype=np.float64))
+    t = np.ascontiguousarray(np.asarray(tgt_xyz.detach().cpu() if isinstance(tgt_xyz, torch.Tensor) else tgt_xyz, dtype=np.float64))
+    if s.ndim != 2 or s.shape[1] != 3 or s.shape != t.shape:
+        raise ValueError(f"Invalid shape: {s.shape} / {t.shape} (two (K, 3) arrays expected)")
+    k = s.shape[0]
+    p = _lib.TeaserParams(float(noise_bound), float(cbar2), float(gnc_factor), float(cost_threshold), int(max_iterations), 0, int(max_clique_nodes))
+    T = np.zeros(16, dtype=np.float64)
+    clique = np.zeros(max(k, 1), dtype=np.int32)
+    stats = np.zeros(5, dtype=np.int32)
+    ctx.bind_stream()
+    _lib.check(ctx.lib.vfmreg_teaser_solve(ctx.handle, s.ctypes.data, t.ctypes.data, k, C.byref(p), T.ctypes.data, clique.ctypes.data,
+                                          stats.ctypes.data), "vfmreg_teaser_solve")
+    return TeaserResult(T=T.reshape(4, 4), clique=clique[:stats[0]].astype(np.int64), exact=bool(stats[1]), iterations=int(stats[2]),
+                        rotation_inliers=int(stats[3]), translation_inliers=int(stats[4]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # a3/a4/a5: projection + feature gather
 # ---------------------------------------------------------------------------------------------------------------------
 @dataclass

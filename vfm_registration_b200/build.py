@@ -22,7 +22,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
           "-Xptxas", "-v"]
 # per-file extra flags; ransac.cu spells every fused multiply-add explicitly (bit parity with the C oracle)
-EXTRA = {"ransac.cu": ["-fmad=false"], "project.cu": ["-fmad=false"], "voxel.cu": ["-fmad=false"], "nnscore.cu": ["-fmad=false"]}
+EXTRA = {"ransac.cu": ["-fmad=false"], "project.cu": ["-fmad=false"], "voxel.cu": ["-fmad=false"], "nnscore.cu": ["-fmad=false"], "teaser.cu": ["-fmad=false"]}
 # tuning knobs: VFM_NVCC_DEFS="-DVFM_TBN=128 -DVFM_EPI_WARPS=4" python -m vfm_registration_b200.build --force
 EXTRA_ALL = os.environ.get("VFM_NVCC_DEFS", "").split()
 

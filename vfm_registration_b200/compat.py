@@ -211,6 +211,28 @@ class RegistrationNode:
             corr = vmap.get_vfm_correspondences(voxel_down_sample(pcl, 1.0), self.min_cosine)
         return corr
 
+    def teaser_registration(self, voxel_map: np.ndarray, raw_scan: np.ndarray, method: str, run_icp: bool = False):
+        """registration_node.py:91-160 for method='vfm': descriptor correspondences (compute_vfm_correspondences) -> the
+        TEASER++ solve with the reference's solver parameters (noise bound 0.2, PMC_EXACT, CHAIN, GNC-TLS) -> optionally the
+        same ICP refinement as ransac_registration.  Returns (teaser_pose, icp_pose | None)."""
+        if method != "vfm":
+            raise ValueError(f"Invalid method: {method}")   # :108-109 ('fpfh' needs Open3D's FPFH features: not on this path)
+        voxel_map, raw_scan = np.asarray(voxel_map), np.asarray(raw_scan)
+        if voxel_map.ndim != 2 or raw_scan.ndim != 2 or voxel_map.shape[1] != raw_scan.shape[1] or raw_scan.shape[1] <= 3:
+            raise ValueError("Invalid shape")
+        src, tgt = self.compute_vfm_correspondences(voxel_map, raw_scan)
+        teaser_pose = api.teaser_solve(src, tgt, noise_bound=0.2, cbar2=1.0, gnc_factor=1.4, max_iterations=10000, cost_threshold=1e-16,
+                                       device=self.device).T
+        if not run_icp:
+            return teaser_pose, None
+        teaser_pose = teaser_pose.copy()
+        teaser_pose[:3, :3] = metrics.orthogonalize_rotation(teaser_pose[:3, :3])   # :143-148
+        icp_map = self._new_map()
+        icp_map.add_points(np.ascontiguousarray(voxel_map[:, :3]))
+        scan_xyz = self._voxel_scan(raw_scan[:, :3]) if self.preprocess else raw_scan[:, :3]
+        sigma = self.initial_threshold
+        return teaser_pose, register_frame(scan_xyz, icp_map, teaser_pose, 3 * sigma, sigma / 3)   # :150-156
+
     def ransac_registration(self, voxel_map: np.ndarray, raw_scan: np.ndarray, method: str, run_icp: bool = False):
         """registration_node.py:273-357 for method='vfm': correspondences -> RANSAC (-> ICP refinement).  The reference
         recovers correspondence indices in the voxelised clouds with KD-trees (:289-309); here the voxel operations

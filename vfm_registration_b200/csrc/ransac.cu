@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t sample_u32(uint64_t seed, uint64_t ctr, uint
 // Rigid fit from the 3x3 cross-covariance S (row-major): see oracle_ref.c:orc_fit_from_sigma for the canonical
 // order.  M = S^T S, cyclic Jacobi (6 sweeps), u_i = S v_i / sigma_i, one Gram-Schmidt step, third pair by cross
 // products (= U diag(1,1,det U det V) V^T).  Returns false for rank-deficient samples.
-__device__ bool fit_from_sigma(const double* S, const double* pm, const double* qm, double* rt) {
+__host__ __device__ bool fit_from_sigma(const double* S, const double* pm, const double* qm, double* rt) {
   double a[3][3], v[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -126,6 +126,9 @@ __device__ bool fit_from_sigma(const double* S, const double* pm, const double* 
     rt[9 + i] = qm[i] - ((rt[i * 3 + 0] * pm[0] + rt[i * 3 + 1] * pm[1]) + rt[i * 3 + 2] * pm[2]);
   return true;
 }
+
+// the same routine for host callers (teaser.cu: weighted Kabsch of the GNC-TLS rotation loop)
+bool host_fit_from_sigma(const double* S, const double* pm, const double* qm, double* rt) { return fit_from_sigma(S, pm, qm, rt); }
 
 __device__ __forceinline__ double resid2(const double* rt, double px, double py, double pz, double qx, double qy,
                                          double qz) {
