@@ -116,6 +116,7 @@ struct vfmreg_ctx {
   int match_ev_head = 0;
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per context, not per process
   bool tc_attr_set = false;
+  int gemm_clusters = 0;           // resident clusters of vit_gemm_kernel on this device (0 = not asked yet)
   uint64_t gemm_attr_mask = 0;     // vit_gemm_kernel<EPI, BN> instantiations already opted in
   size_t attention_tc_smem_attr = 0;   // same for attention_tc_kernel
   size_t attention_smem_attr = 0;  // largest dynamic shared memory size attention_kernel was opted in for

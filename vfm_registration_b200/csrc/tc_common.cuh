@@ -230,6 +230,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
       "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same load multicast to the CTAs of `cta_mask` (same CTA-relative destination offset in each; every destination CTA's
+// bytes are credited to the barrier at this offset in ITS pair's leader when `cluster_bar` points at the issuer's pair leader)
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"

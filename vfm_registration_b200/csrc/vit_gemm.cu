@@ -39,6 +39,13 @@
 
 namespace vfm {
 
+#ifndef VFM_GEMM_CLUSTER
+#define VFM_GEMM_CLUSTER 2
+#endif
+// CTAs per cluster: 2 = one CTA pair; 4 = two pairs on adjacent 256-feature blocks that SHARE the token tile (pair 0 loads it
+// and multicasts each half to the matching CTA of pair 1: the operand traffic per pair drops from 64 to 48 KB per 64-wide K step)
+constexpr int G_CL = VFM_GEMM_CLUSTER;
+static_assert(G_CL == 2 || G_CL == 4, "cluster of one or two CTA pairs");
 constexpr int G_FM = 128;            // features per CTA (256 per pair)
 constexpr int G_BK = 64, G_STAGES = 6;
 #ifndef VFM_GEMM_EPI_WARPS
@@ -132,7 +139,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
 }
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
+__global__ void __cluster_dims__(G_CL, 1, 1) __launch_bounds__(G_THREADS, 1)
     vit_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                     const __grid_constant__ CUtensorMap map_x_tail, const GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -143,8 +150,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
   const uint32_t full0 = bars, empty0 = bars + 8 * G_STAGES, tfull0 = bars + 16 * G_STAGES, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + G_SMEM_BARS + 16 * G_STAGES + 32);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_cta_rank();
-  const int clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const uint32_t crank = cluster_cta_rank();
+  const uint32_t rank = crank & 1u, pair = crank >> 1, lead = crank & ~1u;   // rank inside the CTA pair, pair inside the cluster, the pair's leader
+  const int clusters = gridDim.x / G_CL, cid = blockIdx.x / G_CL;
   const int total = ep.fb_count * (ep.n_full + (ep.tail_w > 0 ? 1 : 0)) * ep.split;   // units of (tile, K split)
 
   TraceScope trace(EPI);
@@ -155,7 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     if (ep.tail_w > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x_tail) : "memory");
     for (int s = 0; s < G_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);    // leader: one arrive.expect_tx per phase, bytes from both CTAs' loads
-      mbar_init(empty0 + 8 * s, 1);   // both CTAs: multicast commit from the leader's MMA warp
+      mbar_init(empty0 + 8 * s, G_CL / 2);   // every CTA: multicast commit from the MMA warp of each pair's leader
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);                  // both CTAs: multicast commit
@@ -181,10 +189,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
       const GemmTile g0 = gemm_tile(ep, cid);
       pre = min(G_STAGES, g0.kb1 - g0.kb0);
       if (elect_one()) {
-        const int w_row = g0.fb * 2 * G_FM + (int)rank * G_FM;
+        const int w_row = ((G_CL / 2) * g0.fb + (int)pair) * 2 * G_FM + (int)rank * G_FM;
         const uint32_t b_bytes = (uint32_t)(g0.w / 2) * (G_BK * 2);
         for (int s = 0; s < pre; ++s) {
-          const uint32_t full_leader = mapa_cluster(full0 + 8 * s, 0);
+          const uint32_t full_leader = mapa_cluster(full0 + 8 * s, lead);
           if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2u * (G_A_BYTES + b_bytes));
           tma_load_2d_2sm(base + s * G_STAGE_BYTES, &map_w, full_leader, (g0.kb0 + s) * G_BK, w_row);
         }
@@ -196,7 +204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     trace.waited();
     for (int t = cid; t < total; t += clusters) {
       const GemmTile g = gemm_tile(ep, t);
-      const int w_row = g.fb * 2 * G_FM + (int)rank * G_FM;
+      const int w_row = ((G_CL / 2) * g.fb + (int)pair) * 2 * G_FM + (int)rank * G_FM;
       const int x_row = g.tok0 + (int)rank * (g.w / 2);
       const bool tail = g.w != ep.nt;   // the tail tile has its own token map: a box of tail_w / 2 rows
       const CUtensorMap* mx = tail ? &map_x_tail : &map_x;
@@ -206,12 +214,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
         const bool early = t == cid && kb - g.kb0 < pre;   // barrier armed and weights already on their way
         if (!early) mbar_wait(empty0 + 8 * stage, phase ^ 1);
         if (elect_one()) {
-          const uint32_t full_leader = mapa_cluster(full0 + 8 * stage, 0);
+          const uint32_t full_leader = mapa_cluster(full0 + 8 * stage, lead);
           if (!early) {
             if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2u * (G_A_BYTES + b_bytes));
             tma_load_2d_2sm(base + stage * G_STAGE_BYTES, &map_w, full_leader, kb * G_BK, w_row);
           }
-          tma_load_2d_2sm(base + stage * G_STAGE_BYTES + G_A_BYTES, mx, full_leader, kb * G_BK, x_row);
+          if (G_CL == 2)
+            tma_load_2d_2sm(base + stage * G_STAGE_BYTES + G_A_BYTES, mx, full_leader, kb * G_BK, x_row);
+          else if (pair == 0)   // this half of the token tile also goes to the CTA of the same rank in the other pair
+            tma_load_2d_2sm_mc(base + stage * G_STAGE_BYTES + G_A_BYTES, mx, full_leader, kb * G_BK, x_row, (uint16_t)(0x5u << rank));
         }
         __syncwarp();
         if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
@@ -220,7 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
   } else if (warp == 1) {
     // ===== MMA issuer: the leader CTA only =====
     pdl_wait();
-    if (rank == 0) {
+    if (rank == 0) {   // the leader of each pair
       uint32_t stage = 0, phase = 0;
       int it = 0;
       const uint64_t da0 = umma_desc_k_sw128(base), db0 = umma_desc_k_sw128(base + G_A_BYTES);
@@ -241,8 +252,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
 #pragma unroll
             for (int k = 0; k < G_BK / 16; ++k)
               tc_mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb != g.kb0 || k != 0) ? 1u : 0u);
-            tc_commit_2sm(empty0 + 8 * stage, (uint16_t)3);   // stage free in both CTAs once these MMAs have read it
-            if (kb == g.kb1 - 1) tc_commit_2sm(tfull0 + 8 * buf, (uint16_t)3);   // accumulator halves complete
+            tc_commit_2sm(empty0 + 8 * stage, (uint16_t)((1u << G_CL) - 1));   // stage free, in every CTA of the cluster, once these MMAs have read it
+            if (kb == g.kb1 - 1) tc_commit_2sm(tfull0 + 8 * buf, (uint16_t)(3u << (2 * pair)));   // accumulator halves complete
           }
           __syncwarp();
           if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
@@ -254,10 +265,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     pdl_wait();   // the epilogue writes what the previous kernels may still be reading
     const int q = warp & 3, half = (warp - 2) >> 2;
     int it = 0;
-    const uint32_t tempty_leader0 = mapa_cluster(tempty0, 0);
+    const uint32_t tempty_leader0 = mapa_cluster(tempty0, lead);
     for (int t = cid; t < total; t += clusters, ++it) {
       const GemmTile g = gemm_tile(ep, t);
-      const int f = g.fb * 2 * G_FM + (int)rank * G_FM + q * 32 + lane;
+      const int f = ((G_CL / 2) * g.fb + (int)pair) * 2 * G_FM + (int)rank * G_FM + q * 32 + lane;
       const bool f_live = f < ep.n;
       float bias = 0.f;
       if (EPI != EPI_F32_PARTIAL && f_live) bias = __ldg(ep.bias + f);
@@ -303,16 +314,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
 // through the L2 (the chip-wide L2 -> SM rate, ~6300 B/clk, is what bounds 256 x 256 x 64 bf16 tiles: 64 KB per 512 MMA
 // cycles per pair = 64 B/clk per SM against ~42 B/clk per SM when all 148 SMs stream).
 static long long gemm_cost(int m, int n, int k, int nt, int split, int clusters, GemmPlan* plan) {
-  const int fb_count = ceil_div(n, 2 * G_FM);
+  const int fb_count = ceil_div(n, G_CL * G_FM);   // feature blocks of the cluster: 256 per CTA pair
   const int n_full = m / nt;
   const int rest = m - n_full * nt;
   const int tail = (rest + 15) / 16 * 16;
   const int kbs = k / G_BK;
   auto unit_cost = [&](int w, int s, long long* bytes) {
     const int kb = (kbs * (s + 1)) / split - (kbs * s) / split;
-    const long long b = (long long)kb * 2 * (G_A_BYTES + (long long)(w / 2) * (G_BK * 2));
+    const long long b = (long long)kb * (G_CL * G_A_BYTES + 2 * (long long)(w / 2) * (G_BK * 2));   // the token tile is loaded once per cluster
     *bytes = b;
-    const long long mma = (long long)kb * 4 * (w / 2), ingest = b / 100;
+    const long long mma = (long long)kb * 4 * (w / 2), ingest = b / (50 * G_CL);
     return (mma > ingest ? mma : ingest) + 600 + (long long)(w / 64 + 1) * 250;
   };
   const int tiles_full = fb_count * n_full, tiles = tiles_full + (tail ? fb_count : 0);
@@ -340,6 +351,8 @@ static long long gemm_cost(int m, int n, int k, int nt, int split, int clusters,
   return worst > l2 ? worst : l2;
 }
 
+static int gemm_clusters(vfmreg_ctx* ctx);
+
 // VFMREG_VIT_PLAN="qkv:256:1,proj:256:3,fc1:192:1,fc2:256:3,pe:128:1" overrides (tile width : K splits) per GEMM of the forward --
 // a tuning aid for tools/bench_kernels.py; unset = the cost model above
 static bool plan_override(const char* which, int* nt, int* split) {
@@ -351,7 +364,7 @@ static bool plan_override(const char* which, int* nt, int* split) {
 }
 
 GemmPlan vit_gemm_plan(vfmreg_ctx* ctx, int m, int n, int k, int max_split, const char* which) {
-  const int clusters = ctx->sm_count / 2;
+  const int clusters = gemm_clusters(ctx);
   GemmPlan best{};
   long long best_cost = -1;
   int fnt = 0, fsplit = 0;
@@ -369,6 +382,25 @@ GemmPlan vit_gemm_plan(vfmreg_ctx* ctx, int m, int n, int k, int max_split, cons
       }
     }
   return best;
+}
+
+// clusters of G_CL CTAs (one per SM, ~200 KB of shared memory each) that can be resident at once: GPC boundaries make this
+// smaller than sm_count / G_CL (a cluster cannot straddle two GPCs); asked once per context
+static int gemm_clusters(vfmreg_ctx* ctx) {
+  if (ctx->gemm_clusters > 0) return ctx->gemm_clusters;
+  int n = ctx->sm_count / G_CL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(G_CL * n);
+  cfg.blockDim = dim3(G_THREADS);
+  cfg.dynamicSmemBytes = G_SMEM_TOTAL;
+  if (cudaFuncSetAttribute(vit_gemm_kernel<EPI_BF16_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_TOTAL) == cudaSuccess) {
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, vit_gemm_kernel<EPI_BF16_BIAS>, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+  }
+  cudaGetLastError();
+  if (getenv("VFMREG_VIT_VERBOSE")) fprintf(stderr, "vit_gemm: %d clusters of %d CTAs resident\n", n, G_CL);
+  ctx->gemm_clusters = n;
+  return n;
 }
 
 template <int EPI>
@@ -396,13 +428,13 @@ int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& w, const TokenMaps& x,
   VFM_CHECK_ARG(ep.k % G_BK == 0 && ep.m > 0 && ep.n % 128 == 0 && plan.nt >= 32 && plan.nt <= 256 && plan.nt % 32 == 0 &&
                     plan.split >= 1 && (plan.split == 1 || epi == EPI_F32_PARTIAL),
                 "vit_gemm: unsupported shape m=%d n=%d k=%d nt=%d split=%d", ep.m, ep.n, ep.k, plan.nt, plan.split);
-  const int clusters = ctx->sm_count / 2;
+  const int clusters = gemm_clusters(ctx);
   ep.nt = plan.nt;
   ep.split = plan.split;
   ep.fb_count = plan.fb_count;
   ep.n_full = plan.n_full;
   ep.tail_w = plan.tail_w;
-  const int grid = 2 * (plan.units < clusters ? plan.units : clusters);
+  const int grid = G_CL * (plan.units < clusters ? plan.units : clusters);
   switch (epi) {
     case EPI_BF16_BIAS: return launch_gemm<EPI_BF16_BIAS>(ctx, w, x.full, x.tail, ep, grid);
     case EPI_BF16_BIAS_GELU: return launch_gemm<EPI_BF16_BIAS_GELU>(ctx, w, x.full, x.tail, ep, grid);
