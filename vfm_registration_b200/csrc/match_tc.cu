@@ -43,25 +43,31 @@
 
 namespace vfm {
 
-#ifndef VFM_EPI_WARPS
-#define VFM_EPI_WARPS 4
-#endif
 constexpr int TBM = 128, TBN = 256, TBK = 64, UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int NBUF = 512 / TBN;          // accumulator buffers in TMEM
 constexpr int CAP = 16;                 // candidate list entries per (row, slot)
 constexpr float MARGIN = 3e-3f;
-// Epilogue warps: 4 (one per TMEM lane quarter) or 8 (warps w and w+4 share a lane quarter -- the hardware ties lanes
-// to warp_id % 4 -- and split the tile's columns; each (row, column group) then keeps its own candidate list, i.e.
-// HALVES device slots per (row, CTA span)).
-constexpr int EPI_WARPS = VFM_EPI_WARPS, EPI_THREADS = EPI_WARPS * 32;
-constexpr int HALVES = EPI_WARPS / 4;     // column groups per tile (warps sharing a TMEM lane quarter split the columns)
-constexpr int COLS_PER_WARP = TBN / HALVES;
-constexpr int TC_THREADS = 64 + EPI_THREADS;
+// Epilogue warps, a template parameter EW of the kernels: 4 (one per TMEM lane quarter) or 8 (warps w and w+4 share a lane
+// quarter -- the hardware ties lanes to warp_id % 4 -- and split the tile's columns; each (row, column group) then keeps its own
+// candidate list, i.e. HALVES device slots per (row, CTA span)).  Measured (tools/bench_kernels.py modes, 10k x 50k x 384): 8
+// warps take top-2 mode from 0.322 to 0.302 ms (0.73 -> 0.78 of the measured bf16 peak); in top-1 mode with the gate floor
+// the two are equal, and inside a batch the 4 extra warps take issue slots from the neighbouring lanes' small kernels
+// (-3 % pairs/s).  So: top-2 searches run EW = 8, top-1 searches EW = 4.
+template <int EW>
+struct Epi {
+  static constexpr int WARPS = EW, THREADS = EW * 32;
+  static constexpr int HALVES = EW / 4;            // column groups per tile
+  static constexpr int COLS = TBN / HALVES;        // columns per warp
+  static constexpr int TC_THREADS = 64 + THREADS;
+  static constexpr uint32_t RING_BYTES = THREADS * CAP * 4;
+};
 constexpr uint32_t A_STAGE_BYTES = TBM * TBK * 2, B_STAGE_BYTES = TBN * TBK * 2;
+// the single-CTA kernel (fewer than two row blocks) always runs 4 epilogue warps
+constexpr int EW1 = 4;
 constexpr uint32_t SMEM_RING_V = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-constexpr uint32_t SMEM_RING_I = SMEM_RING_V + EPI_THREADS * CAP * 4;
-constexpr uint32_t SMEM_BARS = SMEM_RING_I + EPI_THREADS * CAP * 4;
+constexpr uint32_t SMEM_RING_I = SMEM_RING_V + Epi<EW1>::RING_BYTES;
+constexpr uint32_t SMEM_BARS = SMEM_RING_I + Epi<EW1>::RING_BYTES;
 constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 256 + 1024;  // + slack for 1024-byte alignment
 
 constexpr uint32_t IDESC = umma_idesc_f16(TBM, TBN, 0);  // fp16 operands
@@ -110,6 +116,7 @@ __device__ __forceinline__ void epi_row_begin(const TcParams& P, EpiRow& s, int 
 }
 
 // slot of (row block, span): spans are numbered from the first CTA (cluster) whose span contains the row block's first unit
+template <int EW>
 __device__ __forceinline__ void flush_slot(const TcParams& P, int n_rows, int row, long long first_unit, long long total_units,
                                            long long n_workers, long long worker, int half, int etid, const float* ring_v,
                                            const int* ring_i, const EpiRow& s) {
@@ -118,36 +125,36 @@ __device__ __forceinline__ void flush_slot(const TcParams& P, int n_rows, int ro
   long long c0 = (first_unit * g) / total_units;
   while ((total_units * (c0 + 1)) / g <= first_unit) ++c0;
   while (c0 > 0 && (total_units * c0) / g > first_unit) --c0;
-  const int slot = (int)(worker - c0) * HALVES + half;
+  const int slot = (int)(worker - c0) * Epi<EW>::HALVES + half;
   const long long o = ((long long)row * P.slots + slot);
   P.cand_n[o] = s.cnt | (s.lost > -INFINITY ? (1 << 30) : 0);
   P.slot_top2[o] = make_float4(s.best, s.second, s.lost, 0.0f);
   for (int e = 0; e < s.cnt; ++e) {
-    P.cand_v[o * CAP + e] = ring_v[e * EPI_THREADS + etid];
-    P.cand_i[o * CAP + e] = ring_i[e * EPI_THREADS + etid];
+    P.cand_v[o * CAP + e] = ring_v[e * Epi<EW>::THREADS + etid];
+    P.cand_i[o * CAP + e] = ring_i[e * Epi<EW>::THREADS + etid];
   }
 }
 
 // Record one candidate (approximate score v of column `col`) in the thread's list and raise the recording threshold.
-template <bool TOP1>
+template <bool TOP1, int EW>
 __device__ __forceinline__ void push_candidate(float v, int col, int etid, float* ring_v, int* ring_i, EpiRow& s) {
   if (s.cnt == CAP) {  // compact: keep what is still above the (risen) threshold
     int w = 0;
 #pragma unroll 1
     for (int e = 0; e < CAP; ++e) {
-      const float ev = ring_v[e * EPI_THREADS + etid];
-      const int ei = ring_i[e * EPI_THREADS + etid];
+      const float ev = ring_v[e * Epi<EW>::THREADS + etid];
+      const int ei = ring_i[e * Epi<EW>::THREADS + etid];
       if (ev > s.thr) {
-        ring_v[w * EPI_THREADS + etid] = ev;
-        ring_i[w * EPI_THREADS + etid] = ei;
+        ring_v[w * Epi<EW>::THREADS + etid] = ev;
+        ring_i[w * Epi<EW>::THREADS + etid] = ei;
         ++w;
       }
     }
     s.cnt = w;
   }
   if (s.cnt < CAP) {
-    ring_v[s.cnt * EPI_THREADS + etid] = v;
-    ring_i[s.cnt * EPI_THREADS + etid] = col;
+    ring_v[s.cnt * Epi<EW>::THREADS + etid] = v;
+    ring_i[s.cnt * Epi<EW>::THREADS + etid] = col;
     ++s.cnt;
   } else {
     // CAP entries within the margin of the threshold and one more: keep the CAP largest and remember the largest score
@@ -156,15 +163,15 @@ __device__ __forceinline__ void push_candidate(float v, int col, int etid, float
     float lo_v = ring_v[etid];
 #pragma unroll 1
     for (int e = 1; e < CAP; ++e) {
-      const float ev = ring_v[e * EPI_THREADS + etid];
+      const float ev = ring_v[e * Epi<EW>::THREADS + etid];
       if (ev < lo_v) {
         lo_v = ev;
         lo = e;
       }
     }
     if (v > lo_v) {
-      ring_v[lo * EPI_THREADS + etid] = v;
-      ring_i[lo * EPI_THREADS + etid] = col;
+      ring_v[lo * Epi<EW>::THREADS + etid] = v;
+      ring_i[lo * Epi<EW>::THREADS + etid] = col;
       s.lost = fmaxf(s.lost, lo_v);
     } else {
       s.lost = fmaxf(s.lost, v);
@@ -198,7 +205,7 @@ __device__ __forceinline__ float pick32(const uint32_t* r, int i) {
 // warp vote.  Only when some lane clears its threshold does the warp build the per-lane bit mask of qualifying columns
 // (straight-line code, no divergence); lanes with a hit then push -- the usual case, exactly one column, is a single push of
 // (chunk maximum, position); several qualifying columns are pushed in ascending column order through a select tree.
-template <bool TOP1>
+template <bool TOP1, int EW>
 __device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid, int col_base, int etid, float* ring_v, int* ring_i,
                                            EpiRow& s) {
   if (c0 >= valid) return;  // warp-uniform
@@ -226,49 +233,50 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* r, int c0, int valid,
   if (mask == 0) return;   // lanes without a hit wait at the reconvergence point
   if (!partial && (mask & (mask - 1)) == 0) {
     // exactly one qualifying column: it is the chunk maximum
-    push_candidate<TOP1>(mx, col_base + c0 + __ffs(mask) - 1, etid, ring_v, ring_i, s);
+    push_candidate<TOP1, EW>(mx, col_base + c0 + __ffs(mask) - 1, etid, ring_v, ring_i, s);
   } else {
 #pragma unroll 1
     while (mask) {
       const int i = __ffs(mask) - 1;
       mask &= mask - 1;
       const float v = pick32(r, i);
-      if (v > s.thr) push_candidate<TOP1>(v, col_base + c0 + i, etid, ring_v, ring_i, s);
+      if (v > s.thr) push_candidate<TOP1, EW>(v, col_base + c0 + i, etid, ring_v, ring_i, s);
     }
   }
 }
 
-// The epilogue of one warp's share of an accumulator tile (COLS_PER_WARP columns starting at TMEM address t_addr /
+// The epilogue of one warp's share of an accumulator tile (Epi<EW>::COLS columns starting at TMEM address t_addr /
 // database column col_base): 32-column chunks, the next one in flight while the current one is scanned.
-template <bool TOP1>
+template <bool TOP1, int EW>
 __device__ __forceinline__ void epilogue_half(uint32_t t_addr, int col_base, int m, int etid, float* ring_v, int* ring_i, EpiRow& s) {
-  const int valid = min(COLS_PER_WARP, m - col_base);   // may be <= 0 for the padded part of the last tile
+  const int valid = min(Epi<EW>::COLS, m - col_base);   // may be <= 0 for the padded part of the last tile
   uint32_t ra[32], rbuf[32];
   tc_ld32(t_addr, ra);
 #pragma unroll 1
-  for (int c = 0; c < COLS_PER_WARP / 32; c += 2) {
+  for (int c = 0; c < Epi<EW>::COLS / 32; c += 2) {
     tc_wait_ld();
     tc_ld32(t_addr + (c + 1) * 32, rbuf);  // in flight while chunk c is scanned
-    scan_chunk<TOP1>(ra, c * 32, valid, col_base, etid, ring_v, ring_i, s);
+    scan_chunk<TOP1, EW>(ra, c * 32, valid, col_base, etid, ring_v, ring_i, s);
     __syncwarp();
     tc_wait_ld();
-    if (c + 2 < COLS_PER_WARP / 32) tc_ld32(t_addr + (c + 2) * 32, ra);
-    scan_chunk<TOP1>(rbuf, (c + 1) * 32, valid, col_base, etid, ring_v, ring_i, s);
+    if (c + 2 < Epi<EW>::COLS / 32) tc_ld32(t_addr + (c + 2) * 32, ra);
+    scan_chunk<TOP1, EW>(rbuf, (c + 1) * 32, valid, col_base, etid, ring_v, ring_i, s);
     __syncwarp();
   }
 }
 
+template <int EW>
 __device__ __forceinline__ void epilogue_tile(bool top1, uint32_t t_addr, int col_base, int m, int etid, float* ring_v, int* ring_i,
                                               EpiRow& s) {
   if (top1)
-    epilogue_half<true>(t_addr, col_base, m, etid, ring_v, ring_i, s);
+    epilogue_half<true, EW>(t_addr, col_base, m, etid, ring_v, ring_i, s);
   else
-    epilogue_half<false>(t_addr, col_base, m, etid, ring_v, ring_i, s);
+    epilogue_half<false, EW>(t_addr, col_base, m, etid, ring_v, ring_i, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Single-CTA kernel: both operands streamed.  Serves searches with fewer than two 128-row query blocks.
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(Epi<EW1>::TC_THREADS, 1)
     match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, EPI_WARPS);
+      mbar_init(tempty0 + 8 * b, Epi<EW1>::WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int rb = (int)(t / P.col_tiles), ct = (int)(t % P.col_tiles);
       if (rb != cur_rb) {
         if (cur_rb >= 0)
-          flush_slot(P, n_rows, cur_rb * TBM + tid, (long long)cur_rb * P.col_tiles, total_tiles, gridDim.x, blockIdx.x, half, etid,
+          flush_slot<EW1>(P, n_rows, cur_rb * TBM + tid, (long long)cur_rb * P.col_tiles, total_tiles, gridDim.x, blockIdx.x, half, etid,
                      ring_v, ring_i, s);
         cur_rb = rb;
         epi_row_begin(P, s, rb * TBM + tid, n_rows);
@@ -382,14 +390,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t buf = (uint32_t)(it % NBUF);
       mbar_wait(tfull0 + 8 * buf, (uint32_t)((it / NBUF) & 1));
       tc_fence_after();
-      epilogue_tile(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * COLS_PER_WARP, ct * TBN + half * COLS_PER_WARP,
+      epilogue_tile<EW1>(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * Epi<EW1>::COLS, ct * TBN + half * Epi<EW1>::COLS,
                     P.m, etid, ring_v, ring_i, s);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
     if (cur_rb >= 0)
-      flush_slot(P, n_rows, cur_rb * TBM + tid, (long long)cur_rb * P.col_tiles, total_tiles, gridDim.x, blockIdx.x, half, etid, ring_v,
+      flush_slot<EW1>(P, n_rows, cur_rb * TBM + tid, (long long)cur_rb * P.col_tiles, total_tiles, gridDim.x, blockIdx.x, half, etid, ring_v,
                  ring_i, s);
   }
   tc_fence_before();
@@ -418,16 +426,16 @@ constexpr int STAGES3 = 6;
 constexpr uint32_t S3_A = 0;                                   // RESIDENT: dp/64 chunks; streaming: STAGES3 chunks
 constexpr uint32_t S3_B = A_MAX_KB * A_STAGE_BYTES;            // STAGES3 x (128 database rows x 64 k) = 16 KB each
 constexpr uint32_t S3_RING_V = S3_B + STAGES3 * B_HALF_BYTES;
-constexpr uint32_t S3_RING_I = S3_RING_V + EPI_THREADS * CAP * 4;
-constexpr uint32_t S3_BARS = S3_RING_I + EPI_THREADS * CAP * 4;
-constexpr uint32_t S3_TOTAL = S3_BARS + 256 + 1024;
+template <int EW> constexpr uint32_t s3_ring_i() { return S3_RING_V + Epi<EW>::RING_BYTES; }
+template <int EW> constexpr uint32_t s3_bars() { return s3_ring_i<EW>() + Epi<EW>::RING_BYTES; }
+template <int EW> constexpr uint32_t s3_total() { return s3_bars<EW>() + 256 + 1024; }
 constexpr uint32_t IDESC3 = umma_idesc_f16(2 * TBM, TBN, 0);
 static_assert(TBN == 256 && NBUF == 2, "the CTA-pair kernel is written for 256-column tiles");
 static_assert(STAGES3 <= A_MAX_KB, "streamed A chunks reuse the resident region");
-static_assert(S3_TOTAL <= 232448, "shared memory budget of one SM");
+static_assert(s3_total<8>() <= 232448, "shared memory budget of one SM");
 
-template <bool RESIDENT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+template <bool RESIDENT, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW>::TC_THREADS, 1)
     match_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -435,11 +443,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t sA = base + S3_A, sB = base + S3_B;
   float* ring_v = reinterpret_cast<float*>(smem + S3_RING_V);
-  int* ring_i = reinterpret_cast<int*>(smem + S3_RING_I);
-  const uint32_t bars = base + S3_BARS;
+  int* ring_i = reinterpret_cast<int*>(smem + s3_ring_i<EW>());
+  const uint32_t bars = base + s3_bars<EW>();
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES3, tfull0 = bars + 16 * STAGES3, tempty0 = tfull0 + 8 * NBUF;
   const uint32_t afull = tempty0 + 8 * NBUF, aempty = afull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S3_BARS + 16 * STAGES3 + 16 * NBUF + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + s3_bars<EW>() + 16 * STAGES3 + 16 * NBUF + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_cta_rank();
@@ -461,7 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(tfull0 + 8 * b, 1);                // both CTAs: multicast commit
-      mbar_init(tempty0 + 8 * b, 2 * EPI_WARPS);   // leader: epilogue warps of both CTAs
+      mbar_init(tempty0 + 8 * b, 2 * Epi<EW>::WARPS);   // leader: epilogue warps of both CTAs
     }
     mbar_init(afull, 1);
     mbar_init(aempty, 1);
@@ -564,7 +572,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const int rb = 2 * rp + (int)rank;
       if (rb != cur_rb) {
         if (cur_rb >= 0)
-          flush_slot(P, n_rows, cur_rb * TBM + tid, (long long)(cur_rb >> 1) * P.col_tiles, total_units, clusters, cid, half, etid,
+          flush_slot<EW>(P, n_rows, cur_rb * TBM + tid, (long long)(cur_rb >> 1) * P.col_tiles, total_units, clusters, cid, half, etid,
                      ring_v, ring_i, s);
         cur_rb = rb;
         epi_row_begin(P, s, rb * TBM + tid, n_rows);
@@ -572,14 +580,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const uint32_t buf = (uint32_t)(it % NBUF);
       mbar_wait(tfull0 + 8 * buf, (uint32_t)((it / NBUF) & 1));
       tc_fence_after();
-      epilogue_tile(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * COLS_PER_WARP, ct * TBN + half * COLS_PER_WARP,
+      epilogue_tile<EW>(P.top1 != 0, tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + half * Epi<EW>::COLS, ct * TBN + half * Epi<EW>::COLS,
                     P.m, etid, ring_v, ring_i, s);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
     }
     if (cur_rb >= 0)
-      flush_slot(P, n_rows, cur_rb * TBM + tid, (long long)(cur_rb >> 1) * P.col_tiles, total_units, clusters, cid, half, etid, ring_v,
+      flush_slot<EW>(P, n_rows, cur_rb * TBM + tid, (long long)(cur_rb >> 1) * P.col_tiles, total_units, clusters, cid, half, etid, ring_v,
                  ring_i, s);
   }
   tc_fence_before();
@@ -880,7 +888,7 @@ struct TcPlan {
 // `dynamic`: n is only an upper bound, the kernels read the row count from device memory.  The grid is sized for n; the
 // slot bound must then hold for every smaller total: spans of at least one unit cut a row block's col_tiles consecutive
 // units into at most col_tiles + 1 pieces (and spans of at most one unit into at most col_tiles).
-static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic = false) {
+static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic, int halves) {
   TcPlan p;
   p.row_blocks = ceil_div(n, TBM);
   p.col_tiles = ceil_div(m, TBN);
@@ -893,7 +901,7 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic = fals
     const long long min_span = p.total / clusters;
     p.slots = dynamic ? p.col_tiles + 1 : (int)((p.col_tiles + min_span - 1) / min_span) + 1;
     if (p.slots > clusters) p.slots = clusters;
-    p.slots *= HALVES;   // column groups per span
+    p.slots *= halves;   // column groups per span
     return p;
   }
   p.total = (long long)p.row_blocks * p.col_tiles;
@@ -902,12 +910,12 @@ static TcPlan tc_plan(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic = fals
   const long long min_span = p.total / p.grid;
   p.slots = dynamic ? p.col_tiles + 1 : (int)((p.col_tiles + min_span - 1) / min_span) + 1;
   if (p.slots > p.grid) p.slots = p.grid;
-  p.slots *= HALVES;   // column groups per span
+  p.slots *= 1;        // the single-CTA kernel runs 4 epilogue warps
   return p;
 }
 
 size_t match_tc_scratch(vfmreg_ctx* ctx, int64_t n, int64_t m, bool dynamic) {
-  const TcPlan p = tc_plan(ctx, n, m, dynamic);
+  const TcPlan p = tc_plan(ctx, n, m, dynamic, 2);   // sized for the 8-warp variant (two column groups per span)
   return 2 * arena_bytes((size_t)n * p.slots * CAP, 4) + arena_bytes((size_t)n * p.slots, 4) +
          arena_bytes((size_t)n * p.slots, 16) + 2048;
 }
@@ -926,7 +934,9 @@ int match_tc_begin(vfmreg_ctx* ctx, const float* a32, const void* a16, const uin
                    float floor, TcPending* pending) {
   VFM_CHECK_ARG(dp % TBK == 0 && dp <= 1024, "match_tc: padded dim %d must be a multiple of %d and <= 1024 (error bound)", dp, TBK);
   VFM_CHECK_ARG(n > 0 && m > 0 && n < (1LL << 30) && m < (1LL << 30), "match_tc: bad sizes");
-  const TcPlan plan = tc_plan(ctx, n, m, n_dev != nullptr);
+  const bool top1 = sec == nullptr;
+  const int ew = top1 ? 4 : 8;   // epilogue warps of the pair kernel (see Epi)
+  const TcPlan plan = tc_plan(ctx, n, m, n_dev != nullptr, ew / 4);
   float* cand_v = arena_take<float>(ctx, (size_t)n * plan.slots * CAP);
   int* cand_i = arena_take<int>(ctx, (size_t)n * plan.slots * CAP);
   float4* slot_top2 = arena_take<float4>(ctx, (size_t)n * plan.slots);
@@ -953,15 +963,17 @@ int match_tc_begin(vfmreg_ctx* ctx, const float* a32, const void* a16, const uin
   P.cand_i = cand_i;
   P.cand_n = cand_n;
   P.slot_top2 = slot_top2;
-  P.top1 = (sec == nullptr) ? 1 : 0;
+  P.top1 = top1 ? 1 : 0;
   P.n_dev = n_dev;
   P.seed = seed;
   const bool floor_mode = P.top1 && !(floor != floor);
   P.floor = floor_mode ? floor - MARGIN : -INFINITY;
   if (!ctx->tc_attr_set) {   // function attributes are per device; one context per device
     VFM_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-    VFM_CUDA(cudaFuncSetAttribute(match_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_TOTAL));
-    VFM_CUDA(cudaFuncSetAttribute(match_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_TOTAL));
+    VFM_CUDA(cudaFuncSetAttribute(match_tc3_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_total<4>()));
+    VFM_CUDA(cudaFuncSetAttribute(match_tc3_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_total<4>()));
+    VFM_CUDA(cudaFuncSetAttribute(match_tc3_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_total<8>()));
+    VFM_CUDA(cudaFuncSetAttribute(match_tc3_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_total<8>()));
     ctx->tc_attr_set = true;
   }
   const int grp = n_dev ? GROUP_MATCH_PRUNED : GROUP_MATCH;
@@ -979,13 +991,21 @@ int match_tc_begin(vfmreg_ctx* ctx, const float* a32, const void* a16, const uin
   group_begin(ctx, grp);
   int rc_launch = VFMREG_OK;
   if (plan.paired) {
-    if (dp <= A_MAX_KB * TBK)
-      match_tc3_kernel<true><<<plan.grid, TC_THREADS, S3_TOTAL, ctx->stream>>>(map_a, map_b, P);
-    else
-      match_tc3_kernel<false><<<plan.grid, TC_THREADS, S3_TOTAL, ctx->stream>>>(map_a, map_b, P);
+    const bool resident = dp <= A_MAX_KB * TBK;
+    if (ew == 4) {
+      if (resident)
+        match_tc3_kernel<true, 4><<<plan.grid, Epi<4>::TC_THREADS, s3_total<4>(), ctx->stream>>>(map_a, map_b, P);
+      else
+        match_tc3_kernel<false, 4><<<plan.grid, Epi<4>::TC_THREADS, s3_total<4>(), ctx->stream>>>(map_a, map_b, P);
+    } else {
+      if (resident)
+        match_tc3_kernel<true, 8><<<plan.grid, Epi<8>::TC_THREADS, s3_total<8>(), ctx->stream>>>(map_a, map_b, P);
+      else
+        match_tc3_kernel<false, 8><<<plan.grid, Epi<8>::TC_THREADS, s3_total<8>(), ctx->stream>>>(map_a, map_b, P);
+    }
     rc_launch = launch_check(ctx, "match_tc3_kernel");
   } else {
-    match_tc_kernel<<<plan.grid, TC_THREADS, SMEM_TOTAL, ctx->stream>>>(map_a, map_b, P);
+    match_tc_kernel<<<plan.grid, Epi<EW1>::TC_THREADS, SMEM_TOTAL, ctx->stream>>>(map_a, map_b, P);
     rc_launch = launch_check(ctx, "match_tc_kernel");
   }
   group_end(ctx, grp, 1);
