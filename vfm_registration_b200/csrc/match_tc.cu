@@ -452,6 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW>::TC_THREADS,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_cta_rank();
   const long long clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  TraceScope trace(P.n_dev ? 21 : 20);   // trace build only: 20 = full search, 21 = pruned reverse search
   const int n_rows = tc_rows(P);
   const int row_pairs = (n_rows + 2 * TBM - 1) / (2 * TBM);
   const long long total_units = (long long)row_pairs * P.col_tiles;
@@ -597,6 +598,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW>::TC_THREADS,
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 512u);
   }
+  trace.end();
 }
 
 // multiset top-2 merge of (x1 >= x2) into (t1 >= t2)
@@ -1071,3 +1073,5 @@ int match_tc(vfmreg_ctx* ctx, const float* a32, const void* a16, const uint8_t* 
 }
 
 }  // namespace vfm
+
+VFM_TRACE_ATTACH(vfmreg_trace_attach_match)

@@ -16,6 +16,8 @@
 //                      48 K bytes of pq per hypothesis block, L2 resident.
 //   finalize_kernel    one CTA: arg-best by (count desc, sumq asc, id asc) with warp-shuffle reductions, the winner's
 //                      inlier mask, optional least-squares refit, outputs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vfm {
@@ -442,7 +444,8 @@ int ransac_solve(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int 
   if (max_corr >= 3) {
     const int hyp_blocks = ceil_div(n_hyp, HYP_PER_CTA);
     const int max_splits = ceil_div(max_corr, 64);                  // at least 64 correspondences per slice
-    int splits = ceil_div((int64_t)ctx->sm_count * 4, hyp_blocks);  // ~4 CTAs of 128 threads (x 2 hypotheses) per SM
+    static const int per_sm = [] { const char* e = getenv("VFMREG_SCORE_CTAS_PER_SM"); return e ? atoi(e) : 4; }();   // tuning aid
+    int splits = ceil_div((int64_t)ctx->sm_count * per_sm, hyp_blocks);  // ~per_sm CTAs of 128 threads (x 2 hypotheses) per SM
     if (splits < 1) splits = 1;
     if (splits > max_splits) splits = max_splits;
     group_begin(ctx, GROUP_RANSAC);
