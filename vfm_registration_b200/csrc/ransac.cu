@@ -25,7 +25,11 @@ namespace vfm {
 constexpr int SCORE_THREADS = 128;
 constexpr int PREP_THREADS = 128;
 constexpr int SCORE_TILE = 64;   // correspondences per shared-memory tile (3 KB)
-constexpr int HYP_PER_CTA = 2 * SCORE_THREADS;   // two hypotheses per thread
+#ifndef VFM_HYP_PER_THREAD
+#define VFM_HYP_PER_THREAD 2
+#endif
+constexpr int HYP_PER_THREAD = VFM_HYP_PER_THREAD;   // hypotheses per thread: every shared-memory broadcast feeds that many DFMA chains
+constexpr int HYP_PER_CTA = HYP_PER_THREAD * SCORE_THREADS;
 constexpr int SWEEPS = 6;
 constexpr int FIN_THREADS = 256;   // 256 x <= 128 registers: the CTA must fit beside a candidate-search CTA of a neighbouring pair
 
@@ -221,17 +225,22 @@ __global__ void __launch_bounds__(SCORE_THREADS)
   const int per = (K + gridDim.y - 1) / gridDim.y;
   const int k0 = blockIdx.y * per, k1 = min(K, k0 + per);
   if (k0 >= k1) return;
-  const int ha = blockIdx.x * HYP_PER_CTA + threadIdx.x, hb = ha + SCORE_THREADS;
-  // counts[h] is only ever raised by score CTAs, never below 0: -1 marks a degenerate sample
-  const bool live_a = (ha < n_hyp) && (counts[ha] >= 0), live_b = (hb < n_hyp) && (counts[hb] >= 0);
-  double ra[12], rb[12];
+  // hypothesis j of this thread: blockIdx.x * HYP_PER_CTA + j * SCORE_THREADS + threadIdx.x
+  int hid[HYP_PER_THREAD];
+  bool live[HYP_PER_THREAD];
+  double r[HYP_PER_THREAD][12];
+  int cnt[HYP_PER_THREAD];
+  long long sum[HYP_PER_THREAD];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    ra[i] = (ha < n_hyp) ? rts[(int64_t)ha * 12 + i] : 0.0;
-    rb[i] = (hb < n_hyp) ? rts[(int64_t)hb * 12 + i] : 0.0;
+  for (int j = 0; j < HYP_PER_THREAD; ++j) {
+    hid[j] = blockIdx.x * HYP_PER_CTA + j * SCORE_THREADS + threadIdx.x;
+    // counts[h] is only ever raised by score CTAs, never below 0: -1 marks a degenerate sample
+    live[j] = (hid[j] < n_hyp) && (counts[hid[j]] >= 0);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r[j][i] = (hid[j] < n_hyp) ? rts[(int64_t)hid[j] * 12 + i] : 0.0;
+    cnt[j] = 0;
+    sum[j] = 0;
   }
-  int cnt_a = 0, cnt_b = 0;
-  long long sum_a = 0, sum_b = 0;
   const double2* s2 = reinterpret_cast<const double2*>(tile);
   for (int t0 = k0; t0 < k1; t0 += SCORE_TILE) {
     const int rows = min(SCORE_TILE, k1 - t0);
@@ -241,27 +250,23 @@ __global__ void __launch_bounds__(SCORE_THREADS)
     __syncthreads();
 #pragma unroll 2
     for (int k = 0; k < rows; ++k) {
-      const double2 v0 = s2[3 * k], v1 = s2[3 * k + 1], v2 = s2[3 * k + 2];  // warp-wide broadcasts
-      const double da = resid2(ra, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
-      const double db = resid2(rb, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
-      if (da < tau2) {
-        ++cnt_a;
-        sum_a += quant(da, scale);
-      }
-      if (db < tau2) {
-        ++cnt_b;
-        sum_b += quant(db, scale);
+      const double2 v0 = s2[3 * k], v1 = s2[3 * k + 1], v2 = s2[3 * k + 2];  // warp-wide broadcasts, shared by the thread's hypotheses
+#pragma unroll
+      for (int j = 0; j < HYP_PER_THREAD; ++j) {
+        const double d = resid2(r[j], v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
+        if (d < tau2) {
+          ++cnt[j];
+          sum[j] += quant(d, scale);
+        }
       }
     }
   }
-  if (live_a && cnt_a > 0) {
-    atomicAdd(&counts[ha], cnt_a);
-    atomicAdd(&sumq[ha], (unsigned long long)sum_a);
-  }
-  if (live_b && cnt_b > 0) {
-    atomicAdd(&counts[hb], cnt_b);
-    atomicAdd(&sumq[hb], (unsigned long long)sum_b);
-  }
+#pragma unroll
+  for (int j = 0; j < HYP_PER_THREAD; ++j)
+    if (live[j] && cnt[j] > 0) {
+      atomicAdd(&counts[hid[j]], cnt[j]);
+      atomicAdd(&sumq[hid[j]], (unsigned long long)sum[j]);
+    }
 }
 
 struct Best {
