@@ -125,14 +125,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
       o += ep.ldo;
     }
   } else {
-    // patch row tok = img * np + p  ->  residual-stream row img * (np + 1) + 1 + p, position row 1 + p
-    int img = tok_c / ep.np, p = tok_c - img * ep.np;
+    // patch row tok = img * np + p  ->  residual-stream row img * (np + 1) + 1 + p, position row 1 + p.  (img, p) of every
+    // token of the chunk follow from the first one's without a carried dependency: 32 independent load / add / store chains
+    const int img0 = tok_c / ep.np, p0 = tok_c - img0 * ep.np;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       if (FULL || j < valid) {
+        int p = p0 + j, img = img0;
+        while (p >= ep.np) {   // at most a few images per 32-token chunk
+          p -= ep.np;
+          ++img;
+        }
         const long long out_row = (long long)img * (ep.np + 1) + 1 + p;
         ep.x[out_row * ep.ldo + f] = __uint_as_float(r[j]) + bias + __ldg(ep.pos + (long long)(1 + p) * ep.n + f);
-        if (++p == ep.np) { p = 0; ++img; }
       }
     }
   }

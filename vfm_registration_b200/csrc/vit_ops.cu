@@ -16,9 +16,13 @@
 namespace vfm {
 
 // ---------------------------------------------------------------------------------------------------------------------
+// PATCH > 0: the patch size as a compile-time constant (14 for every DINOv2 model: the six divisions by it and by its square
+// become multiplications), 0: the run-time value
+template <int PATCH>
 __global__ void __launch_bounds__(256)
-    preprocess_kernel(const uint8_t* __restrict__ images, int b, int h, int w, int gh, int gw, int patch, float m0, float m1,
+    preprocess_kernel(const uint8_t* __restrict__ images, int b, int h, int w, int gh, int gw, int patch_rt, float m0, float m1,
                       float m2, float s0, float s1, float s2, __nv_bfloat16* __restrict__ patches, int kp) {
+  const int patch = PATCH > 0 ? PATCH : patch_rt;
   pdl_launch_dependents();
   const long long total = (long long)b * gh * gw * kp;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,8 +68,12 @@ __global__ void cls_rows_kernel(float* __restrict__ x, int b, int t, int width, 
 int vit_preprocess(vfmreg_ctx* ctx, const uint8_t* images, int b, int h, int w, int gh, int gw, int patch, const float* ms,
                    __nv_bfloat16* patches, int kp, float* x, const float* cls, const float* pos, int width) {
   const long long total = (long long)b * gh * gw * kp;
-  preprocess_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(images, b, h, w, gh, gw, patch, ms[0], ms[1], ms[2], ms[3],
-                                                                  ms[4], ms[5], patches, kp);
+  if (patch == 14)
+    preprocess_kernel<14><<<ceil_div(total, 256), 256, 0, ctx->stream>>>(images, b, h, w, gh, gw, patch, ms[0], ms[1], ms[2], ms[3],
+                                                                        ms[4], ms[5], patches, kp);
+  else
+    preprocess_kernel<0><<<ceil_div(total, 256), 256, 0, ctx->stream>>>(images, b, h, w, gh, gw, patch, ms[0], ms[1], ms[2], ms[3],
+                                                                       ms[4], ms[5], patches, kp);
   VFM_TRY(launch_check(ctx, "preprocess_kernel"));
   VFM_CUDA(launch_pdl(cls_rows_kernel, dim3(ceil_div((long long)b * width, 256)), dim3(256), 0, ctx->stream, x, b, gh * gw + 1, width,
                       cls, pos));
