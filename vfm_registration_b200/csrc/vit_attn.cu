@@ -35,16 +35,6 @@ constexpr int AT_MAX_T = AT_MAX_CH * 2 * 32;   // 320 tokens per image
 constexpr int AT_FEW = 4;                     // query blocks with at most this many real rows take the shared-row path
 constexpr uint32_t AT_O_COL = 448;   // TMEM column of the O accumulator (S uses columns 0 .. 319)
 
-__device__ __forceinline__ void tc_mma_f16_1sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  tc_mma_f16(tmem_d, desc_a, desc_b, idesc, accum);
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

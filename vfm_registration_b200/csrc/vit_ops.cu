@@ -251,7 +251,7 @@ int vit_final_norm(vfmreg_ctx* ctx, const float* x, int b, int t, int width, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int ATT_Q = 64, ATT_DH = 64, ATT_LD = 72;
+constexpr int ATT_DH = 64, ATT_LD = 72;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
