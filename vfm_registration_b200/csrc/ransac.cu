@@ -450,7 +450,9 @@ int ransac_solve(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int 
     const int hyp_blocks = ceil_div(n_hyp, HYP_PER_CTA);
     const int max_splits = ceil_div(max_corr, 64);                  // at least 64 correspondences per slice
     static const int per_sm = [] { const char* e = getenv("VFMREG_SCORE_CTAS_PER_SM"); return e ? atoi(e) : 4; }();   // tuning aid
-    int splits = ceil_div((int64_t)ctx->sm_count * per_sm, hyp_blocks);  // ~per_sm CTAs of 128 threads (x 2 hypotheses) per SM
+    // per_sm CTAs of 128 threads fit an SM (registers): the grid must not exceed one wave -- rounding the slice count UP left a
+    // second wave of 16 CTAs (608 CTAs on 592 slots) that doubled the kernel's time
+    int splits = (int)(((int64_t)ctx->sm_count * per_sm) / hyp_blocks);
     if (splits < 1) splits = 1;
     if (splits > max_splits) splits = max_splits;
     group_begin(ctx, GROUP_RANSAC);
