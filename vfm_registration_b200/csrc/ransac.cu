@@ -28,6 +28,9 @@ constexpr int SCORE_TILE = 64;   // correspondences per shared-memory tile (3 KB
 #ifndef VFM_HYP_PER_THREAD
 #define VFM_HYP_PER_THREAD 2
 #endif
+#ifndef VFM_SCORE_MIN_CTAS
+#define VFM_SCORE_MIN_CTAS 5
+#endif
 constexpr int HYP_PER_THREAD = VFM_HYP_PER_THREAD;   // hypotheses per thread: every shared-memory broadcast feeds that many DFMA chains
 constexpr int HYP_PER_CTA = HYP_PER_THREAD * SCORE_THREADS;
 constexpr int SWEEPS = 6;
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(PREP_THREADS)
 // The tile is that small on purpose: the kernel runs beside the candidate search of the neighbouring pairs, whose CTAs
 // leave about 18 KB of shared memory (and hardly any L1) per SM -- four of these CTAs still fit there.
 // grid = (blocks of 256 hypotheses) x (slices of the correspondence list).
-__global__ void __launch_bounds__(SCORE_THREADS)
+__global__ void __launch_bounds__(SCORE_THREADS, VFM_SCORE_MIN_CTAS)
     score_kernel(const double* __restrict__ pq, const int32_t* __restrict__ count, int max_corr,
                  const double* __restrict__ rts, int n_hyp, double tau2, double scale, int32_t* __restrict__ counts,
                  unsigned long long* __restrict__ sumq) {
@@ -449,7 +452,7 @@ int ransac_solve(vfmreg_ctx* ctx, const void* src_xyz, const void* tgt_xyz, int 
   if (max_corr >= 3) {
     const int hyp_blocks = ceil_div(n_hyp, HYP_PER_CTA);
     const int max_splits = ceil_div(max_corr, 64);                  // at least 64 correspondences per slice
-    static const int per_sm = [] { const char* e = getenv("VFMREG_SCORE_CTAS_PER_SM"); return e ? atoi(e) : 4; }();   // tuning aid
+    static const int per_sm = [] { const char* e = getenv("VFMREG_SCORE_CTAS_PER_SM"); return e ? atoi(e) : VFM_SCORE_MIN_CTAS; }();   // tuning aid
     // per_sm CTAs of 128 threads fit an SM (registers): the grid must not exceed one wave -- rounding the slice count UP left a
     // second wave of 16 CTAs (608 CTAs on 592 slots) that doubled the kernel's time
     int splits = (int)(((int64_t)ctx->sm_count * per_sm) / hyp_blocks);
