@@ -46,6 +46,19 @@ with tempfile.TemporaryDirectory() as tmp:
             p4 = np.insert(pcl.astype(np.float64), 3, values=1, axis=1).T
             x_im, y_im, idx = ref.project_pcl_to_image(p4, cv2.rotate(im, cv2.ROTATE_90_COUNTERCLOCKWISE), cam)
             out[f"proj{sub}_{cam}_x"], out[f"proj{sub}_{cam}_y"], out[f"proj{sub}_{cam}_idx"] = x_im, y_im, idx
+# ---- RobotCar: the SDK's own CameraModel.undistort (robotcar_sdk/python/camera_model.py) on a demosaiced synthetic Bayer image.
+# colour_demosaicing is not installable offline: the demosaic is the restatement in datasets.py (published bilinear kernels).
+from dataloader.robotcar_sdk.python.camera_model import CameraModel  # noqa: E402
+from vfm_registration_b200 import datasets as _ds  # noqa: E402
+with tempfile.TemporaryDirectory() as tmp:
+    h, w = 320, 416
+    synth_dataset.write_robotcar_models(tmp, h, w)
+    model = CameraModel(tmp, "/x/mono_left/")
+    rgb = _ds.demosaic_bilinear(synth_dataset.robotcar_cfa(h, w).astype(np.float64), "RGGB")
+    out["rc_hw"] = np.asarray([h, w])
+    und = model.undistort(rgb)
+    out["rc_undistorted_patch"] = und[40:56, 60:76].copy()
+    out["rc_undistorted_sha"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(und).tobytes()).digest(), dtype=np.uint8)
 os.makedirs(ROOT / "tests" / "golden", exist_ok=True)
 np.savez_compressed(ROOT / "tests" / "golden" / "datasets_nclt.npz", **out)
 print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})

@@ -63,3 +63,22 @@ def build(root, cameras=("Cam1", "Cam2", "Cam3", "Cam4", "Cam5"), distinct_maps=
     raw[:, 3] = rng.integers(0, 255, n_pts)
     raw.tofile(v / f"{TS}.bin")
     return root
+
+
+# ---- RobotCar: a camera model (intrinsics + distortion look-up table) and a Bayer image -------------------------------------
+def write_robotcar_models(models_dir, h, w, names=("mono_left",)):
+    """<name>.txt (fx fy cx cy + G_camera_image) and <name>_distortion_lut.bin (float64 (2, H*W): u then v of the source pixel)."""
+    models_dir = Path(models_dir)
+    v, u = np.mgrid[0:h, 0:w].astype(np.float64)
+    du, dv = (u - w / 2) / w, (v - h / 2) / h
+    r2 = du * du + dv * dv
+    lut = np.stack([(u + 0.12 * w * du * r2 + 1.5 * np.sin(v / 37.0)).ravel(), (v + 0.12 * h * dv * r2 + 1.1 * np.cos(u / 41.0)).ravel()])
+    for n in names:
+        (models_dir / f"{n}.txt").write_text("400.0 401.0 %.1f %.1f\n0 0 1 0\n1 0 0 0\n0 1 0 0\n0 0 0 1\n" % (w / 2, h / 2))
+        lut.tofile(models_dir / f"{n}_distortion_lut.bin")
+
+
+def robotcar_cfa(h, w):
+    rng = np.random.default_rng(77)
+    import cv2
+    return cv2.resize(rng.integers(0, 256, (h // 4, w // 4), dtype=np.uint8), (w, h), interpolation=cv2.INTER_LINEAR)

@@ -100,3 +100,38 @@ def test_robotcar_loader(tmp_path):
     assert np.array_equal(out, pts[(d > 2.5) & (d < 50)])
     spec = seq.camera_spec("stereo/centre", (760, 1280))
     assert spec.float_bounds and spec.z_inclusive and spec.black_mode == 2 and spec.P.shape == (3, 4)
+
+
+def test_robotcar_raw_image_chain(tmp_path):
+    """Bayer PNG -> bilinear demosaic -> LUT undistortion -> uint8 -> crop (oxford_robotcar.py:101-137).  The undistortion is
+    pinned to the reference's own CameraModel (robotcar_sdk/python/camera_model.py, fixture from oracle/gen_golden_datasets.py);
+    the demosaic (colour_demosaicing is not installable offline) is checked against direct neighbour averaging."""
+    from PIL import Image
+    from vfm_registration_b200 import datasets
+    g = np.load(GOLD)
+    h, w = int(g["rc_hw"][0]), int(g["rc_hw"][1])
+    sdk = tmp_path / "sdk"
+    (sdk / "extrinsics").mkdir(parents=True)
+    (sdk / "models").mkdir()
+    for n in ("velodyne_left", "stereo", "mono_left", "mono_right", "mono_rear", "ins"):
+        (sdk / "extrinsics" / f"{n}.txt").write_text("0 0 0 0 0 0\n")
+    synth_dataset.write_robotcar_models(sdk / "models", h, w)
+    cfa8 = synth_dataset.robotcar_cfa(h, w)
+    cfa = cfa8.astype(np.float64)
+    seq = datasets.OxfordRobotcar("2019-01-10-11-46-21", tmp_path, sdk, cameras=("mono_left",))
+    rgb = datasets.demosaic_bilinear(cfa, "RGGB")
+    # interior pixels: red at (even, even), green at the two mixed sites, blue at (odd, odd)
+    y, x = 10, 12                                         # a red site
+    assert rgb[y, x, 0] == cfa[y, x]
+    assert rgb[y, x, 1] == (cfa[y - 1, x] + cfa[y + 1, x] + cfa[y, x - 1] + cfa[y, x + 1]) / 4
+    assert rgb[y, x, 2] == (cfa[y - 1, x - 1] + cfa[y - 1, x + 1] + cfa[y + 1, x - 1] + cfa[y + 1, x + 1]) / 4
+    y, x = 11, 12                                         # a green site on a blue row
+    assert rgb[y, x, 1] == cfa[y, x] and rgb[y, x, 0] == (cfa[y - 1, x] + cfa[y + 1, x]) / 2 and rgb[y, x, 2] == (cfa[y, x - 1] + cfa[y, x + 1]) / 2
+    und = seq.undistort("mono_left", rgb)
+    # the reference's CameraModel.undistort on the same demosaiced image: every value (sha-256) and a patch
+    sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(und).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(und[40:56, 60:76], g["rc_undistorted_patch"]) and np.array_equal(sha, g["rc_undistorted_sha"])
+    Image.fromarray(cfa8).save(tmp_path / "raw.png")
+    out = seq.read_images([tmp_path / "raw.png"], raw=True)["mono_left"]
+    assert out.shape == (h - 200, w, 3) and out.dtype == np.uint8
+    assert np.array_equal(out, und.astype(np.uint8)[: h - 200])

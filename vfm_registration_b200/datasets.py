@@ -11,7 +11,8 @@ reference, none of which changes a pixel:
     (remap is per-pixel, hence the same fixed-point bilinear samples; tests/test_datasets_cpu.py checks equality against the
     reference's own output);
   * the U2D text maps (2 M lines per camera) are parsed with one vectorised pass instead of a Python loop;
-  * RobotCar extrinsics / camera models are looked up in a directory the caller names (the SDK is not vendored here).
+  * RobotCar extrinsics / camera models / distortion LUTs are looked up in a directory the caller names (the SDK is not
+    vendored here); raw Bayer images go through the same demosaic -> LUT undistortion -> crop chain as the reference's loader.
 """
 from __future__ import annotations
 
@@ -55,6 +56,21 @@ def _pose(xyz, rpy_deg) -> np.ndarray:
     T[:3, :3] = euler_xyz_deg(rpy_deg)
     T[:3, 3] = xyz
     return T
+
+
+def demosaic_bilinear(cfa: np.ndarray, pattern: str) -> np.ndarray:
+    """colour_demosaicing.demosaicing_CFA_Bayer_bilinear (the library the reference calls, oxford_robotcar.py:8,108-111; not
+    installable offline, restated from its published source): each colour plane is the CFA masked to that colour's sites and
+    convolved with the bilinear kernel -- [[1,2,1],[2,4,2],[1,2,1]] / 4 for red and blue, [[0,1,0],[1,4,1],[0,1,0]] / 4 for green --
+    with reflected borders (scipy.ndimage.convolve's default).  ``pattern``: the 2 x 2 Bayer tile, row-major ("RGGB", "GBRG")."""
+    from scipy.ndimage import convolve
+    cfa = np.asarray(cfa, dtype=np.float64)
+    masks = {c: np.zeros(cfa.shape, dtype=np.float64) for c in "RGB"}
+    for ch, (y, x) in zip(pattern.upper(), ((0, 0), (0, 1), (1, 0), (1, 1))):
+        masks[ch][y::2, x::2] = 1.0
+    h_g = np.array([[0, 1, 0], [1, 4, 1], [0, 1, 0]], dtype=np.float64) / 4
+    h_rb = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=np.float64) / 4
+    return np.stack([convolve(cfa * masks["R"], h_rb), convolve(cfa * masks["G"], h_g), convolve(cfa * masks["B"], h_rb)], axis=2)
 
 
 class NCLT:
@@ -197,6 +213,7 @@ class OxfordRobotcar:
         self.sequence, self.root_dir, self.sdk_dir = str(sequence), Path(root_dir), Path(sdk_dir)
         self.image_subsample, self.cameras = int(image_subsample), list(cameras)
         self.lidar_frequency = 10
+        self._luts: Dict[str, np.ndarray] = {}
         self.calib = self.read_calib()
 
     @property
@@ -238,13 +255,44 @@ class OxfordRobotcar:
             G = np.array([[float(x) for x in line.split()] for line in f if line.strip()], dtype=np.float64)
         return (fx, fy), (cx, cy), G
 
-    def read_images(self, filenames: Sequence) -> Dict[str, np.ndarray]:
-        """The undistorted, hood-cropped RGB images the reference caches as <camera>_undistorted/<ts>.png
-        (oxford_robotcar.py:101-137) -- debayering and the SDK's LUT undistortion are left to the SDK that owns the LUTs."""
+    def read_lut(self, camera: str) -> np.ndarray:
+        """models/<model>_distortion_lut.bin (camera_model.py:148-154): float64 (2, H * W) = for every pixel of the undistorted
+        image the (u, v) it comes from in the distorted one.  Returned as the (2, H*W) (row, column) coordinate array that
+        ``undistort`` hands to the interpolation."""
+        if camera not in self._luts:
+            stem = {"stereo/centre": "stereo_narrow_left"}.get(camera, camera)
+            lut = np.fromfile(self.sdk_dir / "models" / f"{stem}_distortion_lut.bin", np.double)
+            lut = lut.reshape(2, lut.size // 2)
+            self._luts[camera] = np.ascontiguousarray(lut[::-1])   # (v, u): row coordinates first
+        return self._luts[camera]
+
+    def undistort(self, camera: str, image: np.ndarray) -> np.ndarray:
+        """CameraModel.undistort (camera_model.py:85-117): bilinear look-up of every channel through the LUT (the same
+        scipy.ndimage.map_coordinates(order=1) call, so the same values), cast back to the image's dtype."""
+        from scipy.ndimage import map_coordinates
+        lut = self.read_lut(camera)
+        if image.ndim != 3:
+            raise ValueError("Undistortion function only works with multi-channel images")
+        if image.shape[0] * image.shape[1] != lut.shape[1]:
+            raise ValueError("Incorrect image size for camera model")
+        coords = lut.reshape(2, image.shape[0], image.shape[1])
+        return np.stack([map_coordinates(image[:, :, c], coords, order=1) for c in range(image.shape[2])], axis=2).astype(image.dtype)
+
+    def read_images(self, filenames: Sequence, raw: bool = False) -> Dict[str, np.ndarray]:
+        """camera -> RGB uint8 image.  ``raw=False``: the files are the undistorted, hood-cropped images the reference caches as
+        <camera>_undistorted/<ts>.png.  ``raw=True``: the files are the Bayer PNGs of the dataset and go through the reference's
+        own chain (oxford_robotcar.py:101-137): bilinear demosaic (GBRG for stereo/centre, RGGB for the mono cameras), LUT
+        undistortion, cast to uint8, crop of the bonnet (150 rows) / of the area without LiDAR coverage (200 rows).  Then the
+        optional bilinear sub-sampling."""
         from PIL import Image
         out = {}
         for camera, path in zip(self.cameras, filenames):
             img = Image.open(path)
+            if raw:
+                rgb = demosaic_bilinear(np.asarray(img, dtype=np.float64), "GBRG" if camera == "stereo/centre" else "RGGB")
+                rgb = self.undistort(camera, rgb).astype(np.uint8)
+                img = Image.fromarray(rgb)
+                img = img.crop((0, 0, img.size[0], img.size[1] - (150 if camera == "stereo/centre" else 200)))
             if self.image_subsample > 1:
                 img = img.resize((img.size[0] // self.image_subsample, img.size[1] // self.image_subsample), Image.BILINEAR)
             out[camera] = np.array(img)
