@@ -317,3 +317,44 @@ def test_non_finite_points_are_dropped_not_fatal(vfm):
     assert np.isfinite(xyz.cpu().numpy()).all() and np.isin(src.cpu().numpy(), good).all()
     assert np.array_equal(xyz.cpu().numpy(), dirty[src.cpu().numpy()])
     m.close()
+
+
+def test_prepare_scene_producer_on_a_synthetic_nclt_tree(vfm, tmp_path, monkeypatch):
+    """scenes.prepare_scene (prepare_scenes.py:110-167) end to end on the miniature NCLT tree: scan decoding, 0.2 / 0.1 m voxel
+    thinning, undistorted images, ViT descriptors through the fused projection + gather kernel, scene file.  The descriptors of
+    a frame equal a direct create_descriptors call; unseen points carry zero rows; the file round-trips."""
+    import json
+    import os
+    import sys
+    pytest.importorskip("cv2")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import synth_dataset
+    import test_scenes_h5_cpu as h5stub
+    import types
+    fake = types.ModuleType("h5py")
+    fake.File = h5stub._File
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    from vfm_registration_b200 import datasets, features, scenes
+    root = tmp_path / "nclt"
+    synth_dataset.build(root, distinct_maps=1)
+    ts, seq = synth_dataset.TS, synth_dataset.SEQ
+    imgs = [f"images/{seq}/lb3/Cam{c}/{ts}.tiff" for c in range(1, 6)]
+    pose = np.eye(4).tolist()
+    scene = {"mapping": {"point_clouds": [f"velodyne_data/{seq}/velodyne_sync/{ts}.bin"] * 2, "images": [imgs, imgs], "poses": [pose, pose]},
+             "registration": [{"point_cloud": f"velodyne_data/{seq}/velodyne_sync/{ts}.bin", "images": imgs, "pose": pose}]}
+    (tmp_path / "scene_000.json").write_text(json.dumps(scene))
+    with pytest.warns(RuntimeWarning):
+        gen = vfm.ImageFeatureGenerator("dinov2", seed=2, random_init=True)
+    out = scenes.prepare_scene(root, tmp_path / "scene_000.json", tmp_path / "processed", gen, dataset="nclt")
+    s = scenes.read_scenes(out)
+    assert len(s["map_point_clouds"]) == 2 and len(s["scene_point_clouds"]) == 1
+    m0, sc = s["map_point_clouds"][0], s["scene_point_clouds"][0]
+    assert m0.shape[1] == 3 + 384 and sc.shape[1] == 387 and sc.shape[0] >= m0.shape[0]     # 0.1 m keeps at least the points 0.2 m keeps
+    loader = datasets.NCLT(seq, root)
+    pcl = vfm.voxel_down_sample(loader.read_pcl(frame_id=0), 0.2).astype(np.float32)
+    assert np.array_equal(m0[:, :3], pcl)
+    images = loader.read_images(frame_id=0)
+    want = features.create_descriptors(images, loader.project_params(images), gen, pcl)
+    assert np.array_equal(m0[:, 3:], want)
+    seen = np.abs(m0[:, 3:]).sum(axis=1) > 0
+    assert 0 < (~seen).sum() < len(seen)      # some points project into no camera: zero rows (prepare_scenes.py:102-104)

@@ -126,3 +126,45 @@ def prepare_scan(point_cloud, voxel_size: float = 0.1, device=None) -> np.ndarra
     """registration_node.py:588-590."""
     point_cloud = np.asarray(point_cloud)
     return voxel_down_sample(point_cloud, voxel_size, device=device).astype(point_cloud.dtype)
+
+
+def prepare_scene(dataset_dir, scene_file, output_dir, feature_generator, *, dataset: str = "", sdk_dir=None, image_subsample: int = 1,
+                  device=None) -> Path:
+    """The producer (prepare_scenes.py:110-167, `python prepare_scenes.py /data/DATASET /scenes/DATASET` for one scene file):
+    every map frame is read, voxel-thinned at 0.2 m and given per-point descriptors from its surround images, every scan the
+    same at 0.1 m, and the scene goes to ``output_dir/<scene>.h5``.  Differences in mechanics only: the voxel thinning and
+    projection + gather run on the GPU (`voxel_down_sample`, `features.create_descriptors` -> one fused kernel per frame
+    instead of the per-point Python loops of project_pcl_to_image / create_descriptors).
+
+    ``dataset``: "nclt" or "robotcar" (default: from the directory name, as the reference decides); ``sdk_dir``: the RobotCar
+    SDK checkout (extrinsics, camera models, LUTs); ``image_subsample`` stays at the loaders' default of 1 -- the reference
+    sets a local `image_subsample = 2` (:119) but never passes it on."""
+    from . import datasets, features
+    dataset_dir, scene_file, output_dir = Path(dataset_dir), Path(scene_file), Path(output_dir)
+    name = dataset or dataset_dir.name
+    if "nclt" in name:
+        make, date_idx = (lambda seq: datasets.NCLT(seq, dataset_dir, image_subsample)), 1
+    elif "robotcar" in name:
+        if sdk_dir is None:
+            raise ValueError("Unknown dataset: RobotCar needs sdk_dir (extrinsics, camera models)")
+        make, date_idx = (lambda seq: datasets.OxfordRobotcar(seq, dataset_dir, sdk_dir, image_subsample)), 0
+    else:
+        raise ValueError("Unknown dataset")   # prepare_scenes.py:117
+    spec = read_scene_json(scene_file)
+    sequences = [spec.map_point_clouds[date_idx].split("/")[1]] + [p.split("/")[date_idx] for p in spec.scan_point_clouds]   # :127-130
+    loaders: Dict[str, object] = {}
+
+    def frame(seq_name: str, pcl_file: str, image_files: Sequence[str], leaf: float) -> np.ndarray:
+        seq = loaders.setdefault(seq_name, make(seq_name))   # one loader (calibration, undistortion maps) per sequence
+        pcl = seq.read_pcl(filename=dataset_dir / pcl_file)
+        pcl = voxel_down_sample(pcl, leaf, device=device).astype(pcl.dtype)
+        files = [dataset_dir / f for f in image_files]
+        images = seq.read_images(filenames=files) if isinstance(seq, datasets.NCLT) else seq.read_images(files, raw=True)
+        desc = features.create_descriptors(images, seq.project_params(images), feature_generator, pcl)
+        return np.c_[pcl, desc]
+
+    map_clouds = [frame(sequences[0], p, imgs, 0.2) for p, imgs in zip(spec.map_point_clouds, spec.map_images)]       # :133-146
+    scan_clouds = [frame(sequences[i + 1], p, imgs, 0.1) for i, (p, imgs) in enumerate(zip(spec.scan_point_clouds, spec.scan_images))]
+    out = output_dir / scene_file.name.replace(".json", ".h5")
+    save_scene(out, sequences, list(spec.map_poses), map_clouds, list(spec.scan_poses), scan_clouds)                   # :166-167
+    return out
