@@ -25,9 +25,12 @@
 // TMEM allocator and, in the leader, the elected-lane MMA issuer (multicast tcgen05.commit frees the stage / publishes the
 // accumulator in both CTAs), warps 2-9 = epilogue (tcgen05.ld 32x32b.x32; warps w and w+4 share a TMEM lane quarter and
 // take alternate 32-token chunks), accumulators double-buffered in TMEM (2 x 256 columns).
-// Every kernel of the forward is launched with programmatic stream serialisation (PDL): barrier init, TMEM allocation and
-// tensor-map prefetch of launch i+1 overlap the tail of launch i; griddepcontrol.wait precedes the first global access.
-// Bound: tensor pipe for large batches; at BASELINE config 3 (6 images) one or two waves per layer.
+// Every kernel of the forward is launched with programmatic stream serialisation (PDL): barrier init, TMEM allocation,
+// tensor-map prefetch AND the weight loads of the first ring of stages of launch i+1 overlap the tail of launch i (the weights
+// do not depend on it); griddepcontrol.wait precedes the first access to anything another kernel produces.
+// Bound: the L2 -> SM operand traffic (64 B/clk per SM for a 256 x 256 x 64 step against ~42 B/clk chip-wide), then the tensor
+// pipe -- ncu: 82 % tensor pipe active at 12.8 TB/s of L2 traffic at 48 images; at BASELINE config 3 (6 images) one or two
+// waves per GEMM and fill / drain latency.  DESIGN.md 4.3.
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
