@@ -48,6 +48,24 @@ def test_vit_forward_vs_oracle(vfm, model, depth, hw, b):
     assert err.mean() < 0.02 and err.max() < 0.25, (float(err.mean()), float(err.max()))
 
 
+def test_many_images_fused_residual_equals_partial_fold(vfm, monkeypatch):
+    """With many images the proj / fc2 GEMMs keep K whole and add into the residual stream in their epilogue
+    (EPI_F32_RESID); with few, K is split and the next LayerNorm folds the partial sums.  Same expression either way:
+    the two forwards agree bit for bit, and both match the oracle."""
+    cfg = ovit.CONFIGS["vits14"]
+    sd = ovit.make_weights(cfg, seed=3)
+    imgs = _images(np.random.default_rng(8), 64, 224, 224)
+    imgs[1:] = np.roll(imgs[1:], 17, axis=2) ^ np.arange(63, dtype=np.uint8)[:, None, None, None]
+    got = vfm.ViTFeaturizer("vits14", sd).forward(imgs).cpu()
+    monkeypatch.setenv("VFMREG_VIT_RESID", "0")
+    folded = vfm.ViTFeaturizer("vits14", sd).forward(imgs).cpu()
+    assert torch.equal(got, folded)
+    pick = [0, 31, 63]
+    want = ovit.forward(sd, cfg, torch.stack([ovit.preprocess(imgs[i]) for i in pick]))
+    cos = torch.nn.functional.cosine_similarity(got[pick].flatten(0, 2), want.flatten(0, 2), dim=1)
+    assert cos.min() > 0.999, float(cos.min())   # bf16 operands through 12 blocks, as in test_vit_forward_vs_oracle
+
+
 def test_image_feature_generator_compat(vfm):
     gen = vfm.ImageFeatureGenerator("dinov2", use_featup=False, seed=1, random_init=True)
     img = _images(np.random.default_rng(0), 1, 70, 82)[0]

@@ -61,6 +61,7 @@ struct vfmreg_vit {
   float* tok_stage = nullptr;
   size_t img_stage_cap = 0, tok_stage_cap = 0;
   int use_graphs = 1;
+  bool fused_resid = true;   // VFMREG_VIT_RESID=0 at creation: always partial sums + fold (residual_gemm)
   cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the legacy default stream cannot capture)
 };
 
@@ -164,6 +165,7 @@ int vfmreg_vit_create(vfmreg_ctx* ctx, const vfmreg_vit_config* cfg, vfmreg_vit*
   VFM_CHECK_ARG(cfg->patch > 0 && cfg->patch_h > 0, "vit_create: bad patch geometry");
   VFM_CUDA(cudaSetDevice(ctx->device));
   vfmreg_vit* v = new vfmreg_vit();
+  if (const char* e = getenv("VFMREG_VIT_RESID")) v->fused_resid = e[0] != '0';
   v->ctx = ctx;
   v->cfg = *cfg;
   const int w = cfg->width, md = cfg->mlp_dim;
@@ -295,6 +297,24 @@ int vfmreg_vit_grid(const vfmreg_vit* v, int32_t img_h, int32_t img_w, int32_t* 
   return VFMREG_OK;
 }
 
+// One residual branch, x += scale * (X W^T + bias).  When the plan keeps K whole the add rides in the GEMM's epilogue and
+// nothing is pending; with K split over several units (few images: it takes the splits to fill the GPU) the units write fp32
+// partial sums and the next normalisation kernel folds them into x in a fixed order.  VFMREG_VIT_RESID=0: always the latter.
+static int residual_gemm(vfmreg_vit* v, int rows, int n, int k, const CUtensorMap& m_w, const TokenMaps& m_x, const GemmPlan& plan,
+                         const float* bias, const float* scale, const void* pf_ptr, size_t pf_bytes, Residual* pending) {
+  GemmEpilogue ep{};
+  ep.m = rows; ep.n = n; ep.k = k; ep.ldo = n;
+  if (pf_ptr) { ep.pf_ptr = (const char*)pf_ptr; ep.pf_bytes = pf_bytes; }
+  if (v->fused_resid && plan.split == 1) {
+    ep.x = v->x; ep.bias = bias; ep.scale = scale;
+    *pending = Residual{};
+    return vit_gemm(v->ctx, EPI_F32_RESID, m_w, m_x, plan, ep);
+  }
+  ep.x = v->ws;
+  *pending = Residual{v->ws, plan.split, bias, scale};
+  return vit_gemm(v->ctx, EPI_F32_PARTIAL, m_w, m_x, plan, ep);
+}
+
 static int vit_enqueue(vfmreg_vit* v, const uint8_t* images, int b, int img_h, int img_w, int gh, int gw, const float* pos,
                        float* tokens) {
   vfmreg_ctx* ctx = v->ctx;
@@ -322,20 +342,14 @@ static int vit_enqueue(vfmreg_vit* v, const uint8_t* images, int b, int img_h, i
       VFM_TRY(vit_attention_tc(ctx, v->m_qkv_attn, b, t, v->cfg.heads, w, v->ao, pf ? l.fc1_w : nullptr, (size_t)md * w * 2));
     else
       VFM_TRY(vit_attention(ctx, v->qkv, b, t, v->cfg.heads, w, v->ao));
-    ep = GemmEpilogue{};
-    ep.m = rows; ep.n = w; ep.k = w; ep.ldo = w; ep.x = v->ws;
-    VFM_TRY(vit_gemm(ctx, EPI_F32_PARTIAL, l.m_proj, v->m_ao, v->p_proj, ep));
-    pending = Residual{v->ws, v->p_proj.split, l.proj_b, l.ls1};
+    VFM_TRY(residual_gemm(v, rows, w, w, l.m_proj, v->m_ao, v->p_proj, l.proj_b, l.ls1, nullptr, 0, &pending));
     VFM_TRY(vit_layernorm_bf16(ctx, v->x, rows, w, pending, l.ln2_g, l.ln2_b, v->cfg.ln_eps, v->xn));
     ep = GemmEpilogue{};
     ep.m = rows; ep.n = md; ep.k = w; ep.ldo = md; ep.bias = l.fc1_b; ep.out_bf16 = v->hbuf;
     if (pf) { ep.pf_ptr = (const char*)l.fc2_w; ep.pf_bytes = (size_t)w * md * 2; }
     VFM_TRY(vit_gemm(ctx, EPI_BF16_BIAS_GELU, l.m_fc1, v->m_xn_fc1, v->p_fc1, ep));
-    ep = GemmEpilogue{};
-    ep.m = rows; ep.n = w; ep.k = md; ep.ldo = w; ep.x = v->ws;
-    if (nxt) { ep.pf_ptr = (const char*)nxt->qkv_w; ep.pf_bytes = (size_t)3 * w * w * 2; }
-    VFM_TRY(vit_gemm(ctx, EPI_F32_PARTIAL, l.m_fc2, v->m_h, v->p_fc2, ep));
-    pending = Residual{v->ws, v->p_fc2.split, l.fc2_b, l.ls2};
+    VFM_TRY(residual_gemm(v, rows, w, md, l.m_fc2, v->m_h, v->p_fc2, l.fc2_b, l.ls2, nxt ? nxt->qkv_w : nullptr, (size_t)3 * w * w * 2,
+                          &pending));
   }
   return vit_final_norm(ctx, v->x, b, t, w, pending, v->norm_g, v->norm_b, v->cfg.ln_eps, v->cn_g, v->cn_b, v->cfg.cn_eps, v->cfg.channel_norm,
                         tokens);

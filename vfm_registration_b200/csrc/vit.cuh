@@ -7,7 +7,7 @@
 
 namespace vfm {
 
-enum { EPI_BF16_BIAS = 0, EPI_BF16_BIAS_GELU = 1, EPI_F32_PARTIAL = 2, EPI_F32_PATCH = 3 };
+enum { EPI_BF16_BIAS = 0, EPI_BF16_BIAS_GELU = 1, EPI_F32_PARTIAL = 2, EPI_F32_PATCH = 3, EPI_F32_RESID = 4 };
 
 struct GemmEpilogue {
   int m, n, k;              // tokens (rows of X), output features (rows of W), k already padded to a multiple of 64
@@ -16,8 +16,9 @@ struct GemmEpilogue {
                                              // the tail tile (0 = none, else a multiple of 16), 256-feature blocks, K splits
   long long ldo;            // row pitch of the output in elements
   const float* bias;        // [n]
+  const float* scale;       // [n] LayerScale gamma (EPI_F32_RESID)
   const float* pos;         // [(1 + np), n] position embedding (EPI_F32_PATCH)
-  float* x;                 // EPI_F32_PATCH: fp32 residual stream; EPI_F32_PARTIAL: workspace [split][m][ldo]
+  float* x;                 // EPI_F32_PATCH / EPI_F32_RESID: fp32 residual stream; EPI_F32_PARTIAL: workspace [split][m][ldo]
   __nv_bfloat16* out_bf16;  // bf16 output (EPI_BF16_*)
   const char* pf_ptr;       // optional: byte range prefetched into L2 while this GEMM runs (the weights of a later GEMM)
   unsigned long long pf_bytes;

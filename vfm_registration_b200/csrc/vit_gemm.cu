@@ -7,6 +7,9 @@
 //                       several clusters; bias, LayerScale, residual add and the reduction over the splits are done by the
 //                       LayerNorm kernel that follows, vit_ops.cu, in a fixed order -- deterministic, and the GEMM's
 //                       epilogue is a plain coalesced store)
+//   EPI_F32_RESID       x[token][feature] += scale * (acc + bias)   (proj / fc2 when the plan does not split K: the residual
+//                       add rides in the epilogue, under the tile's MMAs, and the LayerNorm that follows only reads x --
+//                       8 B per element less HBM traffic per residual branch than partial + fold; many-image batches)
 //   EPI_F32_PATCH       x[token row] = acc + bias + pos_embed       (patch embedding; skips the CLS row of each image)
 //
 // Layout of the work ("swap-AB"): the WEIGHTS are the M operand of the MMA and the TOKENS the N operand.  A CTA pair
@@ -107,8 +110,8 @@ __device__ __forceinline__ GemmTile gemm_tile(const GemmEpilogue& ep, int u) {
 
 // One 32-token chunk of one feature (r[j] = accumulator of token tok_c + j): the epilogue's element-wise tail and store.
 template <int EPI, bool FULL>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t* r, int tok_c, int f, float bias, int split,
-                                               int valid) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t* r, int tok_c, int f, float bias, float scale,
+                                               int split, int valid) {
   if (EPI == EPI_BF16_BIAS || EPI == EPI_BF16_BIAS_GELU) {
     __nv_bfloat16* o = ep.out_bf16 + (long long)tok_c * ep.ldo + f;
 #pragma unroll
@@ -127,6 +130,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
       if (FULL || j < valid) *o = __uint_as_float(r[j]);
       o += ep.ldo;
     }
+  } else if (EPI == EPI_F32_RESID) {
+    // handled by resid_load / resid_store (the loads of x run a chunk ahead of the accumulator reads)
   } else {
     // patch row tok = img * np + p  ->  residual-stream row img * (np + 1) + 1 + p, position row 1 + p.  (img, p) of every
     // token of the chunk follow from the first one's without a carried dependency: 32 independent load / add / store chains
@@ -143,6 +148,38 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
         ep.x[out_row * ep.ldo + f] = __uint_as_float(r[j]) + bias + __ldg(ep.pos + (long long)(1 + p) * ep.n + f);
       }
     }
+  }
+}
+
+// EPI_F32_RESID: x[token][feature] += scale * (acc + bias).  The 32 values of x a thread needs for a chunk do not depend on the
+// MMAs, so they are requested before the accumulator is waited for and, inside a tile, one chunk ahead: an epilogue warp
+// always has 4 KB of reads in flight instead of taking an L2 / HBM round trip per chunk in the shadow of nothing.
+__device__ __forceinline__ int resid_valid(const GemmEpilogue& ep, const GemmTile& g, int c) {
+  return min(32, min(g.w - c * 32, ep.m - (g.tok0 + c * 32)));   // warp-uniform
+}
+__device__ __forceinline__ void resid_load(const GemmEpilogue& ep, const GemmTile& g, int c, int f, float* xv) {
+  const int valid = resid_valid(ep, g, c);
+  const float* o = ep.x + (long long)(g.tok0 + c * 32) * ep.ldo + f;
+  if (valid == 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) xv[j] = o[(long long)j * ep.ldo];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) xv[j] = j < valid ? o[(long long)j * ep.ldo] : 0.f;
+  }
+}
+// same expression as the fold in the normalisation kernel (add_residual_n with one split): identical bits either way
+__device__ __forceinline__ void resid_store(const GemmEpilogue& ep, const GemmTile& g, int c, int f, const uint32_t* r, const float* xv,
+                                            float bias, float scale) {
+  const int valid = resid_valid(ep, g, c);
+  float* o = ep.x + (long long)(g.tok0 + c * 32) * ep.ldo + f;
+  if (valid == 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[(long long)j * ep.ldo] = fmaf(scale, __uint_as_float(r[j]) + bias, xv[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) o[(long long)j * ep.ldo] = fmaf(scale, __uint_as_float(r[j]) + bias, xv[j]);
   }
 }
 
@@ -278,13 +315,38 @@ __global__ void __cluster_dims__(G_CL, 1, 1) __launch_bounds__(G_THREADS, 1)
       const GemmTile g = gemm_tile(ep, t);
       const int f = ((G_CL / 2) * g.fb + (int)pair) * 2 * G_FM + (int)rank * G_FM + q * 32 + lane;
       const bool f_live = f < ep.n;
-      float bias = 0.f;
+      float bias = 0.f, scale = 1.f;
       if (EPI != EPI_F32_PARTIAL && f_live) bias = __ldg(ep.bias + f);
+      if (EPI == EPI_F32_RESID && f_live) scale = __ldg(ep.scale + f);
       const uint32_t buf = (uint32_t)(it & 1);
-      mbar_wait(tfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
       const int n_chunks = (g.w + 31) >> 5;
+      if (EPI == EPI_F32_RESID) {
+        constexpr int CSTEP = G_EPI_WARPS / 4;
+        float xa[32], xb[32];
+        if (f_live && half < n_chunks) resid_load(ep, g, half, f, xa);
+        mbar_wait(tfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = half; c < n_chunks; c += CSTEP) {
+          const bool more = f_live && c + CSTEP < n_chunks;
+          if (more) resid_load(ep, g, c + CSTEP, f, xb);
+          uint32_t r[32];
+          tc_ld32(t_addr + c * 32, r);
+          tc_wait_ld();
+          if (f_live) resid_store(ep, g, c, f, r, xa, bias, scale);
+          if (more) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xa[j] = xb[j];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
+        continue;
+      }
+      mbar_wait(tfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += G_EPI_WARPS / 4) {
         uint32_t r[32];
@@ -296,9 +358,9 @@ __global__ void __cluster_dims__(G_CL, 1, 1) __launch_bounds__(G_THREADS, 1)
         // full chunks run straight-line code (32 independent elements in flight); only the last chunk of a tail tile /
         // of the token range takes the predicated path
         if (valid == 32)
-          epilogue_chunk<EPI, true>(ep, r, tok_c, f, bias, g.split, 32);
+          epilogue_chunk<EPI, true>(ep, r, tok_c, f, bias, scale, g.split, 32);
         else
-          epilogue_chunk<EPI, false>(ep, r, tok_c, f, bias, g.split, valid);
+          epilogue_chunk<EPI, false>(ep, r, tok_c, f, bias, scale, g.split, valid);
       }
       tc_fence_before();
       __syncwarp();
@@ -448,6 +510,7 @@ int vit_gemm(vfmreg_ctx* ctx, int epi, const CUtensorMap& w, const TokenMaps& x,
     case EPI_BF16_BIAS_GELU: return launch_gemm<EPI_BF16_BIAS_GELU>(ctx, w, x.full, x.tail, ep, grid);
     case EPI_F32_PARTIAL: return launch_gemm<EPI_F32_PARTIAL>(ctx, w, x.full, x.tail, ep, grid);
     case EPI_F32_PATCH: return launch_gemm<EPI_F32_PATCH>(ctx, w, x.full, x.tail, ep, grid);
+    case EPI_F32_RESID: return launch_gemm<EPI_F32_RESID>(ctx, w, x.full, x.tail, ep, grid);
   }
   set_error("vit_gemm: bad epilogue %d", epi);
   return VFMREG_ERR_ARG;
