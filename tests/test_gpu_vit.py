@@ -30,6 +30,7 @@ def _images(rng, b, h, w):
 
 @pytest.mark.parametrize("model,depth,hw,b", [("vits14", 12, (224, 224), 2), ("vits14", 12, (70, 82), 1), ("vitb14", 12, (224, 224), 1),
                                               ("vitl14", 24, (224, 224), 1),
+                                              ("vits14", 12, (224, 112), 3),   # 16 x 8 patches + CLS = 129 tokens: one full query block + 1 row
                                               ("vits14", 12, (224, 320), 2)])   # 16 x 22 patches + CLS = 353 tokens: the mma.sync attention (> 320 tokens)
 def test_vit_forward_vs_oracle(vfm, model, depth, hw, b):
     cfg = ovit.CONFIGS[model]

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vfm_registration_b200 as v  # noqa: E402
 from vfm_registration_b200 import _lib  # noqa: E402
 
-KINDS = {0: "gemm qkv", 1: "gemm fc1+gelu", 2: "gemm partial", 3: "gemm patch", 10: "layernorm", 11: "attention"}
+KINDS = {0: "gemm qkv", 1: "gemm fc1+gelu", 2: "gemm partial", 3: "gemm patch", 4: "gemm resid", 10: "layernorm", 11: "attention"}
 model = sys.argv[1] if len(sys.argv) > 1 else "vitl14"
 b = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 lib = _lib.load()
@@ -72,7 +72,7 @@ prev_end = None
 seq = {}
 for k, L in enumerate(launches):
     name = KINDS.get(L["kind"], str(L["kind"]))
-    if L["kind"] == 2:
+    if L["kind"] in (2, 4):
         name += " (proj)" if k and launches[k - 1]["kind"] == 11 else " (fc2)"
     busy = (L["end"] - L["start"]) / 1e3
     gap = (L["start"] - prev_end) / 1e3 if prev_end is not None else 0.0
@@ -95,3 +95,18 @@ if len(marks):   # trace_mark() timestamps of CTA 0 (kernel-internal phases), fi
         sel = m[(m[:, 1] >= first[0][1])][:40]
         print("# marks of CTA 0 (kind: us since the first):", " ".join(f"{int(k)}:{(tt - sel[0][1]) / 1e3:.2f}" for k, tt in zip(sel[:, 0], sel[:, 1])))
 print(f"# sum {tot:.1f} us (final norm / preprocess / cls rows are not traced)")
+dist = os.environ.get("VIT_TRACE_DIST")   # kernel kind (e.g. 11 = attention): per-CTA start / duration spread of its first launches
+if dist:
+    shown = 0
+    for L in launches:
+        if L["kind"] != int(dist):
+            continue
+        sel = (kind == L["kind"]) & (t1 >= L["start"]) & (t2 <= L["end"])
+        st, du = (t1[sel] - L["start"]) / 1e3, (t2[sel] - t1[sel]) / 1e3
+        en = (t2[sel] - L["start"]) / 1e3
+        q = lambda a: " ".join(f"{x:.1f}" for x in np.percentile(a, [0, 10, 50, 90, 100]))
+        print(f"# kind {dist} launch {shown}: {sel.sum()} CTAs; start after first [{q(st)}] us, duration [{q(du)}], exit [{q(en)}] (min p10 p50 p90 max)")
+        shown += 1
+        if shown == 4:
+            break
+

@@ -16,9 +16,9 @@
 //                  columns 448 .. 511
 //   epilogue       the same warps read O (32 channels each), multiply by 1 / (sum of the two halves) and store 64
 //                  contiguous bytes per thread.
-// Thread 0 issues the TMA loads and the MMAs between its own softmax work (the stages of a query block run one after the
-// other anyway: S and P of two blocks do not fit TMEM / shared memory at 257 keys); the S MMAs of block i + 1 are queued
-// right behind the P V MMAs of block i and overlap its epilogue; Q blocks are double buffered.  The bounds of this kernel are
+// Warp 0 (one elected lane, warp-uniform code) issues the TMA loads and the MMAs between its own softmax work (the stages of a query block run one after the
+// other anyway: S and P of two blocks do not fit TMEM / shared memory at 257 keys); the S MMAs of block i + 1 are issued as
+// soon as every warp holds S(i) in registers and run under the exponentials of block i; Q blocks are double buffered.  The bounds of this kernel are
 // the TMEM read of S (~64 B/clk per SM) and the exponentials (MUFU, 16 per clk per SM), about 2200 cycles each per block.  Masked: keys >= t (scores), queries >= t (never
 // stored).  Token counts above 320 use attention_kernel (vit_ops.cu, mma.sync).
 #include <cuda_bf16.h>
@@ -32,8 +32,14 @@ namespace vfm {
 constexpr int AT_DH = 64, AT_QB = 128;
 constexpr int AT_MAX_CH = 5;                  // 32-key chunks per softmax warp (two warps share a row)
 constexpr int AT_MAX_T = AT_MAX_CH * 2 * 32;   // 320 tokens per image
-constexpr int AT_FEW = 4;                     // query blocks with at most this many real rows take the shared-row path
-constexpr uint32_t AT_O_COL = 448;   // TMEM column of the O accumulator (S uses columns 0 .. 319)
+constexpr int AT_FEW = 4;                     // a last query block with at most this many real rows is computed without the tensor core
+// O = P V is a chain of keys / 16 MMAs of 128 x 64 x 16 into one accumulator: ~70 cycles each, measured (0.6 us for the 17 of
+// a 257-token image) against 32 cycles of tensor work.  Not the dependency between them: dealt round-robin over AT_NACC = 3
+// independent accumulators (TMEM columns 320 / 384 / 448, added up by the epilogue) the chain took exactly as long and the
+// epilogue 0.1 us longer (profiles/r2_vit_attn_steps.txt) -- it is the operand read: 4 KB of P + 2 KB of V out of shared
+// memory per MMA.  AT_NACC stays 1.
+constexpr int AT_NACC = 1;
+constexpr uint32_t AT_O_COL = 512 - AT_NACC * 64;   // first TMEM column of the O accumulators
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -72,20 +78,26 @@ __global__ void __launch_bounds__(256, 1)
   uint8_t* smem = smem_raw + (base - raw);
   const AttnSmem L = attn_smem(t);
   const uint32_t sK = base + L.k, sV = base + L.v, sQ = base + L.q, sP = base + L.p, bars = base + L.bars;
-  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40;
+  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, bar_sfree = bars + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool leader = threadIdx.x == 0;             // issues every TMA load and MMA of the CTA
+  const bool leader = threadIdx.x == 0;             // barrier init, trace marks
+  // Warp 0 issues every TMA load and MMA of the CTA, as a WHOLE warp with one elected lane: the descriptors are then
+  // warp-uniform values in uniform registers.  Issued from a single-thread branch (threadIdx.x == 0) every tcgen05.mma was
+  // wrapped by the compiler in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop of ~28 dependent instructions -- 58 ns per MMA,
+  // 1 us for the 17 MMAs of one P V product, on the critical path of every query block (profiles/r2_vit_attn_steps.txt).
+  const bool issuer = warp == 0;
   const int head = blockIdx.x, img = blockIdx.y;
   const int kp = (t + 15) / 16 * 16;                // keys covered by the MMAs (scores of keys >= t are masked, their P is 0)
   const int n_qb = (t + AT_QB - 1) / AT_QB;
+  const int n_acc = kp / 16 < AT_NACC ? kp / 16 : AT_NACC;
   const int row0 = img * t;                         // first token row of this image in the QKV matrix
   const int rows64 = (t + 63) / 64 * 64;
 
   TraceScope trace(11);
   TraceMarks marks;   // phases of CTA 0, thread 0
   pdl_launch_dependents();
-  if (leader) {
+  if (issuer && elect_one()) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
     mbar_init(bar_kv, 1);
     mbar_init(bar_q0, 1);
@@ -93,6 +105,7 @@ __global__ void __launch_bounds__(256, 1)
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 8);
     mbar_init(bar_o, 1);
+    mbar_init(bar_sfree, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512u);
@@ -103,46 +116,52 @@ __global__ void __launch_bounds__(256, 1)
   pdl_wait();
   trace.waited();
 
-  if (leader) l2_prefetch_slice(pf_ptr, pf_bytes, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
+  if (threadIdx.x == 224)   // a thread of the last warp: off the issuer's path to the K / V / Q loads
+    l2_prefetch_slice(pf_ptr, pf_bytes, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
   const int n_lo = kp < 256 ? kp : 256, n_hi = kp - n_lo;
   const uint32_t idesc_lo = umma_idesc_f16(AT_QB, n_lo, 1), idesc_hi = umma_idesc_f16(AT_QB, n_hi > 0 ? n_hi : 16, 1);
   const uint32_t idesc_pv = umma_idesc_f16(AT_QB, AT_DH, 1) | (1u << 16);   // B (= V) is MN-major: channels contiguous
   const uint64_t dK = umma_desc_k_sw128(sK), dV = umma_desc_k_sw128(sV), dP = umma_desc_k_sw128(sP);
-  auto load_q = [&](int qb) {   // leader: query block qb -> buffer qb & 1
+  auto load_q = [&](int qb) {   // one elected lane: query block qb -> buffer qb & 1
     const uint32_t nb = (uint32_t)(qb & 1);
     mbar_expect_tx(bar_q0 + 8 * nb, AT_QB * 128u);
     tma_load_2d(sQ + nb * (AT_QB * 128), &map_qkv, bar_q0 + 8 * nb, head * AT_DH, row0 + qb * AT_QB);
     tma_load_2d(sQ + nb * (AT_QB * 128) + 64 * 128, &map_qkv, bar_q0 + 8 * nb, head * AT_DH, row0 + qb * AT_QB + 64);
   };
-  auto issue_s = [&](int qb) {   // leader: S = Q(qb) K^T into TMEM columns 0 .. kp
+  auto issue_s = [&](int qb) {   // warp 0, converged: S = Q(qb) K^T into TMEM columns 0 .. kp
     const uint32_t qbuf = (uint32_t)(qb & 1);
     mbar_wait(bar_q0 + 8 * qbuf, (uint32_t)((qb >> 1) & 1));
     tc_fence_after();
     const uint64_t dQ = umma_desc_k_sw128(sQ + qbuf * (AT_QB * 128));
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < AT_DH / 16; ++k) {
-      tc_mma_f16(tmem_base, dQ + (uint64_t)(k * 2), dK + (uint64_t)(k * 2), idesc_lo, k != 0 ? 1u : 0u);
-      if (n_hi > 0)   // keys 256 ..: rows 256.. of the K tile = +32 KB
-        tc_mma_f16(tmem_base + 256, dQ + (uint64_t)(k * 2), dK + (uint64_t)((256 * 128) >> 4) + (uint64_t)(k * 2), idesc_hi,
-                   k != 0 ? 1u : 0u);
+      for (int k = 0; k < AT_DH / 16; ++k) {
+        tc_mma_f16(tmem_base, dQ + (uint64_t)(k * 2), dK + (uint64_t)(k * 2), idesc_lo, k != 0 ? 1u : 0u);
+        if (n_hi > 0)   // keys 256 ..: rows 256.. of the K tile = +32 KB
+          tc_mma_f16(tmem_base + 256, dQ + (uint64_t)(k * 2), dK + (uint64_t)((256 * 128) >> 4) + (uint64_t)(k * 2), idesc_hi,
+                     k != 0 ? 1u : 0u);
+      }
+      tc_commit(bar_s);
     }
-    tc_commit(bar_s);
+    __syncwarp();
   };
-  if (leader) {
-    mbar_expect_tx(bar_kv, 2u * (uint32_t)rows64 * 128u);
-    load_q(0);   // Q first: the S MMAs need Q and K
-    for (int r = 0; r < rows64; r += 64) tma_load_2d(sK + r * 128, &map_qkv, bar_kv, width + head * AT_DH, row0 + r);
-    for (int r = 0; r < rows64; r += 64) tma_load_2d(sV + r * 128, &map_qkv, bar_kv, 2 * width + head * AT_DH, row0 + r);
-    if (n_qb > 1) load_q(1);
+  if (issuer) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_kv, 2u * (uint32_t)rows64 * 128u);
+      load_q(0);   // Q first: the S MMAs need Q and K
+      for (int r = 0; r < rows64; r += 64) tma_load_2d(sK + r * 128, &map_qkv, bar_kv, width + head * AT_DH, row0 + r);
+      for (int r = 0; r < rows64; r += 64) tma_load_2d(sV + r * 128, &map_qkv, bar_kv, 2 * width + head * AT_DH, row0 + r);
+      if (n_qb > 1) load_q(1);
+    }
+    __syncwarp();
     mbar_wait(bar_kv, 0);
-    marks.mark(100);
+    if (leader) marks.mark(100);
     issue_s(0);
-    marks.mark(101);
+    if (leader) marks.mark(101);
   }
-  __syncwarp();
 
   // ===== softmax + epilogue: all 8 warps.  TMEM lane quarter = warp % 4 (a hardware rule); the two warps of a quarter
-  // (warp, warp + 4) own the same 32 query rows and split the keys in 32-wide chunks (the first takes the larger half) and the
+  // (warp, warp + 4) own the same 32 query rows and split the keys in 32-wide chunks (the second takes the odd one) and the
   // 64 output channels; row maximum and row sum are exchanged through shared memory. =====
   const int q4 = warp & 3, half = warp >> 2;
   const int r = q4 * 32 + lane;                    // row inside the query block = TMEM lane
@@ -151,46 +170,53 @@ __global__ void __launch_bounds__(256, 1)
   const uint32_t p_row = sP + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
   float* xmax = reinterpret_cast<float*>(smem + L.bars + 128);   // [2][128]
   float* xsum = xmax + 2 * AT_QB;                                  // [2][128]
-  const int n_chunks = (kp + 31) >> 5, c_split = (n_chunks + 1) >> 1;
+  // the second warp of a pair takes the odd chunk: it is the one with the partial last chunk (257 tokens: 4 full chunks against
+  // 4 full + 1 key), and warp 0 of the first halves also issues the MMAs
+  const int n_chunks = (kp + 31) >> 5, c_split = n_chunks >> 1;
   const int c_begin = half ? c_split : 0, c_end = half ? n_chunks : c_split;
   const int pair_bar = 1 + q4;   // named barrier of the two warps of this quarter (0 is __syncthreads)
   for (int qb = 0; qb < n_qb; ++qb) {
     const int q_row = qb * AT_QB + r;
     const bool warp_live = qb * AT_QB + q4 * 32 < t;   // warp-uniform: some row of this warp is a real query
-    mbar_wait(bar_s, (uint32_t)(qb & 1));
-    if (leader) marks.mark(110);
-    tc_fence_after();
     const int live_rows = t - qb * AT_QB;   // real query rows of this block (>= 128: all)
-    // the scores of this thread's keys are read from TMEM ONCE (TMEM reads run at ~64 B/clk per SM: a second pass over the
-    // 128 x keys fp32 tile would cost as much as all the exponentials) and stay in registers: up to AT_MAX_CH chunks
-    uint32_t v[AT_MAX_CH][32];
-    if (warp_live) {
-#pragma unroll
-      for (int i = 0; i < AT_MAX_CH; ++i)
-        if (c_begin + i < c_end) tc_ld32(t_lane + (c_begin + i) * 32, v[i]);
-      tc_wait_ld();
-    }
     if (live_rows <= AT_FEW) {
-      // ---- a block with a handful of real rows (the 257th token of a 16 x 16 patch grid): one thread per row would spend a
-      // full block's worth of MUFU issue slots on them (an exp2 costs the warp 8 cycles however few lanes are active).  The
-      // rows' scores go through shared memory instead and all 256 threads share each row: thread j takes keys j and j + 256.
-      float* srow = xsum + 2 * AT_QB;   // [AT_FEW][AT_MAX_T] scores, then [8] per-warp partials
-      float* wpart = srow + AT_FEW * AT_MAX_T;
-      if (q4 == 0) {
-        if (lane < live_rows) {
-#pragma unroll
-          for (int i = 0; i < AT_MAX_CH; ++i)
-            if (c_begin + i < c_end) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) srow[lane * AT_MAX_T + (c_begin + i) * 32 + j] = __uint_as_float(v[i][j]);
-            }
-        }
-      }
-      asm volatile("bar.sync 9, 256;" ::: "memory");
+      // ---- the last block when it holds a handful of real rows (the 257th token of a 16 x 16 patch grid).  As a 128-row block
+      // it cost 2.7 us of the CTA's 15.8 (S and P V MMAs, the exponentials of one thread per row); here no tensor core is
+      // involved: all 256 threads share each row -- thread j scores keys j and j + 256 against the K tile in shared memory,
+      // the block reduces maximum and sum, and P V is 8 key slices x 32 channel pairs over the V tile.
+      float* srow = xsum + 2 * AT_QB;   // [AT_MAX_T] probabilities of the row (bf16-rounded, like the P tile of a full block)
+      float* wpart = srow + AT_FEW * AT_MAX_T;   // [8] per-warp partials
+      float* obuf = xmax;   // [8][64] partial outputs (the row max / sum exchange area of the full blocks: 512 floats)
       const int tid = threadIdx.x;
+      mbar_wait(bar_kv, 0);   // every thread reads the K / V tiles itself here: each orders its reads behind the TMA writes
+      mbar_wait(bar_q0 + 8 * (uint32_t)(qb & 1), (uint32_t)((qb >> 1) & 1));   // the block's Q rows have landed
+      auto lo = [](uint32_t u) { return __uint_as_float(u << 16); };
+      auto hi = [](uint32_t u) { return __uint_as_float(u & 0xffff0000u); };
       for (int row = 0; row < live_rows; ++row) {
-        const float s0 = tid < t ? srow[row * AT_MAX_T + tid] : -INFINITY;
-        const float s1 = tid + 256 < t ? srow[row * AT_MAX_T + tid + 256] : -INFINITY;
+        // Q row `row` of the block: 128 B, 16-byte chunks XOR-swizzled with the row index (rows < 8: one swizzle atom)
+        const uint8_t* qp = smem + L.q + (uint32_t)(qb & 1) * (AT_QB * 128) + row * 128;
+        float qf[AT_DH];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint4 u = *reinterpret_cast<const uint4*>(qp + ((ch ^ (row & 7)) << 4));
+          qf[8 * ch + 0] = lo(u.x); qf[8 * ch + 1] = hi(u.x); qf[8 * ch + 2] = lo(u.y); qf[8 * ch + 3] = hi(u.y);
+          qf[8 * ch + 4] = lo(u.z); qf[8 * ch + 5] = hi(u.z); qf[8 * ch + 6] = lo(u.w); qf[8 * ch + 7] = hi(u.w);
+        }
+        auto score = [&](int key) {
+          const uint8_t* kr = smem + L.k + key * 128;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 u = *reinterpret_cast<const uint4*>(kr + ((ch ^ (key & 7)) << 4));
+            a0 = fmaf(qf[8 * ch + 0], lo(u.x), a0); a1 = fmaf(qf[8 * ch + 1], hi(u.x), a1);
+            a2 = fmaf(qf[8 * ch + 2], lo(u.y), a2); a3 = fmaf(qf[8 * ch + 3], hi(u.y), a3);
+            a0 = fmaf(qf[8 * ch + 4], lo(u.z), a0); a1 = fmaf(qf[8 * ch + 5], hi(u.z), a1);
+            a2 = fmaf(qf[8 * ch + 6], lo(u.w), a2); a3 = fmaf(qf[8 * ch + 7], hi(u.w), a3);
+          }
+          return (a0 + a1) + (a2 + a3);
+        };
+        const float s0 = tid < t ? score(tid) : -INFINITY;
+        const float s1 = tid + 256 < t ? score(tid + 256) : -INFINITY;
         float mx = fmaxf(s0, s1);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
@@ -205,29 +231,54 @@ __global__ void __launch_bounds__(256, 1)
         float sum = p0 + p1;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (tid < t) srow[tid] = __bfloat162float(__float2bfloat16(p0));
+        if (tid + 256 < t) srow[tid + 256] = __bfloat162float(__float2bfloat16(p1));
         asm volatile("bar.sync 9, 256;" ::: "memory");   // every thread has read the maxima
         if (lane == 0) wpart[warp] = sum;
-        // P[row][key] (bf16) at its swizzled place: key block key / 64, 16-byte chunk (key % 64) / 8 XOR row % 8
-        const uint32_t prow = sP + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
-        auto put = [&](int key, float p) {
-          if (key < kp) {
-            const uint32_t addr = prow + (uint32_t)(key >> 6) * (AT_QB * 128) + (uint32_t)(((((key & 63) >> 3) ^ (row & 7)) << 4) + (key & 7) * 2);
-            const __nv_bfloat16 h = __float2bfloat16(p);
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
-          }
-        };
-        put(tid, p0);
-        put(tid + 256, p1);
-        asm volatile("bar.sync 9, 256;" ::: "memory");
-        if (tid == 0) {
-          float tot = wpart[0];
-          for (int w = 1; w < 8; ++w) tot += wpart[w];   // fixed order: deterministic
-          xsum[row] = tot;
-          xsum[AT_QB + row] = 0.f;
+        // O[row][2 c2, 2 c2 + 1] over the keys = part (mod 8): V rows are 128 B, chunks XOR-swizzled with key % 8 = part
+        const int c2 = tid & 31, part = tid >> 5;
+        const uint8_t* vp = smem + L.v + ((((c2 >> 2) ^ part) << 4) + (c2 & 3) * 4);
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll 8
+        for (int key = part; key < t; key += 8) {   // unrolled: the loads of 8 keys in flight, not one round trip per key
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(vp + key * 128);
+          const float pk = srow[key];
+          o0 = fmaf(pk, lo(u), o0);
+          o1 = fmaf(pk, hi(u), o1);
         }
+        obuf[part * AT_DH + 2 * c2] = o0;
+        obuf[part * AT_DH + 2 * c2 + 1] = o1;
+        asm volatile("bar.sync 9, 256;" ::: "memory");
+        if (tid < AT_DH) {
+          float tot = wpart[0], o = obuf[tid];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) {   // fixed order: deterministic
+            tot += wpart[w];
+            o += obuf[w * AT_DH + tid];
+          }
+          out[(long long)(row0 + qb * AT_QB + row) * width + head * AT_DH + tid] = __float2bfloat16(o / tot);
+        }
+        asm volatile("bar.sync 9, 256;" ::: "memory");   // srow / wpart / obuf are free for the next row
       }
-      asm volatile("bar.sync 9, 256;" ::: "memory");   // the row sums are visible to the epilogue's threads
-    } else
+      break;
+    }
+    mbar_wait(bar_s, (uint32_t)(qb & 1));
+    if (leader) marks.mark(110);
+    tc_fence_after();
+    // the scores of this thread's keys are read from TMEM ONCE (TMEM reads run at ~64 B/clk per SM: a second pass over the
+    // 128 x keys fp32 tile would cost as much as all the exponentials) and stay in registers: up to AT_MAX_CH chunks
+    uint32_t v[AT_MAX_CH][32];
+    if (warp_live) {
+#pragma unroll
+      for (int i = 0; i < AT_MAX_CH; ++i)
+        if (c_begin + i < c_end) tc_ld32(t_lane + (c_begin + i) * 32, v[i]);
+      tc_wait_ld();
+    }
+    // S(qb) now lives in registers: its TMEM columns are free for S(qb + 1), which warp 0 issues as soon as all 8 warps
+    // are here -- those MMAs then run under the exponentials instead of between the P V product and the next block
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_sfree);
     if (warp_live) {
       float mx = -INFINITY;
 #pragma unroll
@@ -247,8 +298,20 @@ __global__ void __launch_bounds__(256, 1)
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       mx = fmaxf(xmax[r], xmax[AT_QB + r]);
       if (leader) marks.mark(111);
+      if (issuer && t - (qb + 1) * AT_QB > AT_FEW) {   // the next block exists and is not on the few-rows path
+        mbar_wait(bar_sfree, (uint32_t)(qb & 1));
+        issue_s(qb + 1);
+        if (qb + 2 < n_qb) {   // into the buffer S(qb) read; those MMAs completed before bar_s(qb)
+          if (elect_one()) load_q(qb + 2);
+          __syncwarp();
+        }
+        if (leader) marks.mark(106);
+      }
       const float mb = -mx * sc;
-      // ---- p = exp2((s - max) * sc) -> row sum (fp32) and bf16 P tile
+      // ---- p = exp2((s - max) * sc) -> row sum (fp32) and bf16 P tile.  ~1.4 us per block for a warp's 4 - 5 chunks: neither
+      // the MUFU pipe (evaluating every second exponential by a polynomial on the FMA pipe changed nothing) nor the issue
+      // slots (20 % busy) bound it, but the latency of two warps per scheduler at 255 registers; issuing the 32 MUFU.EX2 of a
+      // chunk back to back in a pass of their own was slower (profiles/r2_vit_attn_steps.txt).
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < AT_MAX_CH; ++i)
@@ -257,13 +320,16 @@ __global__ void __launch_bounds__(256, 1)
           const int valid = t - c * 32;
           uint32_t pk[16];
           if (valid >= 32) {
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float p0 = ex2_approx(fmaf(__uint_as_float(v[i][j]), sc, mb));
               const float p1 = ex2_approx(fmaf(__uint_as_float(v[i][j + 1]), sc, mb));
-              sum += p0 + p1;
+              s0 += p0;
+              s1 += p1;
               pk[j >> 1] = pack_bf16x2(p0, p1);
             }
+            sum += s0 + s1;
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
@@ -293,26 +359,28 @@ __global__ void __launch_bounds__(256, 1)
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
-    if (leader) {
-      // every warp is done with S(qb) and has written its part of P(qb): O = P V, then S of the next block right behind it
-      // (it overlaps the epilogue below; its Q block has been loaded while this block ran)
+    if (issuer) {
+      // every warp has written its part of P(qb) (and read O(qb - 1)): O = P V
       mbar_wait(bar_p, (uint32_t)(qb & 1));
-      marks.mark(102);
+      if (leader) marks.mark(102);
       tc_fence_after();
-      for (int kk = 0; kk < kp / 16; ++kk) {
-        // A: 16 keys of P = 32 B inside the 128 B swizzle row of key block kk / 4; B: 16 key rows of V = 2 x 1024 B
-        const uint64_t da = dP + (uint64_t)(((kk >> 2) * (AT_QB * 128)) >> 4) + (uint64_t)((kk & 3) * 2);
-        const uint64_t db = dV + (uint64_t)((kk * 2048) >> 4);
-        tc_mma_f16(tmem_base + AT_O_COL, da, db, idesc_pv, kk != 0 ? 1u : 0u);
+      if (elect_one()) {
+        for (int kk = 0; kk < kp / 16; ++kk) {
+          // A: 16 keys of P = 32 B inside the 128 B swizzle row of key block kk / 4; B: 16 key rows of V = 2 x 1024 B
+          const uint64_t da = dP + (uint64_t)(((kk >> 2) * (AT_QB * 128)) >> 4) + (uint64_t)((kk & 3) * 2);
+          const uint64_t db = dV + (uint64_t)((kk * 2048) >> 4);
+          tc_mma_f16(tmem_base + AT_O_COL + (uint32_t)(kk % AT_NACC) * 64u, da, db, idesc_pv, kk >= AT_NACC ? 1u : 0u);
+        }
+        tc_commit(bar_o);
       }
-      tc_commit(bar_o);
-      if (qb + 1 < n_qb) {
-        issue_s(qb + 1);
-        if (qb + 2 < n_qb) load_q(qb + 2);   // into the buffer S(qb) read; those MMAs completed before bar_s(qb)
-      }
-      marks.mark(103);
+      __syncwarp();
+      if (leader) marks.mark(104);
+#ifdef VFM_ATTN_PROBE   // trace experiment: how long after the last issue do the P V MMAs complete?
+      mbar_wait(bar_o, (uint32_t)(qb & 1));
+      if (leader) marks.mark(105);
+#endif
+      if (leader) marks.mark(103);
     }
-    __syncwarp();
     mbar_wait(bar_o, (uint32_t)(qb & 1));
     if (leader) marks.mark(113);
     tc_fence_after();
@@ -322,6 +390,15 @@ __global__ void __launch_bounds__(256, 1)
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // both partial sums of the row are in shared memory
       const float inv_sum = 1.f / (xsum[r] + xsum[AT_QB + r]);
       tc_wait_ld();
+#pragma unroll
+      for (int a = 1; a < AT_NACC; ++a)
+        if (a < n_acc) {   // warp-uniform: accumulators the chain reached (all of them from 48 keys on)
+          uint32_t o2[32];
+          tc_ld32(t_lane + AT_O_COL + a * 64 + half * 32, o2);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(o2[j]));
+        }
       if (q_row < t) {
         __nv_bfloat16* dst = out + (long long)(row0 + q_row) * width + head * AT_DH + half * 32;
 #pragma unroll
