@@ -148,7 +148,10 @@ __device__ __forceinline__ void add_residual(float4* v, int nv, const Residual& 
   }
 }
 
-__global__ void __launch_bounds__(256, 2)
+// HAS_RES = false (nothing pending: the GEMM before added its branch into x itself, EPI_F32_RESID) holds one row copy instead
+// of two: 4 CTAs per SM instead of 2 keep twice the bytes in flight -- this kernel is pure HBM / L2 traffic.
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, HAS_RES ? 2 : 4)
     layernorm_bf16_kernel(float* __restrict__ x, int rows, int width, const Residual res, const float* __restrict__ g,
                           const float* __restrict__ b, float eps, __nv_bfloat16* __restrict__ out) {
   TraceScope trace(10);
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
   for (int i = 0; i < LN_MAX_V4; ++i)
     if (i < nv) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
-  if (res.ws) {
+  if (HAS_RES) {
     add_residual(v, nv, res, row, rows, width, lane);
 #pragma unroll
     for (int i = 0; i < LN_MAX_V4; ++i)
@@ -189,7 +192,10 @@ __global__ void __launch_bounds__(256, 2)
 int vit_layernorm_bf16(vfmreg_ctx* ctx, float* x, int rows, int width, const Residual& res, const float* g, const float* b, float eps,
                        __nv_bfloat16* out) {
   VFM_CHECK_ARG(width % 128 == 0 && width <= 128 * LN_MAX_V4, "layernorm: width %d unsupported", width);
-  VFM_CUDA(launch_pdl(layernorm_bf16_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, ctx->stream, x, rows, width, res, g, b, eps, out));
+  if (res.ws)
+    VFM_CUDA(launch_pdl(layernorm_bf16_kernel<true>, dim3(ceil_div(rows, 8)), dim3(256), 0, ctx->stream, x, rows, width, res, g, b, eps, out));
+  else
+    VFM_CUDA(launch_pdl(layernorm_bf16_kernel<false>, dim3(ceil_div(rows, 8)), dim3(256), 0, ctx->stream, x, rows, width, res, g, b, eps, out));
   return launch_check(ctx, "layernorm_bf16_kernel");
 }
 
