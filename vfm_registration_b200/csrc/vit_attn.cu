@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256, 1)
   uint8_t* smem = smem_raw + (base - raw);
   const AttnSmem L = attn_smem(t);
   const uint32_t sK = base + L.k, sV = base + L.v, sQ = base + L.q, sP = base + L.p, bars = base + L.bars;
-  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, bar_sfree = bars + 48;
+  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40, bar_sfree = bars + 48, bar_v = bars + 56;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool leader = threadIdx.x == 0;             // barrier init, trace marks
@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256, 1)
   pdl_launch_dependents();
   if (issuer && elect_one()) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
-    mbar_init(bar_kv, 1);
+    mbar_init(bar_kv, 1);   // K tile (S needs Q and K only; V has its own barrier and lands under the first block's softmax)
+    mbar_init(bar_v, 1);
     mbar_init(bar_q0, 1);
     mbar_init(bar_q0 + 8, 1);
     mbar_init(bar_s, 1);
@@ -147,10 +148,11 @@ __global__ void __launch_bounds__(256, 1)
   };
   if (issuer) {
     if (elect_one()) {
-      mbar_expect_tx(bar_kv, 2u * (uint32_t)rows64 * 128u);
+      mbar_expect_tx(bar_kv, (uint32_t)rows64 * 128u);
+      mbar_expect_tx(bar_v, (uint32_t)rows64 * 128u);
       load_q(0);   // Q first: the S MMAs need Q and K
       for (int r = 0; r < rows64; r += 64) tma_load_2d(sK + r * 128, &map_qkv, bar_kv, width + head * AT_DH, row0 + r);
-      for (int r = 0; r < rows64; r += 64) tma_load_2d(sV + r * 128, &map_qkv, bar_kv, 2 * width + head * AT_DH, row0 + r);
+      for (int r = 0; r < rows64; r += 64) tma_load_2d(sV + r * 128, &map_qkv, bar_v, 2 * width + head * AT_DH, row0 + r);
       if (n_qb > 1) load_q(1);
     }
     __syncwarp();
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(256, 1)
       float* obuf = xmax;   // [8][64] partial outputs (the row max / sum exchange area of the full blocks: 512 floats)
       const int tid = threadIdx.x;
       mbar_wait(bar_kv, 0);   // every thread reads the K / V tiles itself here: each orders its reads behind the TMA writes
+      mbar_wait(bar_v, 0);
       mbar_wait(bar_q0 + 8 * (uint32_t)(qb & 1), (uint32_t)((qb >> 1) & 1));   // the block's Q rows have landed
       auto lo = [](uint32_t u) { return __uint_as_float(u << 16); };
       auto hi = [](uint32_t u) { return __uint_as_float(u & 0xffff0000u); };
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(256, 1)
     if (issuer) {
       // every warp has written its part of P(qb) (and read O(qb - 1)): O = P V
       mbar_wait(bar_p, (uint32_t)(qb & 1));
+      mbar_wait(bar_v, 0);   // (completes once, during the first block)
       if (leader) marks.mark(102);
       tc_fence_after();
       if (elect_one()) {

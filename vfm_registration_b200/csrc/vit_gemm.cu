@@ -324,6 +324,7 @@ __global__ void __cluster_dims__(G_CL, 1, 1) __launch_bounds__(G_THREADS, 1)
       if (EPI == EPI_F32_RESID) {
         constexpr int CSTEP = G_EPI_WARPS / 4;
         float xa[32], xb[32];
+        // (an L2 prefetch of the tile's remaining x lines at this point changed nothing for proj and cost fc2 5 %: not done)
         if (f_live && half < n_chunks) resid_load(ep, g, half, f, xa);
         mbar_wait(tfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
         tc_fence_after();
