@@ -16,11 +16,16 @@
 //                  columns 448 .. 511
 //   epilogue       the same warps read O (32 channels each), multiply by 1 / (sum of the two halves) and store 64
 //                  contiguous bytes per thread.
-// Warp 0 (one elected lane, warp-uniform code) issues the TMA loads and the MMAs between its own softmax work (the stages of a query block run one after the
-// other anyway: S and P of two blocks do not fit TMEM / shared memory at 257 keys); the S MMAs of block i + 1 are issued as
-// soon as every warp holds S(i) in registers and run under the exponentials of block i; Q blocks are double buffered.  The bounds of this kernel are
-// the TMEM read of S (~64 B/clk per SM) and the exponentials (MUFU, 16 per clk per SM), about 2200 cycles each per block.  Masked: keys >= t (scores), queries >= t (never
-// stored).  Token counts above 320 use attention_kernel (vit_ops.cu, mma.sync).
+// Warp 0 (one elected lane, warp-uniform code) issues the TMA loads and the MMAs between its own softmax work (the stages of a
+// query block run one after the other anyway: S and P of two blocks do not fit TMEM / shared memory at 257 keys); the S MMAs
+// of block i + 1 are issued as soon as every warp holds S(i) in registers and run under the exponentials of block i; Q blocks
+// are double buffered; V has its own mbarrier and lands under the first block's softmax.  A last block of at most AT_FEW real
+// rows (token 257 of a 16 x 16 patch grid) is computed on CUDA cores by all 256 threads, without S / P V MMAs.
+// What bounds it: the latency of the chain S -> max -> exp -> P -> P V -> O inside a block at two warps per scheduler (ncu:
+// XU pipe 20 %, issue slots 26 % busy, a third of the warp samples in mbarrier waits); per block of 128 x 257 about 0.8 us of
+// TMEM read + max, 1.4 us of exponentials and P stores, 0.6 us of P V (operand-read bound), 0.5 us of epilogue -- measured
+// step by step in profiles/r2_vit_attn_steps.txt.  Masked: keys >= t (scores), queries >= t (never stored).  Token counts
+// above 320 use attention_kernel (vit_ops.cu, mma.sync).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -268,8 +273,8 @@ __global__ void __launch_bounds__(256, 1)
     mbar_wait(bar_s, (uint32_t)(qb & 1));
     if (leader) marks.mark(110);
     tc_fence_after();
-    // the scores of this thread's keys are read from TMEM ONCE (TMEM reads run at ~64 B/clk per SM: a second pass over the
-    // 128 x keys fp32 tile would cost as much as all the exponentials) and stay in registers: up to AT_MAX_CH chunks
+    // the scores of this thread's keys are read from TMEM ONCE and stay in registers (up to AT_MAX_CH chunks): a second pass
+    // over the 128 x keys fp32 tile would add another ~0.5 us of TMEM reads per block
     uint32_t v[AT_MAX_CH][32];
     if (warp_live) {
 #pragma unroll
